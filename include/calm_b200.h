@@ -1,0 +1,124 @@
+/*
+ * calm_b200.h -- C ABI of libcalm_b200.so, a B200 (sm_100a) backend for calm's
+ * per-token forward() path.
+ *
+ * The first four functions ARE the reference's CUDA backend boundary: the
+ * reference driver declares exactly these prototypes (reference src/run.c:22-25)
+ * and the reference backend defines them extern "C" (src/infer.cu:69, 73, 743,
+ * 761).  Linking the unmodified reference run.c/tensors.c/tokenizer.c/sampler.c
+ * against this library instead of infer.cu gives a working `run` binary -- see
+ * INTEGRATION.md.  Everything prefixed calm_b200_ is additive.
+ *
+ * Error behaviour follows the reference (infer.cu:12-20, 755): there are no
+ * error codes; a CUDA failure or an unsupported configuration prints one line
+ * to stderr and abort()s.  There is NO CPU fallback: without a usable sm_100
+ * device prepare_cuda() aborts.
+ *
+ * Threading: one host thread, one model per process at a time (the reference
+ * keeps global statics too, infer.cu:40-48).  calm_b200_release() makes the
+ * library reusable for another model in the same process.
+ */
+#ifndef CALM_B200_H
+#define CALM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "calm_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ *
+ * Reference boundary (names, arguments and protocol of the reference) *
+ * ------------------------------------------------------------------ */
+
+/* Copy `size` bytes of a model tensor to the device and return the device
+ * pointer; the caller stores it in struct Weights (run.c:552-560).
+ * Replaces reference infer.cu:69-71 (upload_cuda -> cuda_devicecopy :50-55). */
+void* upload_cuda(void* host, size_t size);
+
+/* One-time set-up after struct Weights holds device pointers: validates the
+ * configuration, allocates activations and the KV cache (honouring
+ * state.kvbits, run.c:534-540), allocates host-visible logits and stores them
+ * in state.logits, builds the per-token launch plan.
+ * Replaces reference infer.cu:73-131. */
+void prepare_cuda(struct Transformer* transformer);
+
+/* Run one token at position `pos`.  Returns a host-readable float[vocab_size]
+ * valid until the next call (the caller may overwrite it, sampler.c:55-66), or
+ * NULL without synchronising when flags & FF_UPDATE_KV_ONLY.
+ * Replaces reference infer.cu:743-759 (forward_cuda -> forward<> :651-741). */
+float* forward_cuda(struct Transformer* transformer, int token, int pos, unsigned flags);
+
+/* Print the per-stage time / bandwidth table gathered so far (only when
+ * profiling was enabled with CALM_B200_PERF=1 or CUDA_INJECTION64_PATH, as in
+ * the reference).  Replaces reference infer.cu:761-801. */
+void perf_cuda(void);
+
+/* ------------------------------------------------------------------ *
+ * Additive entry points                                               *
+ * ------------------------------------------------------------------ */
+
+#define CALM_B200_ABI_VERSION 1
+int calm_b200_abi_version(void);
+
+/* Select the CUDA device used by upload_cuda/prepare_cuda (default: env
+ * CALM_B200_DEVICE, else 0 like reference infer.cu:79).  Call before upload. */
+void calm_b200_set_device(int device);
+
+/* Free a pointer returned by upload_cuda(). */
+void calm_b200_free(void* device_ptr);
+
+/* Free everything prepare_cuda() created for this transformer (the reference
+ * never frees, run.c:636) so another model can be prepared in this process. */
+void calm_b200_release(struct Transformer* transformer);
+
+/* Which engine forward_cuda() uses: 0 = one kernel per stage (CUDA graph),
+ * 1 = persistent fused kernel.  Default from env CALM_B200_ENGINE, else 1.
+ * Must be called before prepare_cuda(). */
+void calm_b200_set_engine(int engine);
+
+/* forward + device-side greedy sample.  Returns argmax(logits) with the
+ * reference's tie rule (lowest index, sampler.c:34-42).  The logits are still
+ * written to state.logits. */
+int calm_b200_forward_argmax(struct Transformer* transformer, int token, int pos);
+
+/* Device-resident greedy decode: feeds token0 at pos0, then n_tokens-1 times the
+ * argmax of the previous step, without a host round trip between tokens.
+ * out_tokens[i] receives the token sampled after step i (n_tokens values).
+ * This is what bench.py times as the in-HBM throughput. */
+void calm_b200_decode_greedy(struct Transformer* transformer, int token0, int pos0, int n_tokens, int* out_tokens);
+
+/* Device timer on the library's stream (CUDA events): start, ..., stop -> ms. */
+void calm_b200_timer_start(void);
+float calm_b200_timer_stop(void);
+
+/* The cudaStream_t all kernels of this library are launched on. */
+void* calm_b200_stream(void);
+
+/* Number of kernels this library has launched since load (bench "gpu_launches"). */
+uint64_t calm_b200_launch_count(void);
+
+/* Read back one KV-cache entry as floats in the reference's logical order
+ * (kv_dim values each, reference infer.c:378-381); for parity tests. */
+void calm_b200_read_kv(struct Transformer* transformer, int layer, int kv_pos, float* k_out, float* v_out);
+
+/* Fill the KV cache positions [0, n_pos) of every layer with a deterministic
+ * pseudo-random pattern (bench: decode at a late position without running the
+ * whole prefix). */
+void calm_b200_fill_kv(struct Transformer* transformer, int n_pos, uint64_t seed);
+
+/* Stand-alone run of the production matvec kernel: y[d] = W[d,n] . x[n] with W
+ * in the `dbits` format at device pointer `w_device`; x and y are HOST arrays.
+ * Returns the kernel's device time in milliseconds (mean over `iters` launches
+ * after `warmup` launches).  Used by the unit parity tests (vs reference
+ * infer.c:209-221) and by the per-kernel roofline bench. */
+float calm_b200_matvec(int dbits, const void* w_device, const float* x_host, float* y_host, int n, int d, int warmup, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CALM_B200_H */
