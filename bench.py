@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- tokens/s of single-batch decode through libcalm_b200.so (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--engine E]
+
+One "step" = one token of single-sequence decode (one pass of the per-token forward() path).  The
+N = 1 workload is BASELINE.json configs[1]: Llama-3-8B shape, random-init fp8 (e5m2) weights, 4096-token
+context, the timed tokens sitting at the END of the context (the reference's own "last tokens" protocol,
+README.md:86) so attention reads the whole KV cache.  Every token streams all 7.5 GB of weights, far more
+than the 126 MB L2, so no L2 flush is needed between steps.
+
+Printed JSON (one line, rank 0):
+  value      tokens/s with everything resident in HBM: device-side greedy loop (forward + argmax feeding
+             the next token, no host round trip), CUDA events on the library's stream, max over ranks.
+  e2e        tokens/s through the reference-facing C ABI with HOST buffers: forward_cuda(token, pos) per
+             token, logits returned in host memory (device->host inside the timed region), greedy pick on
+             the host, next token passed back in.  This is the call a calm user makes (run.c:209).
+  roofline   dominant kernel: algorithmic bytes per launch / mean launch duration vs measured HBM peak.
+  cpu_baseline  the reference's CPU implementation (oracle/_ref, or the oracle port) on this box's cores,
+             bounded sample of the same workload.  Reported, not a target.
+With --impl reference the same metric is measured on the reference's CPU path only (no product code).
+For N > 1 every rank decodes its own sequence on its own GPU (replicas: the 8B model fits one GPU and the
+path has no exchange step at this size); value is the aggregate, "scaling": "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi samples of SM clock / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path, nothing of ours on the path
+
+def host_model(spec, seed):
+    """The workload's model in host memory (generated on the GPU when there is one: 7.5 GB of randn is slow on CPU)."""
+    import torch
+
+    from calm_b200 import modelgen as mg
+
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    t = mg.generate(spec, seed, device=dev)
+    return mg.HostModel(spec, tensors=t, seq_len=4096 if spec.max_seq_len >= 4096 else None)
+
+
+def cpu_tokens_per_s(spec, seed, n_tokens, warmup, pos0, budget_s=None, model=None):
+    """Time the reference CPU forward() (oracle/_ref when it travelled, else the oracle port) on all host
+    threads.  Returns (tok/s, kind, threads, n_timed)."""
+    import oracle
+
+    kind = "reference" if oracle.available("reference") else "port"
+    if kind == "port" and not oracle.available("port"):
+        oracle.build(ref=False)
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))  # reference default is nproc/2 (infer.c:171-176); use all
+    model = model or host_model(spec, seed)
+    ck = oracle.Checker(kind)
+    ck.prepare(model)
+    tok = 17
+    for i in range(warmup):
+        ck.forward(model, tok, pos0 + i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(n_tokens):
+        logits = ck.forward(model, tok, pos0 + warmup + i)
+        tok = int(np.argmax(logits))
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, kind, int(os.environ["OMP_NUM_THREADS"]), done
+
+
+def run_reference_arm(args, spec):
+    rank, world, local = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    pos0 = max(0, 4096 - args.steps - args.warmup)
+    tps, kind, threads, done = cpu_tokens_per_s(spec, args.seed, args.steps, args.warmup, pos0)
+    out = {
+        "impl": "reference", "metric": "tok/s single-batch decode", "value": tps, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / tps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp8 e5m2 weights)",
+        "data": "synthetic", "config": workload_config(spec, pos0, args),
+        "cpu_baseline": {"value": tps, "unit": "tok/s", "cores": threads, "kind": kind,
+                         "sample": f"{done} tokens at pos {pos0 + args.warmup}.. of the same model, all {threads} host threads"},
+        "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(spec, pos0, args):
+    return {"workload": f"{spec.name}: {spec.n_layers} layers, dim {spec.dim}, hidden {spec.hidden_dim}, heads {spec.n_heads}/{spec.n_kv_heads}x{spec.head_dim}, "
+                        f"vocab {spec.vocab_size}, {spec.dtype} weights, fp16 KV cache, context 4096, batch 1",
+            "positions": f"{pos0}..{pos0 + args.steps + args.warmup - 1} (KV cache pre-filled to pos0)", "l2": "inputs (7.5 GB of weights per step) exceed the 126 MB L2; no flush",
+            "parallelism": "replicas" if args.gpus > 1 else "single GPU"}
+
+
+# ------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="llama3-8b-fp8")
+    ap.add_argument("--engine", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--layers", type=int, default=None, help="(debug) override the layer count")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    from dataclasses import replace
+
+    from calm_b200 import modelgen as mg
+
+    spec = mg.SPECS[args.workload]
+    if args.layers:
+        spec = replace(spec, n_layers=args.layers)
+
+    if args.impl == "reference":
+        run_reference_arm(args, spec)
+        return
+
+    import torch
+
+    from calm_b200 import build as cbuild
+    from calm_b200 import lib
+
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if not use_dist:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cbuild.build()
+    L = lib.load()
+    seq_len = 4096
+    tensors = mg.generate(spec, args.seed + rank, device="cuda")
+    torch.cuda.synchronize()
+    dm = lib.DeviceModel(spec, tensors, seq_len=seq_len, device=local, engine=args.engine)
+    K, W = args.steps, args.warmup
+    pos0 = max(0, seq_len - (K + W))
+    dm.fill_kv(min(pos0, seq_len), seed=1 + rank)
+
+    alg_bytes = mg.algorithmic_bytes(spec)
+    kv_b = [mg.kv_bytes(spec, pos0 + W + i, seq_len) for i in range(K)]
+    bytes_per_tok = alg_bytes + float(np.mean(kv_b))
+
+    # ---- leg 1: device-resident greedy decode (inputs resident in HBM)
+    dm.decode_greedy(17, pos0, W)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = L.calm_b200_launch_count()
+    t_wall0 = time.time()
+    L.calm_b200_timer_start()
+    toks = dm.decode_greedy(23, pos0 + W, K)
+    ms = L.calm_b200_timer_stop()
+    barrier()
+    t_wall1 = time.time()
+    launches = int(L.calm_b200_launch_count() - l0)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms = max_over_ranks(ms)
+    value = world * K / (ms / 1e3)
+
+    # ---- leg 2: end to end through forward_cuda with host buffers
+    tok = 23
+    for i in range(W):
+        p = dm.forward_raw(tok, pos0 + i)
+        tok = int(np.argmax(np.ctypeslib.as_array(p, shape=(spec.vocab_size,))))
+    barrier()
+    t0 = time.perf_counter()
+    tok = 23
+    for i in range(K):
+        p = dm.forward_raw(tok, pos0 + W + i)  # host int in -> host float[vocab] out
+        tok = int(np.argmax(np.ctypeslib.as_array(p, shape=(spec.vocab_size,))))
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = world * K / e2e_s
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = measured_peak()
+    roof = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src)
+
+    out = {
+        "metric": "tok/s single-batch decode", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp8 e5m2 weights, f32 accumulate, fp16 KV)" if spec.dtype == "fp8" else f"f32 ({spec.dtype} weights)",
+        "data": "synthetic", "config": workload_config(spec, pos0, args),
+        "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": spec.vocab_size * 4},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "algorithmic_gb_per_token": bytes_per_tok / 1e9, "hbm_gbs_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3),
+        "frac_of_peak_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3) / peak, "engine": os.environ.get("CALM_B200_ENGINE", args.engine),
+    }
+    dm.close()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            hm = mg.HostModel(spec, tensors=tensors, seq_len=seq_len)
+            del tensors
+            tps, kind, threads, done = cpu_tokens_per_s(spec, args.seed, 10 ** 6, 1, seq_len - 64, budget_s=args.cpu_budget, model=hm)
+            out["cpu_baseline"] = {"value": tps, "unit": "tok/s", "cores": threads, "kind": kind,
+                                   "sample": f"{done} tokens at pos {seq_len - 63}.. of the same model ({args.cpu_budget:.0f} s budget), {threads} threads"}
+        except Exception as e:  # the baseline is reported, never required
+            out["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def dm_roofline(dm, L, spec, pos, peak, peak_src):
+    """Dominant kernel = the stage with the largest share of the token's time.  Durations are measured
+    live with CUDA events around every launch on the library's stream (an eager pass of 8 tokens after the
+    timed legs); achieved = that stage's algorithmic bytes per launch (rows x cols x
+    dbits/8) / mean launch duration."""
+    stats = dm.profile(23, pos, 8)
+    total_ms = sum(v[0] for v in stats.values())
+    name, (ms, by, nl) = max(stats.items(), key=lambda kv: kv[1][0])
+    achieved = by / 1e9 / (ms / 1e3) if ms > 0 else None
+    table = {k: {"share": v[0] / total_ms, "us_per_launch": v[0] / max(v[2], 1) * 1e3, "gbs": (v[1] / 1e9 / (v[0] / 1e3)) if v[0] > 0 else None}
+             for k, v in stats.items()}
+    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+            "traffic": None, "peak_source": peak_src, "bytes_per_launch": by / max(nl, 1), "us_per_launch": ms / max(nl, 1) * 1e3, "stages": table}
+
+
+if __name__ == "__main__":
+    main()

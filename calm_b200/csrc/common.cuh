@@ -1,0 +1,255 @@
+// common.cuh -- shared device/host helpers for libcalm_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+// Same failure behaviour as the reference backend (infer.cu:12-20): report and abort.
+#define CUDA_CHECK(x)                                                                                         \
+	do {                                                                                                      \
+		cudaError_t err_ = (x);                                                                               \
+		if (err_ != cudaSuccess) {                                                                            \
+			fprintf(stderr, "calm_b200: CUDA error in %s at %s:%d: %s (%s=%d)\n", __FUNCTION__, __FILE__, \
+			        __LINE__, cudaGetErrorString(err_), cudaGetErrorName(err_), (int)err_);                   \
+			abort();                                                                                          \
+		}                                                                                                     \
+	} while (0)
+
+#define CALM_FATAL(...)                       \
+	do {                                      \
+		fprintf(stderr, "calm_b200: " __VA_ARGS__); \
+		fprintf(stderr, "\n");                \
+		abort();                              \
+	} while (0)
+
+// Per-token scalars.  Lives in device memory so that a captured CUDA graph can
+// be replayed for every token: the host (forward_cuda) or the device
+// (k_advance, greedy decode) rewrites it between replays.
+struct TokenParams {
+	int token;   // input token id
+	int pos;     // absolute position
+	int kv_pos;  // cache slot written this step  (reference infer.c:330-332)
+	int kv_len;  // cache slots attended this step
+	int kv_sink; // 0, or KV_SINKS once the cache rolls over
+	int step;    // index into out_tokens (greedy decode)
+	int seq_len;
+	int pad;
+};
+
+// ---------------------------------------------------------------- warp / block reductions
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+	for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+	return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+	for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+	return v;
+}
+
+// Sum over the whole CTA; every thread gets the result.  `red` is >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+	v = warp_sum(v);
+	__syncthreads(); // protect `red` from a previous use
+	if (lane == 0) red[warp] = v;
+	__syncthreads();
+	float r = lane < nwarps ? red[lane] : 0.f;
+	return warp_sum(r);
+}
+
+// ---------------------------------------------------------------- streaming loads
+
+// 16-byte weight load: read-only path, no L1 allocation (every weight byte is used once per token).
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ uint2 ldg_stream8(const uint2* p) {
+	uint2 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+	return r;
+}
+
+// ---------------------------------------------------------------- weight formats
+//
+// A weight row is consumed in 16-byte vectors.  VW = weights per vector.  The
+// activation vector is staged in shared memory in a layout that makes the
+// matching reads conflict-free 16-byte loads: for vector v = 32*c + lane the
+// VW activations are stored as VW/4 float4 "quads", quad q at float4 index
+// (c*(VW/4) + q)*32 + lane.  xs_index() maps an activation index to that slot.
+
+template <int DBITS>
+struct WFmt;
+template <>
+struct WFmt<16> {
+	static constexpr int VW = 8;
+};
+template <>
+struct WFmt<8> {
+	static constexpr int VW = 16;
+};
+template <>
+struct WFmt<4> {
+	static constexpr int VW = 32;
+};
+
+template <int DBITS>
+__device__ __forceinline__ int xs_index(int j) {
+	constexpr int VW = WFmt<DBITS>::VW, Q = VW / 4;
+	int v = j / VW, w = j % VW;
+	int c = v >> 5, lane = v & 31;
+	return (((c * Q + (w >> 2)) << 5) + lane) * 4 + (w & 3);
+}
+
+// number of floats of the staged activation vector (whole 32-vector chunks, zero padded)
+template <int DBITS>
+__host__ __device__ __forceinline__ int xs_floats(int n) {
+	constexpr int VW = WFmt<DBITS>::VW;
+	int nvec = n / VW;
+	return ((nvec + 31) & ~31) * VW;
+}
+
+// e5m2 pair (two bytes) -> two floats.  An e5m2 byte is the high byte of a half
+// (reference infer.c:28-35, helpers.cuh:65-98), so a byte permute builds the half2.
+__device__ __forceinline__ float2 e5m2x2_lo(uint32_t w) {
+	uint32_t h = __byte_perm(w, 0, 0x1404);
+	return __half22float2(*reinterpret_cast<__half2*>(&h));
+}
+__device__ __forceinline__ float2 e5m2x2_hi(uint32_t w) {
+	uint32_t h = __byte_perm(w, 0, 0x3424);
+	return __half22float2(*reinterpret_cast<__half2*>(&h));
+}
+__device__ __forceinline__ float e5m2_to_float(uint8_t b) {
+	return __half2float(__ushort_as_half((unsigned short)(b << 8)));
+}
+
+// float -> e5m2, round to nearest even, saturating to the largest finite value: the same
+// conversion the reference's KVT(float) = __nv_fp8_e5m2(float) constructor performs (infer.cu:476-481).
+__device__ __forceinline__ uint8_t float_to_e5m2(float f) {
+	return (uint8_t)__nv_cvt_float_to_fp8(f, __NV_SATFINITE, __NV_E5M2);
+}
+
+// Dot of one 16-byte weight vector with its VW activations (already in registers).
+template <int DBITS>
+__device__ __forceinline__ float dot_vec(const uint4& w, const float4 (&xv)[WFmt<DBITS>::VW / 4], float acc);
+
+template <>
+__device__ __forceinline__ float dot_vec<16>(const uint4& w, const float4 (&xv)[2], float acc) {
+	float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+	float2 b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+	float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.z));
+	float2 d = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+	acc = fmaf(a.x, xv[0].x, acc);
+	acc = fmaf(a.y, xv[0].y, acc);
+	acc = fmaf(b.x, xv[0].z, acc);
+	acc = fmaf(b.y, xv[0].w, acc);
+	acc = fmaf(c.x, xv[1].x, acc);
+	acc = fmaf(c.y, xv[1].y, acc);
+	acc = fmaf(d.x, xv[1].z, acc);
+	acc = fmaf(d.y, xv[1].w, acc);
+	return acc;
+}
+
+__device__ __forceinline__ float dot_e5m2x4(uint32_t w, const float4& x, float acc) {
+	float2 lo = e5m2x2_lo(w), hi = e5m2x2_hi(w);
+	acc = fmaf(lo.x, x.x, acc);
+	acc = fmaf(lo.y, x.y, acc);
+	acc = fmaf(hi.x, x.z, acc);
+	acc = fmaf(hi.y, x.w, acc);
+	return acc;
+}
+
+template <>
+__device__ __forceinline__ float dot_vec<8>(const uint4& w, const float4 (&xv)[4], float acc) {
+	acc = dot_e5m2x4(w.x, xv[0], acc);
+	acc = dot_e5m2x4(w.y, xv[1], acc);
+	acc = dot_e5m2x4(w.z, xv[2], acc);
+	acc = dot_e5m2x4(w.w, xv[3], acc);
+	return acc;
+}
+
+// gf4 word: bits 0..7 e5m2 scale s, then eight 3-bit codes; w_k = (q_k - 4) * s / -4
+// (reference infer.c:37-40).  sum_k w_k x_k = (-s/4) * sum_k (q_k - 4) x_k; the integer
+// code is turned into a float with the 2^23 magic (0x4B000000 | q  ==  8388608 + q, exact).
+__device__ __forceinline__ float dot_gf4_word(uint32_t w, const float4& x0, const float4& x1, float acc) {
+	float sf = e5m2_to_float((uint8_t)(w & 0xff)) * -0.25f;
+	const float magic = 8388612.f; // 2^23 + 4
+	float g = 0.f;
+	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 8) & 7)) - magic, x0.x, g);
+	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 11) & 7)) - magic, x0.y, g);
+	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 14) & 7)) - magic, x0.z, g);
+	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 17) & 7)) - magic, x0.w, g);
+	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 20) & 7)) - magic, x1.x, g);
+	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 23) & 7)) - magic, x1.y, g);
+	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 26) & 7)) - magic, x1.z, g);
+	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 29) & 7)) - magic, x1.w, g);
+	return fmaf(sf, g, acc);
+}
+
+template <>
+__device__ __forceinline__ float dot_vec<4>(const uint4& w, const float4 (&xv)[8], float acc) {
+	acc = dot_gf4_word(w.x, xv[0], xv[1], acc);
+	acc = dot_gf4_word(w.y, xv[2], xv[3], acc);
+	acc = dot_gf4_word(w.z, xv[4], xv[5], acc);
+	acc = dot_gf4_word(w.w, xv[6], xv[7], acc);
+	return acc;
+}
+
+// single weight decode (embedding row)
+template <int DBITS>
+__device__ __forceinline__ float weight_at(const void* w, size_t idx);
+template <>
+__device__ __forceinline__ float weight_at<16>(const void* w, size_t idx) {
+	return __half2float(reinterpret_cast<const __half*>(w)[idx]);
+}
+template <>
+__device__ __forceinline__ float weight_at<8>(const void* w, size_t idx) {
+	return e5m2_to_float(reinterpret_cast<const uint8_t*>(w)[idx]);
+}
+template <>
+__device__ __forceinline__ float weight_at<4>(const void* w, size_t idx) {
+	uint32_t word = reinterpret_cast<const uint32_t*>(w)[idx >> 3];
+	float sf = e5m2_to_float((uint8_t)(word & 0xff)) / -4.f;
+	return (float)((int)((word >> (8 + (idx & 7) * 3)) & 7) - 4) * sf;
+}
+
+// ---------------------------------------------------------------- KV cache element access
+
+__device__ __forceinline__ void kv_store(__half* p, float v) {
+	*p = __float2half_rn(v);
+}
+__device__ __forceinline__ void kv_store(uint8_t* p, float v) {
+	*p = float_to_e5m2(v);
+}
+__device__ __forceinline__ float kv_load(const __half* p) {
+	return __half2float(*p);
+}
+__device__ __forceinline__ float kv_load(const uint8_t* p) {
+	return e5m2_to_float(*p);
+}
+
+// 8 consecutive cache elements -> 8 floats
+__device__ __forceinline__ void kv_load8(const __half* p, float (&o)[8]) {
+	uint4 r = *reinterpret_cast<const uint4*>(p);
+	float2 a = __half22float2(*reinterpret_cast<__half2*>(&r.x));
+	float2 b = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+	float2 c = __half22float2(*reinterpret_cast<__half2*>(&r.z));
+	float2 d = __half22float2(*reinterpret_cast<__half2*>(&r.w));
+	o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y, o[4] = c.x, o[5] = c.y, o[6] = d.x, o[7] = d.y;
+}
+__device__ __forceinline__ void kv_load8(const uint8_t* p, float (&o)[8]) {
+	uint2 r = *reinterpret_cast<const uint2*>(p);
+	float2 a = e5m2x2_lo(r.x), b = e5m2x2_hi(r.x), c = e5m2x2_lo(r.y), d = e5m2x2_hi(r.y);
+	o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y, o[4] = c.x, o[5] = c.y, o[6] = d.x, o[7] = d.y;
+}

@@ -1,0 +1,644 @@
+// engine.cu -- host side of libcalm_b200.so: the reference's CUDA backend boundary
+// (upload_cuda / prepare_cuda / forward_cuda / perf_cuda, reference src/run.c:22-25 and
+// src/infer.cu:69-131, 651-801) implemented over the sm_100a kernels in stages.cuh.
+//
+// The per-token kernel sequence is captured once into CUDA graphs and replayed; per-token scalars
+// live in a device-resident TokenParams record that the host (forward_cuda) or the device
+// (greedy decode) rewrites between replays.
+
+#include "../../include/calm_b200.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "stages.cuh"
+
+namespace {
+
+enum Stage { ST_EMBED, ST_QKV, ST_ATTN, ST_WO, ST_FFN_UP, ST_FFN_DOWN, ST_OUTPUT, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"embed", "matmul_qkv", "attention", "matmul_attn", "matmul_ffn_up", "matmul_ffn_down", "output"};
+
+struct Engine {
+	bool ready = false;
+	int device = -1;
+	int sms = 0;
+	cudaStream_t stream = nullptr;
+	struct Config cfg;
+	struct Weights w;
+	int kvbits = 16;
+	int nact = 1;
+	int q_dim = 0, kv_dim = 0, kv_mul = 1;
+
+	// device buffers
+	float *x = nullptr, *xb = nullptr, *q = nullptr, *att = nullptr, *hb = nullptr, *logits_dev = nullptr;
+	float* logits_host = nullptr; // pinned + mapped
+	void *kc = nullptr, *vc = nullptr;
+	float* rope_freq = nullptr;
+	float* attn_partial = nullptr;
+	unsigned* attn_counter = nullptr;
+	MoeSel* moe_sel = nullptr;
+	TokenParams* tp = nullptr;
+	float* cand_val = nullptr;
+	int* cand_idx = nullptr;
+	int* out_tokens = nullptr;
+	int out_tokens_cap = 0;
+	int* last_token = nullptr; // pinned + mapped
+	int ncand = 0;
+
+	// attention launch shape
+	int attn_hg = 1, attn_qgroups = 1, attn_nsplit = 1, attn_lpp = 1;
+
+	// launch plan (grid sizes / dynamic shared memory), fixed at prepare time
+	int grid_qkv = 0, grid_wo = 0, grid_up = 0, grid_down = 0, grid_out = 0;
+	size_t smem_dim = 0, smem_qdim = 0, smem_hidden = 0;
+	int cur_kv_len = 0; // host copy, for the perf table only
+
+	// graphs: 0 = kv only, 1 = logits to host, 2 = logits to device + greedy advance, 3 = logits to host + argmax
+	cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+	int graph_launches[4] = {0, 0, 0, 0};
+	bool use_graph = true;
+
+	// profiling (perf_cuda)
+	bool perf = false;
+	bool debug = false;
+	double stage_ms[ST_COUNT] = {};
+	double stage_bytes[ST_COUNT] = {};
+	long stage_launches[ST_COUNT] = {};
+	int perf_runs = 0;
+	cudaEvent_t ev[2] = {nullptr, nullptr};
+	cudaEvent_t timer[2] = {nullptr, nullptr};
+};
+
+Engine g;
+int g_device_override = -1;
+int g_engine_kind = -1;
+uint64_t g_launches = 0;
+
+void select_device() {
+	if (g.device >= 0) return;
+	int dev = g_device_override;
+	if (dev < 0) {
+		const char* e = getenv("CALM_B200_DEVICE");
+		dev = e ? atoi(e) : 0;
+	}
+	int count = 0;
+	cudaError_t err = cudaGetDeviceCount(&count);
+	if (err != cudaSuccess || count == 0) CALM_FATAL("no CUDA device available (%s); this backend has no CPU fallback", cudaGetErrorString(err));
+	if (dev >= count) CALM_FATAL("device %d requested but only %d present", dev, count);
+	CUDA_CHECK(cudaSetDevice(dev));
+	g.device = dev;
+}
+
+void* dev_alloc(size_t bytes) {
+	void* p = nullptr;
+	CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16));
+	return p;
+}
+
+template <typename F>
+int max_ctas(F kernel, int block, size_t smem) {
+	if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+	if (per_sm < 1) CALM_FATAL("kernel does not fit on an SM (block %d, %zu bytes of shared memory)", block, smem);
+	return per_sm * g.sms;
+}
+
+int imin(int a, int b) { return a < b ? a : b; }
+int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+template <int DBITS>
+size_t xs_bytes(int n) {
+	return (size_t)(32 + xs_floats<DBITS>(n)) * sizeof(float);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one token = this sequence of launches
+
+struct StageTimer {
+	bool on;
+	Stage st;
+	StageTimer(Stage s, double bytes) : on(g.perf), st(s) {
+		if (on) {
+			CUDA_CHECK(cudaEventRecord(g.ev[0], g.stream));
+			g.stage_bytes[st] += bytes;
+		}
+	}
+	~StageTimer() {
+		if (g.debug) { // CALM_B200_DEBUG=1: find the stage that faults or hangs
+			cudaError_t e = cudaStreamSynchronize(g.stream);
+			fprintf(stderr, "calm_b200: stage %s -> %s\n", kStageNames[st], cudaGetErrorName(e));
+		}
+		if (on) {
+			CUDA_CHECK(cudaEventRecord(g.ev[1], g.stream));
+			CUDA_CHECK(cudaEventSynchronize(g.ev[1]));
+			float ms = 0;
+			CUDA_CHECK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+			g.stage_ms[st] += ms;
+			g.stage_launches[st] += 1;
+		}
+	}
+};
+
+template <typename KVT, int HG>
+void launch_attn(const AttnArgs& a, int nunits, int* nl) {
+	size_t smem = (size_t)4 * HG * (a.head_dim + 2) * sizeof(float);
+	k_attn<KVT, HG><<<nunits * a.nsplit, 128, smem, g.stream>>>(a);
+	++*nl;
+}
+
+template <typename KVT>
+void dispatch_attn(const AttnArgs& a, int nunits, int* nl) {
+	switch (g.attn_hg) {
+	case 1: launch_attn<KVT, 1>(a, nunits, nl); break;
+	case 2: launch_attn<KVT, 2>(a, nunits, nl); break;
+	case 3: launch_attn<KVT, 3>(a, nunits, nl); break;
+	case 4: launch_attn<KVT, 4>(a, nunits, nl); break;
+	case 5: launch_attn<KVT, 5>(a, nunits, nl); break;
+	case 6: launch_attn<KVT, 6>(a, nunits, nl); break;
+	case 7: launch_attn<KVT, 7>(a, nunits, nl); break;
+	default: launch_attn<KVT, 8>(a, nunits, nl); break;
+	}
+}
+
+// mode: 0 kv only, 1 logits -> host, 2 logits -> device + advance (greedy loop), 3 logits -> host + argmax
+template <int DBITS, typename KVT>
+int run_token(int mode) {
+	const Config& c = g.cfg;
+	const Weights& w = g.w;
+	const int dim = c.dim, hidden = c.hidden_dim, hd = c.head_dim;
+	const size_t wb = (size_t)DBITS; // bits per weight
+	int nl = 0;
+
+	{
+		StageTimer t(ST_EMBED, 0);
+		EmbedArgs<KVT> a;
+		a.x = g.x, a.table = w.token_embedding_table, a.tp = g.tp, a.dim = dim;
+		a.embed_blocks = cdiv(dim, 256);
+		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq;
+		a.n_layers = c.n_layers, a.n_kv_heads = c.n_kv_heads, a.head_dim = hd, a.seq_len = c.seq_len;
+		k_embed<DBITS, KVT><<<a.embed_blocks + 8, 256, 0, g.stream>>>(a);
+		++nl;
+	}
+
+	const size_t kv_layer = (size_t)c.n_kv_heads * c.seq_len * hd; // elements per layer
+
+	for (int l = 0; l < c.n_layers; ++l) {
+		{
+			StageTimer t(ST_QKV, (double)(g.q_dim + 2 * g.kv_dim) * dim * wb / 8);
+			QkvArgs<KVT> a;
+			a.x = g.x, a.normw = w.rms_att_weight[l], a.wq = w.wq[l], a.wk = w.wk[l], a.wv = w.wv[l], a.bias = w.bqkv[l];
+			a.q_out = g.q, a.kc = (KVT*)g.kc + l * kv_layer, a.vc = (KVT*)g.vc + l * kv_layer;
+			a.rope_freq = g.rope_freq, a.xb_out = c.norm_par ? g.xb : nullptr, a.tp = g.tp;
+			a.dim = dim, a.q_dim = g.q_dim, a.kv_dim = g.kv_dim, a.head_dim = hd, a.seq_len = c.seq_len;
+			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln;
+			k_qkv<DBITS, KVT><<<g.grid_qkv, 256, g.smem_dim, g.stream>>>(a);
+			++nl;
+		}
+		{
+			StageTimer t(ST_ATTN, 2.0 * g.kv_dim * g.cur_kv_len * (g.kvbits / 8));
+			AttnArgs a;
+			a.q = g.q, a.kc = (KVT*)g.kc + l * kv_layer, a.vc = (KVT*)g.vc + l * kv_layer;
+			a.partial = g.attn_partial, a.counter = g.attn_counter, a.out = g.att, a.tp = g.tp;
+			a.head_dim = hd, a.seq_len = c.seq_len, a.nsplit = g.attn_nsplit, a.lpp = g.attn_lpp;
+			a.kv_mul = g.kv_mul, a.qgroups = g.attn_qgroups;
+			a.inv_sqrt_hd = 1.0f / sqrtf((float)hd);
+			dispatch_attn<KVT>(a, c.n_kv_heads * g.attn_qgroups, &nl);
+		}
+		{
+			StageTimer t(ST_WO, (double)dim * g.q_dim * wb / 8);
+			MatResArgs a;
+			a.xin = g.att, a.w = w.wo[l], a.y = g.x, a.sel = nullptr, a.n = g.q_dim, a.d = dim, a.nact = 1, a.accumulate = 1;
+			k_matres<DBITS><<<g.grid_wo, 256, g.smem_qdim, g.stream>>>(a);
+			++nl;
+		}
+		{
+			StageTimer t(ST_FFN_UP, (double)2 * g.nact * hidden * dim * wb / 8);
+			FfnUpArgs a;
+			a.x = (c.norm_par ? g.xb : g.x), a.normw = c.norm_par ? nullptr : w.rms_ffn_weight[l];
+			a.gate = c.n_experts ? w.moegate[l] : nullptr, a.w1 = w.w1[l], a.w3 = w.w3[l], a.hb = g.hb, a.sel = g.moe_sel;
+			a.dim = dim, a.hidden = hidden, a.n_experts = c.n_experts, a.nact = g.nact;
+			a.eps = c.norm_eps, a.ln = c.norm_ln, a.gelu = c.act_gelu;
+			k_ffn_up<DBITS><<<g.grid_up, 256, g.smem_dim, g.stream>>>(a);
+			++nl;
+		}
+		{
+			StageTimer t(ST_FFN_DOWN, (double)g.nact * hidden * dim * wb / 8);
+			MatResArgs a;
+			a.xin = g.hb, a.w = w.w2[l], a.y = g.x, a.sel = c.n_experts ? g.moe_sel : nullptr;
+			a.n = hidden, a.d = dim, a.nact = g.nact, a.accumulate = 1;
+			k_matres<DBITS><<<g.grid_down, 256, g.smem_hidden, g.stream>>>(a);
+			++nl;
+		}
+	}
+
+	if (mode == 0) return nl;
+
+	{
+		StageTimer t(ST_OUTPUT, (double)c.vocab_size * dim * wb / 8);
+		OutputArgs a;
+		a.x = g.x, a.normw = w.rms_final_weight, a.wcls = w.wcls;
+		a.logits = (mode == 2) ? g.logits_dev : g.logits_host;
+		a.cand_val = (mode >= 2) ? g.cand_val : nullptr, a.cand_idx = g.cand_idx;
+		a.dim = dim, a.vocab = c.vocab_size, a.eps = c.norm_eps, a.ln = c.norm_ln;
+		int grid = g.grid_out;
+		k_output<DBITS><<<grid, 256, g.smem_dim, g.stream>>>(a);
+		++nl;
+		if (mode >= 2) {
+			k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, grid, g.tp, g.out_tokens, g.last_token, mode == 2);
+			++nl;
+		}
+	}
+	return nl;
+}
+
+// Fix grid sizes and shared-memory opt-ins for this model (called once from prepare_cuda).
+template <int DBITS, typename KVT>
+void make_plan() {
+	const Config& c = g.cfg;
+	g.smem_dim = xs_bytes<DBITS>(c.dim);
+	g.smem_qdim = xs_bytes<DBITS>(g.q_dim);
+	g.smem_hidden = xs_bytes<DBITS>(c.hidden_dim);
+	size_t smem_res = g.smem_qdim > g.smem_hidden ? g.smem_qdim : g.smem_hidden;
+	if (smem_res > 227 * 1024 || g.smem_dim > 227 * 1024) CALM_FATAL("activation vector does not fit in shared memory (dim %d, hidden %d)", c.dim, c.hidden_dim);
+	g.grid_qkv = imin(max_ctas(k_qkv<DBITS, KVT>, 256, g.smem_dim), cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8));
+	max_ctas(k_matres<DBITS>, 256, smem_res); // opt in to the larger of the two sizes
+	g.grid_wo = imin(max_ctas(k_matres<DBITS>, 256, g.smem_qdim), cdiv(c.dim / 2, 8));
+	g.grid_down = imin(max_ctas(k_matres<DBITS>, 256, g.smem_hidden), cdiv(c.dim / 2, 8));
+	g.grid_up = imin(max_ctas(k_ffn_up<DBITS>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
+	g.grid_out = imin(max_ctas(k_output<DBITS>, 256, g.smem_dim), cdiv(c.vocab_size, 32));
+	g.ncand = g.grid_out;
+}
+
+template <int DBITS>
+void make_plan_kv() {
+	if (g.kvbits == 8)
+		make_plan<DBITS, uint8_t>();
+	else
+		make_plan<DBITS, __half>();
+}
+
+template <int DBITS>
+int run_token_kv(int mode) {
+	return g.kvbits == 8 ? run_token<DBITS, uint8_t>(mode) : run_token<DBITS, __half>(mode);
+}
+
+int run_token_any(int mode) {
+	switch (g.w.dbits) {
+	case 16: return run_token_kv<16>(mode);
+	case 8: return run_token_kv<8>(mode);
+	default: return run_token_kv<4>(mode);
+	}
+}
+
+void launch_token(int mode) {
+	if (!g.use_graph || g.perf) {
+		g_launches += run_token_any(mode);
+		CUDA_CHECK(cudaGetLastError());
+		return;
+	}
+	if (!g.graph[mode]) {
+		cudaGraph_t graph;
+		CUDA_CHECK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+		g.graph_launches[mode] = run_token_any(mode);
+		CUDA_CHECK(cudaStreamEndCapture(g.stream, &graph));
+		CUDA_CHECK(cudaGraphInstantiate(&g.graph[mode], graph, 0));
+		CUDA_CHECK(cudaGraphDestroy(graph));
+	}
+	CUDA_CHECK(cudaGraphLaunch(g.graph[mode], g.stream));
+	g_launches += g.graph_launches[mode];
+}
+
+void set_params(int token, int pos, int step) {
+	g.cur_kv_len = pos >= g.cfg.seq_len ? g.cfg.seq_len : pos + 1;
+	k_set_params<<<1, 1, 0, g.stream>>>(g.tp, token, pos, g.cfg.seq_len, step);
+	++g_launches;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+
+extern "C" int calm_b200_abi_version(void) {
+	return CALM_B200_ABI_VERSION;
+}
+
+extern "C" void calm_b200_set_device(int device) {
+	g_device_override = device;
+}
+
+extern "C" void calm_b200_set_engine(int engine) {
+	g_engine_kind = engine;
+}
+
+extern "C" void* upload_cuda(void* host, size_t size) {
+	select_device();
+	void* dev = dev_alloc(size);
+	CUDA_CHECK(cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice));
+	return dev;
+}
+
+extern "C" void calm_b200_free(void* device_ptr) {
+	if (device_ptr) CUDA_CHECK(cudaFree(device_ptr));
+}
+
+extern "C" void prepare_cuda(struct Transformer* transformer) {
+	select_device();
+	if (g.ready) CALM_FATAL("prepare_cuda called twice; call calm_b200_release() first (one model per process, as in the reference)");
+
+	const Config& c = transformer->config;
+	const Weights& w = transformer->weights;
+	RunState* s = &transformer->state;
+
+	cudaDeviceProp prop;
+	CUDA_CHECK(cudaGetDeviceProperties(&prop, g.device));
+	if (prop.major != 10) CALM_FATAL("device %s is sm_%d%d; this library contains sm_100a code only and has no fallback", prop.name, prop.major, prop.minor);
+	g.sms = prop.multiProcessorCount;
+	if (!getenv("CALM_B200_QUIET"))
+		printf("# CUDA: %s, compute %d.%d, %d SMs, %.1f GiB, peak bandwidth %.0f GB/s (ECC %d)\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
+		       (double)prop.totalGlobalMem / (1024 * 1024 * 1024), (double)prop.memoryClockRate * (prop.memoryBusWidth / 8) * 2 / 1e6, prop.ECCEnabled);
+
+	// configuration checks (the reference asserts the same alignment, infer.cu:670, 755)
+	if (w.dbits != 4 && w.dbits != 8 && w.dbits != 16) CALM_FATAL("unsupported dbits %d: must be 4, 8 or 16", w.dbits);
+	if (s->kvbits != 8 && s->kvbits != 16) CALM_FATAL("unsupported kvbits %d: must be 8 or 16", s->kvbits);
+	int q_dim = c.head_dim * c.n_heads, kv_dim = c.head_dim * c.n_kv_heads;
+	if (c.dim % 32 || kv_dim % 32 || c.hidden_dim % 32 || q_dim % 32) CALM_FATAL("dim, q_dim, kv_dim and hidden_dim must be multiples of 32");
+	if (c.head_dim % 8 || c.head_dim > 256) CALM_FATAL("head_dim %d unsupported (multiple of 8, <= 256)", c.head_dim);
+	if (c.n_heads % c.n_kv_heads) CALM_FATAL("n_heads must be a multiple of n_kv_heads");
+	if (c.n_layers > MAX_LAYERS) CALM_FATAL("too many layers");
+	if (c.n_experts > MAX_EXPERTS || c.n_experts_ac > CALM_MAX_ACTIVE) CALM_FATAL("too many experts (%d, %d active)", c.n_experts, c.n_experts_ac);
+	if (c.seq_len <= KV_SINKS) CALM_FATAL("seq_len too small");
+
+	g.cfg = c;
+	g.w = w;
+	g.kvbits = s->kvbits;
+	g.nact = c.n_experts ? c.n_experts_ac : 1;
+	g.q_dim = q_dim, g.kv_dim = kv_dim, g.kv_mul = c.n_heads / c.n_kv_heads;
+	g.use_graph = !(getenv("CALM_B200_GRAPH") && atoi(getenv("CALM_B200_GRAPH")) == 0);
+	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
+	if (g.debug) g.use_graph = false;
+	g.perf = (getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF"))) || getenv("CUDA_INJECTION64_PATH");
+
+	CUDA_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i) {
+		CUDA_CHECK(cudaEventCreate(&g.ev[i]));
+		CUDA_CHECK(cudaEventCreate(&g.timer[i]));
+	}
+
+	g.x = (float*)dev_alloc(c.dim * sizeof(float));
+	g.xb = (float*)dev_alloc(c.dim * sizeof(float));
+	g.q = (float*)dev_alloc(q_dim * sizeof(float));
+	g.att = (float*)dev_alloc(q_dim * sizeof(float));
+	g.hb = (float*)dev_alloc((size_t)g.nact * c.hidden_dim * sizeof(float));
+	g.logits_dev = (float*)dev_alloc((size_t)c.vocab_size * sizeof(float));
+	CUDA_CHECK(cudaHostAlloc((void**)&g.logits_host, (size_t)c.vocab_size * sizeof(float), cudaHostAllocMapped));
+	CUDA_CHECK(cudaHostAlloc((void**)&g.last_token, sizeof(int), cudaHostAllocMapped));
+	memset(g.logits_host, 0, (size_t)c.vocab_size * sizeof(float));
+
+	size_t kvbytes = (size_t)c.n_layers * c.seq_len * kv_dim * (g.kvbits / 8);
+	g.kc = dev_alloc(kvbytes);
+	g.vc = dev_alloc(kvbytes);
+	CUDA_CHECK(cudaMemsetAsync(g.kc, 0, kvbytes, g.stream));
+	CUDA_CHECK(cudaMemsetAsync(g.vc, 0, kvbytes, g.stream));
+
+	// RoPE frequencies with the host libm, exactly as the CPU reference forms them (infer.c:225-226)
+	std::vector<float> freq(c.head_dim / 2);
+	for (int i = 0; i < c.head_dim; i += 2) freq[i / 2] = i >= c.rotary_dim ? 0.f : 1.0f / powf(c.rope_theta, (float)i / (float)c.rotary_dim);
+	g.rope_freq = (float*)dev_alloc(freq.size() * sizeof(float));
+	CUDA_CHECK(cudaMemcpyAsync(g.rope_freq, freq.data(), freq.size() * sizeof(float), cudaMemcpyHostToDevice, g.stream));
+	CUDA_CHECK(cudaStreamSynchronize(g.stream)); // freq is a local
+
+	// attention shape: query-head group per CTA (largest divisor of kv_mul <= 8), lanes per position, slices
+	g.attn_hg = 1;
+	for (int h = 8; h >= 1; --h)
+		if (g.kv_mul % h == 0) {
+			g.attn_hg = h;
+			break;
+		}
+	g.attn_qgroups = g.kv_mul / g.attn_hg;
+	g.attn_lpp = 1;
+	while (g.attn_lpp * 8 < c.head_dim) g.attn_lpp *= 2;
+	int units = c.n_kv_heads * g.attn_qgroups;
+	int want = cdiv(2 * g.sms, units);                  // ~2 CTAs per SM
+	int maxsplit = cdiv(c.seq_len, 64);                 // at least 64 positions per slice at full context
+	g.attn_nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
+	g.attn_partial = (float*)dev_alloc((size_t)units * g.attn_nsplit * g.attn_hg * (c.head_dim + 2) * sizeof(float));
+	g.attn_counter = (unsigned*)dev_alloc(units * sizeof(unsigned));
+	CUDA_CHECK(cudaMemset(g.attn_counter, 0, units * sizeof(unsigned)));
+
+	g.moe_sel = (MoeSel*)dev_alloc(sizeof(MoeSel));
+	CUDA_CHECK(cudaMemset(g.moe_sel, 0, sizeof(MoeSel)));
+	g.tp = (TokenParams*)dev_alloc(sizeof(TokenParams));
+	CUDA_CHECK(cudaMemset(g.tp, 0, sizeof(TokenParams)));
+
+	switch (w.dbits) {
+	case 16: make_plan_kv<16>(); break;
+	case 8: make_plan_kv<8>(); break;
+	default: make_plan_kv<4>(); break;
+	}
+	g.cand_val = (float*)dev_alloc(g.ncand * sizeof(float));
+	g.cand_idx = (int*)dev_alloc(g.ncand * sizeof(int));
+	g.out_tokens_cap = 1 << 16;
+	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
+
+	// what the reference backend publishes in RunState (infer.cu:99-112)
+	s->x = g.x, s->hb = g.hb, s->he = g.hb, s->q = g.q, s->att = g.att;
+	s->key_cache = g.kc, s->value_cache = g.vc;
+	s->logits = g.logits_host;
+
+	g.ready = true;
+	CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+extern "C" void calm_b200_release(struct Transformer* transformer) {
+	if (!g.ready) return;
+	CUDA_CHECK(cudaDeviceSynchronize());
+	for (int i = 0; i < 4; ++i)
+		if (g.graph[i]) CUDA_CHECK(cudaGraphExecDestroy(g.graph[i]));
+	cudaFree(g.x), cudaFree(g.xb), cudaFree(g.q), cudaFree(g.att), cudaFree(g.hb), cudaFree(g.logits_dev);
+	cudaFreeHost(g.logits_host), cudaFreeHost(g.last_token);
+	cudaFree(g.kc), cudaFree(g.vc), cudaFree(g.rope_freq), cudaFree(g.attn_partial), cudaFree(g.attn_counter);
+	cudaFree(g.moe_sel), cudaFree(g.tp), cudaFree(g.cand_val), cudaFree(g.cand_idx), cudaFree(g.out_tokens);
+	for (int i = 0; i < 2; ++i) cudaEventDestroy(g.ev[i]), cudaEventDestroy(g.timer[i]);
+	cudaStreamDestroy(g.stream);
+	int dev = g.device;
+	g = Engine();
+	g.device = dev;
+	if (transformer) {
+		int kvbits = transformer->state.kvbits;
+		memset(&transformer->state, 0, sizeof(transformer->state));
+		transformer->state.kvbits = kvbits;
+	}
+}
+
+static void check_call(struct Transformer* transformer, int token, int pos) {
+	if (!g.ready) CALM_FATAL("forward before prepare_cuda");
+	(void)transformer;
+	if (token < 0 || token >= g.cfg.vocab_size) CALM_FATAL("token %d out of range", token);
+	if (pos < 0) CALM_FATAL("negative position");
+}
+
+extern "C" float* forward_cuda(struct Transformer* transformer, int token, int pos, unsigned flags) {
+	check_call(transformer, token, pos);
+	set_params(token, pos, 0);
+	if (flags & FF_UPDATE_KV_ONLY) {
+		launch_token(0);
+		return NULL; // no synchronisation: prompt tokens pipeline (reference infer.cu:724-727)
+	}
+	launch_token(1);
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	CUDA_CHECK(cudaGetLastError());
+	if (g.perf) ++g.perf_runs;
+	return g.logits_host;
+}
+
+extern "C" int calm_b200_forward_argmax(struct Transformer* transformer, int token, int pos) {
+	check_call(transformer, token, pos);
+	set_params(token, pos, 0);
+	launch_token(3);
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	return *(volatile int*)g.last_token;
+}
+
+extern "C" void calm_b200_decode_greedy(struct Transformer* transformer, int token0, int pos0, int n_tokens, int* out_tokens) {
+	check_call(transformer, token0, pos0);
+	if (n_tokens > g.out_tokens_cap) CALM_FATAL("decode_greedy: at most %d tokens per call", g.out_tokens_cap);
+	set_params(token0, pos0, 0);
+	for (int i = 0; i < n_tokens; ++i) launch_token(2);
+	CUDA_CHECK(cudaMemcpyAsync(out_tokens, g.out_tokens, n_tokens * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+}
+
+extern "C" void calm_b200_timer_start(void) {
+	CUDA_CHECK(cudaEventRecord(g.timer[0], g.stream));
+}
+
+extern "C" float calm_b200_timer_stop(void) {
+	CUDA_CHECK(cudaEventRecord(g.timer[1], g.stream));
+	CUDA_CHECK(cudaEventSynchronize(g.timer[1]));
+	float ms = 0;
+	CUDA_CHECK(cudaEventElapsedTime(&ms, g.timer[0], g.timer[1]));
+	return ms;
+}
+
+extern "C" void* calm_b200_stream(void) {
+	return (void*)g.stream;
+}
+
+extern "C" uint64_t calm_b200_launch_count(void) {
+	return g_launches;
+}
+
+extern "C" void calm_b200_read_kv(struct Transformer* transformer, int layer, int kv_pos, float* k_out, float* v_out) {
+	(void)transformer;
+	const Config& c = g.cfg;
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	size_t es = g.kvbits / 8;
+	std::vector<unsigned char> kb(c.head_dim * es), vb(c.head_dim * es);
+	for (int h = 0; h < c.n_kv_heads; ++h) {
+		size_t off = (((size_t)layer * c.n_kv_heads + h) * c.seq_len + kv_pos) * c.head_dim * es;
+		CUDA_CHECK(cudaMemcpy(kb.data(), (char*)g.kc + off, kb.size(), cudaMemcpyDeviceToHost));
+		CUDA_CHECK(cudaMemcpy(vb.data(), (char*)g.vc + off, vb.size(), cudaMemcpyDeviceToHost));
+		for (int d = 0; d < c.head_dim; ++d) {
+			float kf, vf;
+			if (es == 2) {
+				kf = __half2float(((__half*)kb.data())[d]);
+				vf = __half2float(((__half*)vb.data())[d]);
+			} else {
+				kf = __half2float(__ushort_as_half((unsigned short)(kb[d] << 8)));
+				vf = __half2float(__ushort_as_half((unsigned short)(vb[d] << 8)));
+			}
+			k_out[h * c.head_dim + d] = kf;
+			v_out[h * c.head_dim + d] = vf;
+		}
+	}
+}
+
+extern "C" void calm_b200_fill_kv(struct Transformer* transformer, int n_pos, uint64_t seed) {
+	(void)transformer;
+	const Config& c = g.cfg;
+	size_t lh = (size_t)c.n_layers * c.n_kv_heads;
+	if (n_pos > c.seq_len) n_pos = c.seq_len;
+	if (g.kvbits == 8)
+		k_fill_kv<uint8_t><<<g.sms * 4, 256, 0, g.stream>>>((uint8_t*)g.kc, (uint8_t*)g.vc, lh, c.seq_len, c.head_dim, n_pos, seed);
+	else
+		k_fill_kv<__half><<<g.sms * 4, 256, 0, g.stream>>>((__half*)g.kc, (__half*)g.vc, lh, c.seq_len, c.head_dim, n_pos, seed);
+	++g_launches;
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+}
+
+template <int DBITS>
+static float matvec_impl(const void* w_device, const float* x_host, float* y_host, int n, int d, int warmup, int iters) {
+	cudaStream_t st;
+	CUDA_CHECK(cudaStreamCreate(&st));
+	float *x, *y;
+	CUDA_CHECK(cudaMalloc(&x, n * sizeof(float)));
+	CUDA_CHECK(cudaMalloc(&y, d * sizeof(float)));
+	CUDA_CHECK(cudaMemcpy(x, x_host, n * sizeof(float), cudaMemcpyHostToDevice));
+	cudaDeviceProp prop;
+	CUDA_CHECK(cudaGetDeviceProperties(&prop, g.device));
+	g.sms = prop.multiProcessorCount;
+	size_t smem = xs_bytes<DBITS>(n);
+	int cap = max_ctas(k_matvec<DBITS>, 256, smem);
+	int grid = imin(cap, cdiv((d + 1) / 2, 8));
+	MatvecArgs a{x, w_device, y, n, d};
+	cudaEvent_t e0, e1;
+	CUDA_CHECK(cudaEventCreate(&e0));
+	CUDA_CHECK(cudaEventCreate(&e1));
+	for (int i = 0; i < warmup; ++i) k_matvec<DBITS><<<grid, 256, smem, st>>>(a);
+	CUDA_CHECK(cudaEventRecord(e0, st));
+	for (int i = 0; i < iters; ++i) k_matvec<DBITS><<<grid, 256, smem, st>>>(a);
+	CUDA_CHECK(cudaEventRecord(e1, st));
+	CUDA_CHECK(cudaEventSynchronize(e1));
+	CUDA_CHECK(cudaGetLastError());
+	g_launches += warmup + iters;
+	float ms = 0;
+	CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+	CUDA_CHECK(cudaMemcpy(y_host, y, d * sizeof(float), cudaMemcpyDeviceToHost));
+	cudaFree(x), cudaFree(y), cudaEventDestroy(e0), cudaEventDestroy(e1), cudaStreamDestroy(st);
+	return iters > 0 ? ms / iters : 0.f;
+}
+
+extern "C" float calm_b200_matvec(int dbits, const void* w_device, const float* x_host, float* y_host, int n, int d, int warmup, int iters) {
+	select_device();
+	if (n % 32) CALM_FATAL("matvec: n must be a multiple of 32");
+	switch (dbits) {
+	case 16: return matvec_impl<16>(w_device, x_host, y_host, n, d, warmup, iters);
+	case 8: return matvec_impl<8>(w_device, x_host, y_host, n, d, warmup, iters);
+	case 4: return matvec_impl<4>(w_device, x_host, y_host, n, d, warmup, iters);
+	}
+	CALM_FATAL("matvec: unsupported dbits %d", dbits);
+	return 0.f;
+}
+
+extern "C" void calm_b200_set_perf(int on) {
+	g.perf = on != 0;
+	if (!on) return;
+	for (int i = 0; i < ST_COUNT; ++i) g.stage_ms[i] = 0, g.stage_bytes[i] = 0, g.stage_launches[i] = 0;
+	g.perf_runs = 0;
+}
+
+extern "C" int calm_b200_stage_stats(int stage, char* name, int name_cap, double* ms_total, double* bytes_total, long* launches) {
+	if (stage < 0 || stage >= ST_COUNT) return 0;
+	if (name && name_cap > 0) {
+		strncpy(name, kStageNames[stage], name_cap - 1);
+		name[name_cap - 1] = 0;
+	}
+	*ms_total = g.stage_ms[stage], *bytes_total = g.stage_bytes[stage], *launches = g.stage_launches[stage];
+	return 1;
+}
+
+extern "C" void perf_cuda(void) {
+	if (!g.ready || !g.perf || g.perf_runs == 0) return;
+	double total = 0;
+	for (int i = 0; i < ST_COUNT; ++i) total += g.stage_ms[i];
+	printf("\nforward breakdown (over %d runs, avg %.1f usec/run):\n", g.perf_runs, total / g.perf_runs * 1e3);
+	for (int i = 0; i < ST_COUNT; ++i) {
+		if (g.stage_ms[i] == 0) continue;
+		printf("\t[%d] %16s: %4.1f%%; %8.1f usec/run, %6.1f GB/s\n", i, kStageNames[i], g.stage_ms[i] / total * 100, g.stage_ms[i] / g.perf_runs * 1e3,
+		       g.stage_bytes[i] / 1e9 / (g.stage_ms[i] / 1e3));
+	}
+}

@@ -247,10 +247,10 @@ def metadata(spec: ModelSpec) -> Dict[str, str]:
 
 
 def synthetic_tokenizer(spec: ModelSpec):
-    """tokenizer.tokens / tokenizer.scores tensors: pieces "<t%d>" so that every id
-    decodes to something printable and `<t5>` round-trips through the reference's
-    special-token path (tokenizer.c:203-269)."""
-    pieces = b"".join(b"<t%d>\0" % i for i in range(spec.vocab_size))
+    """tokenizer.tokens / tokenizer.scores tensors: pieces "<|t%d|>" so that every id
+    decodes to something printable and `<|t5|>` round-trips through the reference's
+    special-token path (tokenizer.c:219-240)."""
+    pieces = b"".join(b"<|t%d|>\0" % i for i in range(spec.vocab_size))
     return {
         "tokenizer.tokens": torch.frombuffer(bytearray(pieces), dtype=torch.uint8),
         "tokenizer.scores": torch.zeros(spec.vocab_size, dtype=torch.float32),

@@ -110,6 +110,14 @@ void calm_b200_read_kv(struct Transformer* transformer, int layer, int kv_pos, f
  * whole prefix). */
 void calm_b200_fill_kv(struct Transformer* transformer, int n_pos, uint64_t seed);
 
+/* Per-stage profiling at run time (what CALM_B200_PERF=1 enables from the start): while on, every
+ * stage is launched eagerly and bracketed by CUDA events on the library's stream.  set_perf(1) also
+ * clears the counters.  stage_stats() returns 0 past the last stage; totals are over all launches of
+ * that stage since set_perf(1): milliseconds, algorithmic bytes (the reference's per-stage accounting,
+ * infer.cu:683-699) and launch count. */
+void calm_b200_set_perf(int on);
+int calm_b200_stage_stats(int stage, char* name, int name_cap, double* ms_total, double* bytes_total, long* launches);
+
 /* Stand-alone run of the production matvec kernel: y[d] = W[d,n] . x[n] with W
  * in the `dbits` format at device pointer `w_device`; x and y are HOST arrays.
  * Returns the kernel's device time in milliseconds (mean over `iters` launches
