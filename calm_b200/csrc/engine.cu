@@ -13,6 +13,7 @@
 
 #include <vector>
 
+#include "fused.cuh"
 #include "stages.cuh"
 
 namespace {
@@ -54,6 +55,22 @@ struct Engine {
 	int grid_qkv = 0, grid_wo = 0, grid_up = 0, grid_down = 0, grid_out = 0;
 	size_t smem_dim = 0, smem_qdim = 0, smem_hidden = 0;
 	int cur_kv_len = 0; // host copy, for the perf table only
+	int cur_pos = 0;
+	int engine = 1;
+	bool debug_stages = false;
+	int attn_nsplit_cap = 1 << 30;
+
+	// fused engine (engine kind 1)
+	bool fused_ok = false;   // model/configuration is served by the persistent kernel
+	bool fused_attr_set = false;
+	int fused_xr = 64;
+	int fused_slot_bytes = 0, fused_nslots = 0, fused_scratch = 0;
+	size_t fused_smem = 0;
+	int fused_nsplit = 1;
+	unsigned* fused_bar = nullptr;
+	int* fused_err = nullptr; // pinned + mapped
+	cudaGraphExec_t fgraph[4] = {nullptr, nullptr, nullptr, nullptr};
+	int fgraph_launches[4] = {0, 0, 0, 0};
 
 	// graphs: 0 = kv only, 1 = logits to host, 2 = logits to device + greedy advance, 3 = logits to host + argmax
 	cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -293,7 +310,144 @@ int run_token_any(int mode) {
 	}
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fused engine: plan + launch
+
+template <int DBITS, int XR>
+void fused_launch_t(const FusedArgs& fa) {
+	if (!g.fused_attr_set) { // per model (the ring size depends on the shapes); first call comes from fused_plan()
+		CUDA_CHECK(cudaFuncSetAttribute(k_fused<DBITS, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.fused_smem));
+		g.fused_attr_set = true;
+		if (fa.dim == 0) return; // attribute-only call
+	}
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(g.sms), cfg.blockDim = dim3(FUSED_THREADS), cfg.dynamicSmemBytes = g.fused_smem, cfg.stream = g.stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeCooperative;
+	at[0].val.cooperative = 1;
+	cfg.attrs = at, cfg.numAttrs = 1;
+	CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_fused<DBITS, XR>, fa));
+}
+
+void fused_launch(const FusedArgs& fa) {
+	const int key = g.w.dbits * 1000 + g.fused_xr;
+	switch (key) {
+	case 8064: fused_launch_t<8, 64>(fa); break;
+	case 8128: fused_launch_t<8, 128>(fa); break;
+	case 16064: fused_launch_t<16, 64>(fa); break;
+	case 16128: fused_launch_t<16, 128>(fa); break;
+	case 4064: fused_launch_t<4, 64>(fa); break;
+	case 4128: fused_launch_t<4, 128>(fa); break;
+	default: CALM_FATAL("fused engine: no kernel for dbits %d / xr %d", g.w.dbits, g.fused_xr);
+	}
+}
+
+// Decide whether the persistent kernel can serve this model and size its ring.
+void fused_plan() {
+	const Config& c = g.cfg;
+	g.fused_ok = false;
+	if (c.n_experts || g.kvbits != 16) return; // MoE and fp8 KV: staged engine
+	const int vw = g.w.dbits == 16 ? 8 : (g.w.dbits == 8 ? 16 : 32);
+	int nvmax = (c.hidden_dim > g.q_dim ? c.hidden_dim : g.q_dim);
+	if (c.dim > nvmax) nvmax = c.dim;
+	nvmax /= vw;
+	int need_it = cdiv(nvmax, FUSED_NCW * 32);
+	if (need_it <= 64 / vw)
+		g.fused_xr = 64;
+	else if (need_it <= 128 / vw)
+		g.fused_xr = 128;
+	else
+		return;
+	// slot: must hold the smallest legal tile of every stage; prefer 32 KB
+	size_t rb_dim = (size_t)c.dim * g.w.dbits / 8, rb_q = (size_t)g.q_dim * g.w.dbits / 8, rb_hid = (size_t)c.hidden_dim * g.w.dbits / 8;
+	size_t need = 2 * rb_dim;
+	if (rb_q > need) need = rb_q;
+	if (rb_hid > need) need = rb_hid;
+	if ((size_t)4 * c.head_dim > need) need = (size_t)4 * c.head_dim;
+	size_t slot = 32 * 1024;
+	if (need > slot) slot = (need + 1023) & ~(size_t)1023;
+	g.fused_scratch = (int)(((size_t)FUSED_NCW * g.attn_hg * (c.head_dim + 2) * sizeof(float) + 127) & ~(size_t)127);
+	size_t fixed = ((sizeof(FusedShared) + 127) & ~(size_t)127) + g.fused_scratch;
+	size_t avail = 227 * 1024 - fixed;
+	int nslots = (int)(avail / slot);
+	if (nslots > FUSED_MAX_SLOTS) nslots = FUSED_MAX_SLOTS;
+	if (nslots < 2) return;
+	g.fused_slot_bytes = (int)slot, g.fused_nslots = nslots;
+	g.fused_smem = fixed + (size_t)nslots * slot;
+	int units = c.n_kv_heads * g.attn_qgroups;
+	g.fused_nsplit = g.sms / units;
+	if (g.fused_nsplit < 1) return; // more (kv head, query group) units than SMs: staged engine
+	int maxsplit = cdiv(c.seq_len, 16);
+	if (g.fused_nsplit > maxsplit) g.fused_nsplit = maxsplit;
+	if (g.fused_nsplit > g.attn_nsplit_cap) g.fused_nsplit = g.attn_nsplit_cap;
+
+	FusedLayer layers[MAX_LAYERS] = {};
+	for (int l = 0; l < c.n_layers; ++l) {
+		layers[l].wq = g.w.wq[l], layers[l].wk = g.w.wk[l], layers[l].wv = g.w.wv[l], layers[l].wo = g.w.wo[l];
+		layers[l].w1 = g.w.w1[l], layers[l].w2 = g.w.w2[l], layers[l].w3 = g.w.w3[l];
+		layers[l].rms_att = g.w.rms_att_weight[l], layers[l].rms_ffn = g.w.rms_ffn_weight[l], layers[l].bqkv = g.w.bqkv[l];
+	}
+	CUDA_CHECK(cudaMemcpyToSymbol(c_fused_layers, layers, sizeof(layers)));
+	g.fused_bar = (unsigned*)dev_alloc(sizeof(unsigned));
+	CUDA_CHECK(cudaMemset(g.fused_bar, 0, sizeof(unsigned)));
+	CUDA_CHECK(cudaHostAlloc((void**)&g.fused_err, sizeof(int), cudaHostAllocMapped));
+	*g.fused_err = 0;
+	g.fused_attr_set = false;
+	FusedArgs none = {};
+	fused_launch(none); // sets the shared-memory opt-in outside of any stream capture
+	g.fused_ok = true;
+}
+
+int run_token_fused(int mode) {
+	const Config& c = g.cfg;
+	FusedArgs fa = {};
+	fa.dim = c.dim, fa.hidden = c.hidden_dim, fa.q_dim = g.q_dim, fa.kv_dim = g.kv_dim, fa.head_dim = c.head_dim;
+	fa.n_heads = c.n_heads, fa.n_kv_heads = c.n_kv_heads, fa.n_layers = c.n_layers, fa.vocab = c.vocab_size, fa.seq_len = c.seq_len, fa.kv_mul = g.kv_mul;
+	fa.eps = c.norm_eps, fa.clip = c.qkv_clip, fa.ln = c.norm_ln, fa.norm_par = c.norm_par, fa.gelu = c.act_gelu;
+	fa.x = g.x, fa.xb = g.xb, fa.q = g.q, fa.att = g.att, fa.hb = g.hb;
+	fa.logits = (mode == 2) ? g.logits_dev : g.logits_host;
+	fa.attn_partial = g.attn_partial, fa.attn_counter = g.attn_counter;
+	fa.kc = (__half*)g.kc, fa.vc = (__half*)g.vc, fa.rope_freq = g.rope_freq;
+	fa.embed = g.w.token_embedding_table, fa.wcls = g.w.wcls, fa.rms_final = g.w.rms_final_weight;
+	fa.tp = g.tp, fa.bar = g.fused_bar, fa.err = g.fused_err;
+	fa.cand_val = (mode >= 2) ? g.cand_val : nullptr, fa.cand_idx = g.cand_idx;
+	fa.mode = mode;
+	fa.slot_bytes = g.fused_slot_bytes, fa.nslots = g.fused_nslots;
+	fa.attn_nsplit = g.fused_nsplit, fa.attn_hg = g.attn_hg, fa.attn_qgroups = g.attn_qgroups, fa.attn_lpp = g.attn_lpp;
+	fa.attn_scratch_bytes = g.fused_scratch;
+	fa.inv_sqrt_hd = 1.0f / sqrtf((float)c.head_dim);
+	fused_launch(fa);
+	int nl = 1;
+	if (mode >= 2) {
+		k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, g.sms, g.tp, g.out_tokens, g.last_token, mode == 2);
+		++nl;
+	}
+	return nl;
+}
+
 void launch_token(int mode) {
+	// the persistent kernel serves every token it can; the rest (MoE, fp8 KV, rolled-over cache,
+	// per-stage profiling) goes through the staged engine.  Both are CUDA paths over the same buffers.
+	const bool fused = g.engine == 1 && g.fused_ok && !g.perf && !g.debug_stages && g.cur_pos < g.cfg.seq_len;
+	if (fused) {
+		if (!g.use_graph) {
+			g_launches += run_token_fused(mode);
+			CUDA_CHECK(cudaGetLastError());
+			return;
+		}
+		if (!g.fgraph[mode]) {
+			cudaGraph_t graph;
+			CUDA_CHECK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+			g.fgraph_launches[mode] = run_token_fused(mode);
+			CUDA_CHECK(cudaStreamEndCapture(g.stream, &graph));
+			CUDA_CHECK(cudaGraphInstantiate(&g.fgraph[mode], graph, 0));
+			CUDA_CHECK(cudaGraphDestroy(graph));
+		}
+		CUDA_CHECK(cudaGraphLaunch(g.fgraph[mode], g.stream));
+		g_launches += g.fgraph_launches[mode];
+		return;
+	}
 	if (!g.use_graph || g.perf) {
 		g_launches += run_token_any(mode);
 		CUDA_CHECK(cudaGetLastError());
@@ -313,6 +467,7 @@ void launch_token(int mode) {
 
 void set_params(int token, int pos, int step) {
 	g.cur_kv_len = pos >= g.cfg.seq_len ? g.cfg.seq_len : pos + 1;
+	g.cur_pos = pos;
 	k_set_params<<<1, 1, 0, g.stream>>>(g.tp, token, pos, g.cfg.seq_len, step);
 	++g_launches;
 }
@@ -379,7 +534,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.q_dim = q_dim, g.kv_dim = kv_dim, g.kv_mul = c.n_heads / c.n_kv_heads;
 	g.use_graph = !(getenv("CALM_B200_GRAPH") && atoi(getenv("CALM_B200_GRAPH")) == 0);
 	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
-	if (g.debug) g.use_graph = false;
+	if (g.debug) g.use_graph = false, g.debug_stages = true;
 	g.perf = (getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF"))) || getenv("CUDA_INJECTION64_PATH");
 
 	CUDA_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
@@ -429,20 +584,30 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.attn_counter = (unsigned*)dev_alloc(units * sizeof(unsigned));
 	CUDA_CHECK(cudaMemset(g.attn_counter, 0, units * sizeof(unsigned)));
 
+	g.attn_nsplit_cap = g.attn_nsplit; // the partial buffer below is sized for this many slices
+	if (g.sms / units > g.attn_nsplit_cap) {
+		g.attn_nsplit_cap = g.sms / units;
+		CUDA_CHECK(cudaFree(g.attn_partial));
+		g.attn_partial = (float*)dev_alloc((size_t)units * g.attn_nsplit_cap * g.attn_hg * (c.head_dim + 2) * sizeof(float));
+	}
 	g.moe_sel = (MoeSel*)dev_alloc(sizeof(MoeSel));
 	CUDA_CHECK(cudaMemset(g.moe_sel, 0, sizeof(MoeSel)));
 	g.tp = (TokenParams*)dev_alloc(sizeof(TokenParams));
 	CUDA_CHECK(cudaMemset(g.tp, 0, sizeof(TokenParams)));
 
+	g.engine = g_engine_kind >= 0 ? g_engine_kind : (getenv("CALM_B200_ENGINE") ? atoi(getenv("CALM_B200_ENGINE")) : 1);
 	switch (w.dbits) {
 	case 16: make_plan_kv<16>(); break;
 	case 8: make_plan_kv<8>(); break;
 	default: make_plan_kv<4>(); break;
 	}
-	g.cand_val = (float*)dev_alloc(g.ncand * sizeof(float));
-	g.cand_idx = (int*)dev_alloc(g.ncand * sizeof(int));
+	const int ncand_cap = g.ncand > g.sms ? g.ncand : g.sms; // the fused engine publishes one candidate per SM
+	g.cand_val = (float*)dev_alloc(ncand_cap * sizeof(float));
+	g.cand_idx = (int*)dev_alloc(ncand_cap * sizeof(int));
 	g.out_tokens_cap = 1 << 16;
 	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
+
+	if (g.engine == 1) fused_plan();
 
 	// what the reference backend publishes in RunState (infer.cu:99-112)
 	s->x = g.x, s->hb = g.hb, s->he = g.hb, s->q = g.q, s->att = g.att;
@@ -456,8 +621,12 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 extern "C" void calm_b200_release(struct Transformer* transformer) {
 	if (!g.ready) return;
 	CUDA_CHECK(cudaDeviceSynchronize());
-	for (int i = 0; i < 4; ++i)
+	for (int i = 0; i < 4; ++i) {
 		if (g.graph[i]) CUDA_CHECK(cudaGraphExecDestroy(g.graph[i]));
+		if (g.fgraph[i]) CUDA_CHECK(cudaGraphExecDestroy(g.fgraph[i]));
+	}
+	if (g.fused_bar) cudaFree(g.fused_bar);
+	if (g.fused_err) cudaFreeHost(g.fused_err);
 	cudaFree(g.x), cudaFree(g.xb), cudaFree(g.q), cudaFree(g.att), cudaFree(g.hb), cudaFree(g.logits_dev);
 	cudaFreeHost(g.logits_host), cudaFreeHost(g.last_token);
 	cudaFree(g.kc), cudaFree(g.vc), cudaFree(g.rope_freq), cudaFree(g.attn_partial), cudaFree(g.attn_counter);
@@ -471,6 +640,15 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 		int kvbits = transformer->state.kvbits;
 		memset(&transformer->state, 0, sizeof(transformer->state));
 		transformer->state.kvbits = kvbits;
+	}
+}
+
+static void sync_stream() {
+	cudaError_t e = cudaStreamSynchronize(g.stream);
+	if (e != cudaSuccess) {
+		int code = g.fused_err ? *(volatile int*)g.fused_err : 0;
+		fprintf(stderr, "calm_b200: device failure: %s (%s); fused-engine watchdog code %d\n", cudaGetErrorString(e), cudaGetErrorName(e), code);
+		abort();
 	}
 }
 
@@ -489,7 +667,7 @@ extern "C" float* forward_cuda(struct Transformer* transformer, int token, int p
 		return NULL; // no synchronisation: prompt tokens pipeline (reference infer.cu:724-727)
 	}
 	launch_token(1);
-	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	sync_stream();
 	CUDA_CHECK(cudaGetLastError());
 	if (g.perf) ++g.perf_runs;
 	return g.logits_host;
@@ -499,7 +677,7 @@ extern "C" int calm_b200_forward_argmax(struct Transformer* transformer, int tok
 	check_call(transformer, token, pos);
 	set_params(token, pos, 0);
 	launch_token(3);
-	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	sync_stream();
 	return *(volatile int*)g.last_token;
 }
 
@@ -507,9 +685,12 @@ extern "C" void calm_b200_decode_greedy(struct Transformer* transformer, int tok
 	check_call(transformer, token0, pos0);
 	if (n_tokens > g.out_tokens_cap) CALM_FATAL("decode_greedy: at most %d tokens per call", g.out_tokens_cap);
 	set_params(token0, pos0, 0);
-	for (int i = 0; i < n_tokens; ++i) launch_token(2);
-	CUDA_CHECK(cudaMemcpyAsync(out_tokens, g.out_tokens, n_tokens * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	for (int i = 0; i < n_tokens; ++i) {
+		g.cur_pos = pos0 + i;
+		launch_token(2);
+	}
+	sync_stream();
+	CUDA_CHECK(cudaMemcpy(out_tokens, g.out_tokens, n_tokens * sizeof(int), cudaMemcpyDeviceToHost));
 }
 
 extern "C" void calm_b200_timer_start(void) {

@@ -1,0 +1,893 @@
+// fused.cuh -- the "fused" engine: ONE persistent kernel runs a whole token.
+//
+// Why: at batch 1 a Llama-3-8B token is ~165 stage executions of 2-18 us of HBM time each, so launch
+// gaps, pipeline fill and wave tails -- not bandwidth -- decide the roofline fraction of a kernel-per-stage
+// design.  Here the weights never stop streaming:
+//
+//   * grid = one CTA per SM (cooperative launch), 1 producer warp + 8 consumer warps;
+//   * every CTA owns a fixed, contiguous row range of every matrix, so its share of the model is a
+//     STATIC list of contiguous byte ranges ("tiles");
+//   * the producer lane walks that list for the whole token and moves tile after tile into a ring of
+//     shared-memory slots with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx).  It never looks at
+//     activations, so it runs ahead across stage boundaries: while the consumers sit in a grid barrier
+//     the ring (up to ~200 KB per SM, ~30 MB chip-wide) keeps filling with the next stages' weights;
+//   * consumers keep their slice of the activation vector IN REGISTERS (a warp group of WG warps owns a
+//     row, each thread a fixed set of 16-byte column vectors), read weights from the ring with
+//     conflict-free 16-byte shared loads, dequantise in registers, FMA in fp32, reduce by shuffles, and
+//     the last warp to finish a tile folds the per-warp partial sums in a fixed order (deterministic)
+//     and runs the stage epilogue (bias/clip/RoPE/KV append, residual, SiLU-gate, logits/argmax);
+//   * attention streams K/V tiles through the same ring (flash-decoding split over positions; the
+//     entry written this step is read through the generic path after the barrier instead).
+//
+// Stage order and arithmetic are those of stages.cuh (reference infer.c:311-472).  Five grid barriers per
+// layer (after QKV, attention, wo, FFN-up, FFN-down); MoE models, fp8 KV caches and the rolled-over
+// cache (pos >= seq_len) are served by the staged engine.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "stages.cuh"
+
+#define FUSED_NCW 8                          // consumer warps
+#define FUSED_THREADS ((FUSED_NCW + 1) * 32) // + 1 producer warp
+#define FUSED_MAX_SLOTS 16
+#define FUSED_SPIN_LIMIT (1u << 27)          // watchdog for every spin loop (~1 s)
+
+struct FusedLayer {
+	const void *wq, *wk, *wv, *wo, *w1, *w2, *w3;
+	const float *rms_att, *rms_ffn, *bqkv;
+};
+
+struct FusedArgs {
+	int dim, hidden, q_dim, kv_dim, head_dim, n_heads, n_kv_heads, n_layers, vocab, seq_len, kv_mul;
+	float eps, clip;
+	int ln, norm_par, gelu;
+	float *x, *xb, *q, *att, *hb, *logits;
+	float* attn_partial;
+	unsigned* attn_counter;
+	__half *kc, *vc;
+	const float* rope_freq;
+	const void* embed;
+	const void* wcls;
+	const float* rms_final;
+	const TokenParams* tp;
+	unsigned* bar; // grid barrier word
+	int* err;      // watchdog report: nonzero = which wait timed out
+	float* cand_val;
+	int* cand_idx;
+	int mode;      // 0 kv only, >= 1 logits (cand_val != NULL: also greedy candidates)
+	int slot_bytes, nslots;
+	int attn_nsplit, attn_hg, attn_qgroups, attn_lpp, attn_scratch_bytes;
+	float inv_sqrt_hd;
+};
+
+__constant__ FusedLayer c_fused_layers[MAX_LAYERS];
+
+// ---------------------------------------------------------------- PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+// bulk global -> shared copy, completion counted on an mbarrier; weights are read once: evict-first in L2
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+	             : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ void consumer_sync() { // named barrier 1: the 8 consumer warps only
+	asm volatile("bar.sync 1, %0;" ::"n"(FUSED_NCW * 32) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(const void* p) {
+	uint4 r;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+	return r;
+}
+
+__device__ __noinline__ void fused_fail(int* err, int code) {
+	atomicCAS(err, 0, code);
+	__threadfence_system();
+	__trap();
+}
+
+#define SPIN_WAIT(cond, err, code)                          \
+	do {                                                    \
+		unsigned spins_ = 0;                                \
+		while (!(cond)) {                                   \
+			if (++spins_ > FUSED_SPIN_LIMIT) fused_fail(err, code); \
+		}                                                   \
+	} while (0)
+
+// Self-resetting grid barrier (counter gains exactly 2^31 per round: CTA 0 adds 2^31 - (G-1), the
+// others add 1; a round is over when bit 31 flips).  Split into arrive / wait so the caller can place
+// independent work in between.  Called by one thread per CTA.
+__device__ __forceinline__ unsigned grid_arrive(unsigned* bar) {
+	unsigned nb = blockIdx.x == 0 ? 0x80000000u - (gridDim.x - 1) : 1u;
+	unsigned old;
+	__threadfence();
+	asm volatile("atom.add.release.gpu.u32 %0, [%1], %2;" : "=r"(old) : "l"(bar), "r"(nb) : "memory");
+	return old;
+}
+__device__ __forceinline__ void grid_wait(unsigned* bar, unsigned old, int* err, int code) {
+	unsigned cur;
+	unsigned spins = 0;
+	do {
+		asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
+		if (++spins > FUSED_SPIN_LIMIT) fused_fail(err, code);
+	} while (((old ^ cur) & 0x80000000u) == 0);
+}
+
+// ---------------------------------------------------------------- shared-memory layout
+
+struct FusedShared {
+	uint64_t full[FUSED_MAX_SLOTS];  // producer -> consumers: tile landed (tx bytes)
+	uint64_t empty[FUSED_MAX_SLOTS]; // consumers -> producer: tile consumed (FUSED_NCW arrivals)
+	int cnt[FUSED_MAX_SLOTS];        // warps done with the tile in this slot (last one finalises)
+	float red[FUSED_MAX_SLOTS][32][FUSED_NCW]; // per-row, per-warp partial sums
+	float scratch[64];               // block reductions
+	float best_val[FUSED_NCW];       // greedy candidates per finalising warp
+	int best_idx[FUSED_NCW];
+	int flag;
+};
+
+// ---------------------------------------------------------------- tile schedule (shared by producer and consumers)
+
+struct Tile {
+	const char* src[2];
+	uint32_t seg_bytes; // bytes per segment
+	int nseg;
+	int rows;           // rows per segment
+	int row0;           // first row (index within its matrix)
+};
+
+__device__ __forceinline__ void cta_range(int units, int& u0, int& u1) {
+	u0 = (int)(((long long)blockIdx.x * units) / gridDim.x);
+	u1 = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x);
+}
+
+// rows per tile for a matrix stage
+__device__ __forceinline__ int tile_rows(int slot_bytes, int nseg, int rowbytes, int unit) {
+	int r = slot_bytes / (nseg * rowbytes);
+	if (r > 32 / nseg) r = 32 / nseg;
+	r -= r % unit;
+	return r < unit ? unit : r;
+}
+
+// Ring bookkeeping common to both sides: slot index and phase of the k-th tile of this CTA.
+struct RingPos {
+	int slot;
+	uint32_t phase;
+	int nslots;
+	__device__ __forceinline__ void init(int n) { slot = 0, phase = 0, nslots = n; }
+	__device__ __forceinline__ void advance() {
+		if (++slot == nslots) slot = 0, phase ^= 1;
+	}
+};
+
+// ---------------------------------------------------------------- producer
+
+struct Producer {
+	FusedShared* sh;
+	char* ring;
+	int slot_bytes;
+	RingPos rp;
+	uint64_t pol_w, pol_kv;
+	int* err;
+
+	__device__ __forceinline__ void push(const Tile& t) {
+		SPIN_WAIT(mbar_try_wait(&sh->empty[rp.slot], rp.phase ^ 1), err, 101);
+		mbar_expect_tx(&sh->full[rp.slot], t.seg_bytes * t.nseg);
+		char* dst = ring + (size_t)rp.slot * slot_bytes;
+		tma_load_1d(dst, t.src[0], t.seg_bytes, &sh->full[rp.slot], pol_w);
+		if (t.nseg == 2) tma_load_1d(dst + t.seg_bytes, t.src[1], t.seg_bytes, &sh->full[rp.slot], pol_w);
+		rp.advance();
+	}
+
+	// all tiles of rows [r0, r1) of one matrix (or of two matrices read in lock step)
+	__device__ __forceinline__ void matrix(const void* w0, const void* w1, int rowbytes, int r0, int r1, int R) {
+		Tile t;
+		t.nseg = w1 ? 2 : 1;
+		for (int a = r0; a < r1; a += R) {
+			int rows = min(R, r1 - a);
+			t.src[0] = (const char*)w0 + (size_t)a * rowbytes;
+			t.src[1] = w1 ? (const char*)w1 + (size_t)a * rowbytes : nullptr;
+			t.seg_bytes = (uint32_t)rows * rowbytes;
+			t.rows = rows, t.row0 = a;
+			push(t);
+		}
+	}
+};
+
+// ---------------------------------------------------------------- consumer: matvec over ring tiles
+
+// How the 8 consumer warps share a row of `nvec` 16-byte vectors: WG warps per row (power of two),
+// IT vectors per thread.
+struct RowMap {
+	int wg, ng, it, tg; // warps per group, groups, vectors per thread, threads per group
+};
+template <int DBITS, int XR>
+__device__ __forceinline__ RowMap row_map(int nvec) {
+	constexpr int ITMAX = XR / WFmt<DBITS>::VW;
+	RowMap m;
+	m.wg = 1;
+	while (m.wg < FUSED_NCW && (nvec + m.wg * 32 - 1) / (m.wg * 32) > ITMAX / 2) m.wg *= 2; // aim at half the register budget...
+	while ((nvec + m.wg * 32 - 1) / (m.wg * 32) > ITMAX && m.wg < FUSED_NCW) m.wg *= 2;         // ...but never exceed it
+	m.ng = FUSED_NCW / m.wg;
+	m.tg = m.wg * 32;
+	m.it = (nvec + m.tg - 1) / m.tg;
+	return m;
+}
+
+template <int DBITS, int XR>
+struct Consumer {
+	static constexpr int VW = WFmt<DBITS>::VW;
+	static constexpr int ITMAX = XR / VW;
+	static constexpr int Q = VW / 4;
+
+	FusedShared* sh;
+	const char* ring;
+	int slot_bytes;
+	int* err;
+	int cw, lane; // consumer warp 0..7
+	float best_v;
+	int best_i;   // greedy candidate seen by this thread (classifier stage)
+	float xr[ITMAX][VW];
+
+	// --- activation slice into registers -------------------------------------------------------
+	// xin: global vector written by other CTAs in this launch (read through L2), or, for layer 0, the
+	// embedding row (decoded here).  Optional norm (reference infer.c:183-207).
+	template <bool EMBED>
+	__device__ __forceinline__ void load_x(const RowMap& m, const float* xin, const void* table, int token, int n, const float* normw, float eps, bool ln,
+	                                       float* xb_out) {
+		const int nvec = n / VW;
+		const int tgi = (cw % m.wg) * 32 + lane;
+		float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+		for (int it = 0; it < ITMAX; ++it) {
+			int v = tgi + it * m.tg;
+			bool ok = it < m.it && v < nvec;
+#pragma unroll
+			for (int q = 0; q < Q; ++q) {
+				float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (ok) {
+					if (EMBED) {
+						size_t base = (size_t)token * n + (size_t)v * VW + q * 4;
+						f.x = weight_at<DBITS>(table, base), f.y = weight_at<DBITS>(table, base + 1);
+						f.z = weight_at<DBITS>(table, base + 2), f.w = weight_at<DBITS>(table, base + 3);
+					} else {
+						f = __ldcg(reinterpret_cast<const float4*>(xin + (size_t)v * VW) + q);
+					}
+				}
+				xr[it][q * 4 + 0] = f.x, xr[it][q * 4 + 1] = f.y, xr[it][q * 4 + 2] = f.z, xr[it][q * 4 + 3] = f.w;
+				ssum += (f.x + f.y) + (f.z + f.w);
+			}
+		}
+		if (!normw) return;
+		float mean = 0.f;
+		if (ln) mean = block_total(ssum) / (float)(m.ng * n);
+#pragma unroll
+		for (int it = 0; it < ITMAX; ++it) {
+			int v = tgi + it * m.tg;
+			bool ok = it < m.it && v < nvec;
+#pragma unroll
+			for (int e = 0; e < VW; ++e) {
+				float d = ok ? xr[it][e] - mean : 0.f;
+				ssq = fmaf(d, d, ssq);
+			}
+		}
+		float var = block_total(ssq) / (float)(m.ng * n); // every group holds one full copy of the vector
+		float scale = 1.0f / sqrtf(var + eps);
+#pragma unroll
+		for (int it = 0; it < ITMAX; ++it) {
+			int v = tgi + it * m.tg;
+			bool ok = it < m.it && v < nvec;
+			if (ok) {
+#pragma unroll
+				for (int q = 0; q < Q; ++q) {
+					float4 w = __ldg(reinterpret_cast<const float4*>(normw + (size_t)v * VW) + q);
+					float* xp = &xr[it][q * 4];
+					xp[0] = (xp[0] - mean) * scale * w.x, xp[1] = (xp[1] - mean) * scale * w.y;
+					xp[2] = (xp[2] - mean) * scale * w.z, xp[3] = (xp[3] - mean) * scale * w.w;
+					if (xb_out && cw / m.wg == 0) *(reinterpret_cast<float4*>(xb_out + (size_t)v * VW) + q) = make_float4(xp[0], xp[1], xp[2], xp[3]);
+				}
+			}
+		}
+	}
+
+	// sum over all 256 consumer threads (every thread gets it)
+	__device__ __forceinline__ float block_total(float v) {
+		v = warp_sum(v);
+		consumer_sync();
+		if (lane == 0) sh->scratch[cw] = v;
+		consumer_sync();
+		float r = lane < FUSED_NCW ? sh->scratch[lane] : 0.f;
+		return warp_sum(r);
+	}
+
+	// --- one matrix stage ---------------------------------------------------------------------
+	// Consumes the tiles the producer pushed for rows [r0, r1) (R rows per tile, nseg segments).
+	// epi(row, v0, v1): called by one lane per row (v1 = second segment's value when nseg == 2); for
+	// PAIR stages it is called once per even row with (row, value(row), value(row + 1)).
+	template <int IT, bool PAIR, typename Epi>
+	__device__ __forceinline__ void matrix_it(RingPos& rp, const RowMap& m, int nvec, int nseg, int r0, int r1, int R, Epi epi) {
+		const int grp = cw / m.wg, wig = cw % m.wg;
+		const int tgi = wig * 32 + lane;
+		const int rowbytes = nvec * 16;
+		for (int a = r0; a < r1; a += R) {
+			const int rows = min(R, r1 - a);
+			const int vrows = rows * nseg;
+			SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), err, 201);
+			const char* tile = ring + (size_t)rp.slot * slot_bytes;
+			for (int vr = grp; vr < vrows; vr += m.ng) {
+				const uint4* rowp = reinterpret_cast<const uint4*>(tile + (size_t)vr * rowbytes);
+				uint4 w[IT];
+#pragma unroll
+				for (int it = 0; it < IT; ++it) { // all loads first (zero weights contribute exactly 0)
+					int v = tgi + it * m.tg;
+					w[it] = v < nvec ? lds128(rowp + v) : make_uint4(0, 0, 0, 0);
+				}
+				float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+				for (int it = 0; it < IT; ++it) {
+					float4 xv[Q];
+#pragma unroll
+					for (int q = 0; q < Q; ++q) xv[q] = make_float4(xr[it][q * 4], xr[it][q * 4 + 1], xr[it][q * 4 + 2], xr[it][q * 4 + 3]);
+					if (it & 1)
+						acc1 = dot_vec<DBITS>(w[it], xv, acc1);
+					else
+						acc0 = dot_vec<DBITS>(w[it], xv, acc0);
+				}
+				float acc = warp_sum(acc0 + acc1);
+				if (lane == 0) sh->red[rp.slot][vr][wig] = acc;
+			}
+			// this warp is done reading the tile; find out whether it is the last one
+			__syncwarp();
+			int last = 0;
+			if (lane == 0) {
+				__threadfence_block();
+				last = atomicAdd(&sh->cnt[rp.slot], 1) == FUSED_NCW - 1;
+			}
+			last = __shfl_sync(0xffffffffu, last, 0);
+			if (last) {
+				__threadfence_block();
+				if (lane == 0) sh->cnt[rp.slot] = 0;
+				// fold the per-warp partials in a fixed order and run the epilogue
+				const int nrow_calls = PAIR ? rows / 2 : rows;
+				for (int i = lane; i < nrow_calls; i += 32) {
+					int r = PAIR ? 2 * i : i;
+					float v0 = 0.f, v1 = 0.f;
+					const int ra = r, rb = PAIR ? r + 1 : rows + r; // second value: next row, or same row of segment 2
+					for (int w_ = 0; w_ < m.wg; ++w_) v0 += sh->red[rp.slot][ra][w_];
+					if (PAIR || nseg == 2)
+						for (int w_ = 0; w_ < m.wg; ++w_) v1 += sh->red[rp.slot][rb][w_];
+					epi(a + r, v0, v1);
+				}
+				__syncwarp();
+			}
+			if (lane == 0) mbar_arrive(&sh->empty[rp.slot]);
+			rp.advance();
+		}
+	}
+
+	// dispatch on the (power-of-two) number of vectors per thread so the inner loops are fully unrolled
+	template <bool PAIR, typename Epi>
+	__device__ __forceinline__ void matrix(RingPos& rp, const RowMap& m, int nvec, int nseg, int r0, int r1, int R, Epi epi) {
+		if (m.it <= 1)
+			matrix_it<1, PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
+		else if (ITMAX >= 2 && m.it <= 2)
+			matrix_it<(ITMAX >= 2 ? 2 : 1), PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
+		else if (ITMAX >= 4 && m.it <= 4)
+			matrix_it<(ITMAX >= 4 ? 4 : 1), PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
+		else if (ITMAX >= 8 && m.it <= 8)
+			matrix_it<(ITMAX >= 8 ? 8 : 1), PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
+		else
+			matrix_it<ITMAX, PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
+	}
+};
+
+// ---------------------------------------------------------------- consumer: attention over ring tiles
+// Same arithmetic as k_attn (stages.cuh).  One work item = (unit of HG query heads sharing a kv head,
+// slice [t0, t1) of positions).  K and V of 'TP' positions arrive per ring slot (K at the slot base, V at
+// TP * kvrow); the entry of the current step (written by stage 1 of this launch, possibly after the tile was
+// prefetched) is skipped in the tile and read through L2 instead.
+
+__device__ __forceinline__ void halves8(const uint4& r, float (&o)[8]) {
+	float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+	float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+	float2 c = __half22float2(*reinterpret_cast<const __half2*>(&r.z));
+	float2 d = __half22float2(*reinterpret_cast<const __half2*>(&r.w));
+	o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y, o[4] = c.x, o[5] = c.y, o[6] = d.x, o[7] = d.y;
+}
+
+template <int HG>
+__device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, FusedShared* sh, const char* ring, float* scratch, const TokenParams& tp,
+                                             const __half* kc_l, const __half* vc_l, int unit, int split, int kvh, int t0, int t1, int TP, int warp, int lane) {
+	constexpr int P = HG > 4 ? 2 : 4;
+	const int hd = a.head_dim, lpp = a.attn_lpp;
+	const int G = 32 / lpp;
+	const int grp = lane / lpp, li = lane % lpp;
+	const bool dact = li * 8 < hd;
+	const int kvrow = hd * 2;
+	const int hbase = kvh * a.kv_mul + (unit % a.attn_qgroups) * HG;
+
+	float qr[HG][8], acc[HG][8], m[HG], l[HG];
+#pragma unroll
+	for (int h = 0; h < HG; ++h) {
+		m[h] = -FLT_MAX, l[h] = 0.f;
+		float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+		if (dact) {
+			const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)(hbase + h) * hd + li * 8);
+			q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
+		}
+		qr[h][0] = q0.x, qr[h][1] = q0.y, qr[h][2] = q0.z, qr[h][3] = q0.w, qr[h][4] = q1.x, qr[h][5] = q1.y, qr[h][6] = q1.z, qr[h][7] = q1.w;
+#pragma unroll
+		for (int d = 0; d < 8; ++d) acc[h][d] = 0.f;
+	}
+
+	// online-softmax update with P (position, K, V) triples held by this lane group
+	auto update = [&](const float (&kf)[P][8], const float (&vf)[P][8], const bool (&ok)[P]) {
+#pragma unroll
+		for (int h = 0; h < HG; ++h) {
+			float s[P], smax = m[h];
+#pragma unroll
+			for (int i = 0; i < P; ++i) {
+				float d = 0.f;
+#pragma unroll
+				for (int e = 0; e < 8; ++e) d = fmaf(qr[h][e], kf[i][e], d);
+				for (int o = 1; o < lpp; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+				s[i] = ok[i] ? d * a.inv_sqrt_hd : -FLT_MAX;
+				smax = fmaxf(smax, s[i]);
+			}
+			float corr = expf(m[h] - smax);
+			m[h] = smax;
+			float pw[P], ps = 0.f;
+#pragma unroll
+			for (int i = 0; i < P; ++i) {
+				pw[i] = ok[i] ? expf(s[i] - smax) : 0.f;
+				ps += pw[i];
+			}
+			l[h] = fmaf(l[h], corr, ps);
+#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				float v = acc[h][e] * corr;
+#pragma unroll
+				for (int i = 0; i < P; ++i) v = fmaf(pw[i], vf[i][e], v);
+				acc[h][e] = v;
+			}
+		}
+	};
+
+	for (int tb = t0; tb < t1; tb += TP) {
+		const int np = min(TP, t1 - tb);
+		SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), a.err, 202);
+		const char* kt = ring + (size_t)rp.slot * a.slot_bytes;
+		const char* vt = kt + (size_t)TP * kvrow;
+		for (int pb = 0; pb < np; pb += FUSED_NCW * G * P) { // warp-uniform trip count
+			float kf[P][8], vf[P][8];
+			bool ok[P];
+#pragma unroll
+			for (int i = 0; i < P; ++i) {
+				int p = pb + (i * FUSED_NCW + warp) * G + grp;
+				ok[i] = p < np && (tb + p) != tp.kv_pos;
+				if (ok[i] && dact) {
+					halves8(lds128(kt + (size_t)p * kvrow + li * 16), kf[i]);
+					halves8(lds128(vt + (size_t)p * kvrow + li * 16), vf[i]);
+				} else {
+#pragma unroll
+					for (int d = 0; d < 8; ++d) kf[i][d] = 0.f, vf[i][d] = 0.f;
+				}
+			}
+			update(kf, vf, ok);
+		}
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&sh->empty[rp.slot]);
+		rp.advance();
+	}
+
+	// the entry appended this step: fresh from L2 (warp 0 only; its first lane group holds it)
+	if (warp == 0 && tp.kv_pos >= t0 && tp.kv_pos < t1) {
+		float kf[P][8], vf[P][8];
+		bool ok[P];
+#pragma unroll
+		for (int i = 0; i < P; ++i) {
+			ok[i] = i == 0 && grp == 0;
+#pragma unroll
+			for (int d = 0; d < 8; ++d) kf[i][d] = 0.f, vf[i][d] = 0.f;
+		}
+		if (grp == 0 && dact) {
+			size_t off = ((size_t)kvh * a.seq_len + tp.kv_pos) * hd + li * 8;
+			halves8(__ldcg(reinterpret_cast<const uint4*>(kc_l + off)), kf[0]);
+			halves8(__ldcg(reinterpret_cast<const uint4*>(vc_l + off)), vf[0]);
+		}
+		update(kf, vf, ok);
+	}
+
+	// merge lane groups of a warp
+	for (int o = lpp; o < 32; o <<= 1) {
+#pragma unroll
+		for (int h = 0; h < HG; ++h) {
+			float mo = __shfl_xor_sync(0xffffffffu, m[h], o), lo = __shfl_xor_sync(0xffffffffu, l[h], o);
+			float mn = fmaxf(m[h], mo);
+			float ca = expf(m[h] - mn), cb = expf(mo - mn);
+			l[h] = l[h] * ca + lo * cb;
+#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				float ao = __shfl_xor_sync(0xffffffffu, acc[h][e], o);
+				acc[h][e] = acc[h][e] * ca + ao * cb;
+			}
+			m[h] = mn;
+		}
+	}
+	// merge warps: scratch[warp][h][hd + 2]
+	const int rec = hd + 2;
+	if (grp == 0) {
+#pragma unroll
+		for (int h = 0; h < HG; ++h) {
+			float* r = scratch + ((size_t)warp * HG + h) * rec;
+			if (dact) {
+#pragma unroll
+				for (int e = 0; e < 8; ++e) r[li * 8 + e] = acc[h][e];
+			}
+			if (li == 0) r[hd] = m[h], r[hd + 1] = l[h];
+		}
+	}
+	consumer_sync();
+	const int tid = warp * 32 + lane;
+	float* part = a.attn_partial + ((size_t)unit * a.attn_nsplit + split) * HG * rec;
+	for (int idx = tid; idx < HG * rec; idx += FUSED_NCW * 32) {
+		int h = idx / rec, e = idx % rec;
+		float mn = -FLT_MAX;
+		for (int w = 0; w < FUSED_NCW; ++w) mn = fmaxf(mn, scratch[((size_t)w * HG + h) * rec + hd]);
+		float v;
+		if (e == hd) {
+			v = mn;
+		} else {
+			v = 0.f;
+			for (int w = 0; w < FUSED_NCW; ++w) {
+				const float* r = scratch + ((size_t)w * HG + h) * rec;
+				v += r[e] * expf(r[hd] - mn);
+			}
+		}
+		__stcg(part + idx, v);
+	}
+	__threadfence();
+	consumer_sync();
+	if (tid == 0) {
+		unsigned old = atomicAdd(a.attn_counter + unit, 1u);
+		sh->flag = (old == (unsigned)a.attn_nsplit - 1);
+	}
+	consumer_sync();
+	if (!sh->flag) return rp;
+	__threadfence();
+	const float* pk = a.attn_partial + (size_t)unit * a.attn_nsplit * HG * rec;
+	for (int idx = tid; idx < HG * hd; idx += FUSED_NCW * 32) {
+		int h = idx / hd, e = idx % hd;
+		float mn = -FLT_MAX;
+		for (int s = 0; s < a.attn_nsplit; ++s) mn = fmaxf(mn, __ldcg(pk + ((size_t)s * HG + h) * rec + hd));
+		float num = 0.f, den = 0.f;
+		for (int s = 0; s < a.attn_nsplit; ++s) {
+			const float* r = pk + ((size_t)s * HG + h) * rec;
+			float cf = expf(__ldcg(r + hd) - mn);
+			num = fmaf(__ldcg(r + e), cf, num);
+			den = fmaf(__ldcg(r + hd + 1), cf, den);
+		}
+		__stcg(a.att + (size_t)(hbase + h) * hd + e, num / den);
+	}
+	if (tid == 0) a.attn_counter[unit] = 0;
+	return rp;
+}
+
+// ---------------------------------------------------------------- stages (one noinline function each:
+// bounded register live ranges and code size; the activation slice lives only inside its stage)
+
+struct StageCtx {
+	FusedShared* sh;
+	const char* ring;
+	float* attn_scratch;
+	int warp, lane;
+};
+
+// all consumer warps finished the stage -> publish; then wait for every CTA
+__device__ __forceinline__ void stage_barrier(const FusedArgs& a, int code) {
+	consumer_sync();
+	if (threadIdx.x == 0) {
+		unsigned old = grid_arrive(a.bar);
+		grid_wait(a.bar, old, a.err, code);
+	}
+	consumer_sync();
+}
+
+template <int DBITS, int XR>
+__device__ __forceinline__ Consumer<DBITS, XR> make_consumer(const FusedArgs& a, const StageCtx& cx) {
+	Consumer<DBITS, XR> c;
+	c.sh = cx.sh, c.ring = cx.ring, c.slot_bytes = a.slot_bytes, c.err = a.err;
+	c.cw = cx.warp, c.lane = cx.lane;
+	c.best_v = -FLT_MAX, c.best_i = 0x7fffffff;
+	return c;
+}
+
+// stage 1: norm -> q,k,v (+bias, clip, RoPE) -> q vector / cache append   (reference infer.c:352-381)
+template <int DBITS, int XR>
+__device__ __noinline__ RingPos stage_qkv(const FusedArgs& a, const StageCtx cx, RingPos rp, int l, const TokenParams tp) {
+	constexpr int VW = WFmt<DBITS>::VW;
+	const FusedLayer& L = c_fused_layers[l];
+	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
+	const int nv = a.dim / VW;
+	const RowMap m = row_map<DBITS, XR>(nv);
+	const int R = tile_rows(a.slot_bytes, 1, nv * 16, 2);
+	int q0, q1, k0, k1;
+	cta_range(a.q_dim / 2, q0, q1), q0 *= 2, q1 *= 2;
+	cta_range(a.kv_dim / 2, k0, k1), k0 *= 2, k1 *= 2;
+	float* xb_out = a.norm_par && blockIdx.x == 0 ? a.xb : nullptr;
+	if (l == 0)
+		c.template load_x<true>(m, nullptr, a.embed, tp.token, a.dim, L.rms_att, a.eps, a.ln != 0, xb_out);
+	else
+		c.template load_x<false>(m, a.x, nullptr, 0, a.dim, L.rms_att, a.eps, a.ln != 0, xb_out);
+
+	const size_t kv_layer = (size_t)a.n_kv_heads * a.seq_len * a.head_dim;
+	__half* kc_l = a.kc + l * kv_layer;
+	__half* vc_l = a.vc + l * kv_layer;
+	auto epi = [&](int which, int k, float v0, float v1) {
+		int j = which == 0 ? k : (which == 1 ? a.q_dim + k : a.q_dim + a.kv_dim + k);
+		if (L.bqkv) v0 += L.bqkv[j], v1 += L.bqkv[j + 1];
+		v0 = fminf(fmaxf(v0, -a.clip), a.clip);
+		v1 = fminf(fmaxf(v1, -a.clip), a.clip);
+		if (which < 2) {
+			float fcr, fci;
+			sincosf((float)tp.pos * a.rope_freq[(k % a.head_dim) >> 1], &fci, &fcr);
+			float r0 = v0 * fcr - v1 * fci, r1 = v0 * fci + v1 * fcr;
+			v0 = r0, v1 = r1;
+		}
+		if (which == 0) {
+			__stcg(reinterpret_cast<float2*>(a.q + k), make_float2(v0, v1));
+		} else {
+			__half* cbase = which == 1 ? kc_l : vc_l;
+			int h = k / a.head_dim, d = k % a.head_dim;
+			*reinterpret_cast<__half2*>(cbase + ((size_t)h * a.seq_len + tp.kv_pos) * a.head_dim + d) = __floats2half2_rn(v0, v1);
+		}
+	};
+	c.template matrix<true>(rp, m, nv, 1, q0, q1, R, [&](int r, float v0, float v1) { epi(0, r, v0, v1); });
+	c.template matrix<true>(rp, m, nv, 1, k0, k1, R, [&](int r, float v0, float v1) { epi(1, r, v0, v1); });
+	c.template matrix<true>(rp, m, nv, 1, k0, k1, R, [&](int r, float v0, float v1) { epi(2, r, v0, v1); });
+	stage_barrier(a, 301);
+	return rp;
+}
+
+// stage 3: x += wo . att   (reference infer.c:410-415)
+template <int DBITS, int XR>
+__device__ __noinline__ RingPos stage_wo(const FusedArgs& a, const StageCtx cx, RingPos rp, int l, int token) {
+	constexpr int VW = WFmt<DBITS>::VW;
+	const FusedLayer& L = c_fused_layers[l];
+	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
+	const int nv = a.q_dim / VW;
+	const RowMap m = row_map<DBITS, XR>(nv);
+	const int R = tile_rows(a.slot_bytes, 1, nv * 16, 1);
+	int o0, o1;
+	cta_range(a.dim, o0, o1);
+	c.template load_x<false>(m, a.att, nullptr, 0, a.q_dim, nullptr, 0.f, false, nullptr);
+	c.template matrix<false>(rp, m, nv, 1, o0, o1, R, [&](int r, float v0, float) {
+		float base = l == 0 ? weight_at<DBITS>(a.embed, (size_t)token * a.dim + r) : __ldcg(a.x + r);
+		__stcg(a.x + r, base + v0);
+	});
+	(void)L;
+	stage_barrier(a, 303);
+	return rp;
+}
+
+// stage 4: norm -> act(w1 . xn) * (w3 . xn)   (reference infer.c:417-450)
+template <int DBITS, int XR>
+__device__ __noinline__ RingPos stage_up(const FusedArgs& a, const StageCtx cx, RingPos rp, int l) {
+	constexpr int VW = WFmt<DBITS>::VW;
+	const FusedLayer& L = c_fused_layers[l];
+	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
+	const int nv = a.dim / VW;
+	const RowMap m = row_map<DBITS, XR>(nv);
+	const int R = tile_rows(a.slot_bytes, 2, nv * 16, 1);
+	int h0, h1;
+	cta_range(a.hidden, h0, h1);
+	if (a.norm_par)
+		c.template load_x<false>(m, a.xb, nullptr, 0, a.dim, nullptr, 0.f, false, nullptr);
+	else
+		c.template load_x<false>(m, a.x, nullptr, 0, a.dim, L.rms_ffn, a.eps, a.ln != 0, nullptr);
+	c.template matrix<false>(rp, m, nv, 2, h0, h1, R, [&](int r, float v1, float v3) { __stcg(a.hb + r, (a.gelu ? act_gelu(v1) : act_silu(v1)) * v3); });
+	stage_barrier(a, 304);
+	return rp;
+}
+
+// stage 5: x += w2 . hb   (reference infer.c:452-456)
+template <int DBITS, int XR>
+__device__ __noinline__ RingPos stage_down(const FusedArgs& a, const StageCtx cx, RingPos rp) {
+	constexpr int VW = WFmt<DBITS>::VW;
+	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
+	const int nv = a.hidden / VW;
+	const RowMap m = row_map<DBITS, XR>(nv);
+	const int R = tile_rows(a.slot_bytes, 1, nv * 16, 1);
+	int o0, o1;
+	cta_range(a.dim, o0, o1);
+	c.template load_x<false>(m, a.hb, nullptr, 0, a.hidden, nullptr, 0.f, false, nullptr);
+	c.template matrix<false>(rp, m, nv, 1, o0, o1, R, [&](int r, float v0, float) { __stcg(a.x + r, __ldcg(a.x + r) + v0); });
+	stage_barrier(a, 305);
+	return rp;
+}
+
+// classifier: logits = wcls . norm(x), greedy candidates   (reference infer.c:466-469, sampler.c:34-42)
+template <int DBITS, int XR>
+__device__ __noinline__ RingPos stage_out(const FusedArgs& a, const StageCtx cx, RingPos rp) {
+	constexpr int VW = WFmt<DBITS>::VW;
+	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
+	FusedShared* sh = cx.sh;
+	const int nv = a.dim / VW;
+	const RowMap m = row_map<DBITS, XR>(nv);
+	const int R = tile_rows(a.slot_bytes, 1, nv * 16, 1);
+	int c0, c1;
+	cta_range(a.vocab, c0, c1);
+	c.template load_x<false>(m, a.x, nullptr, 0, a.dim, a.rms_final, a.eps, a.ln != 0, nullptr);
+	c.template matrix<false>(rp, m, nv, 1, c0, c1, R, [&](int r, float v0, float) {
+		a.logits[r] = v0;
+		if (v0 > c.best_v || (v0 == c.best_v && r < c.best_i)) c.best_v = v0, c.best_i = r; // first maximum wins
+	});
+	if (a.cand_val) {
+		float bv = c.best_v;
+		int bi = c.best_i;
+		for (int o = 16; o > 0; o >>= 1) {
+			float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+			int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+		}
+		if (cx.lane == 0) sh->best_val[cx.warp] = bv, sh->best_idx[cx.warp] = bi;
+		consumer_sync();
+		if (threadIdx.x == 0) {
+			bv = -FLT_MAX, bi = 0x7fffffff;
+			for (int w = 0; w < FUSED_NCW; ++w)
+				if (sh->best_val[w] > bv || (sh->best_val[w] == bv && sh->best_idx[w] < bi)) bv = sh->best_val[w], bi = sh->best_idx[w];
+			a.cand_val[blockIdx.x] = bv, a.cand_idx[blockIdx.x] = bi;
+		}
+	}
+	return rp;
+}
+
+// ---------------------------------------------------------------- the kernel
+
+template <int DBITS, int XR>
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constant__ FusedArgs a) {
+	extern __shared__ __align__(128) char smem_raw[];
+	FusedShared* sh = reinterpret_cast<FusedShared*>(smem_raw);
+	float* attn_scratch = reinterpret_cast<float*>(smem_raw + ((sizeof(FusedShared) + 127) & ~(size_t)127));
+	char* ring = reinterpret_cast<char*>(attn_scratch) + a.attn_scratch_bytes;
+
+	constexpr int VW = WFmt<DBITS>::VW;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const TokenParams tp = *a.tp;
+
+	if (threadIdx.x == 0) {
+		for (int i = 0; i < a.nslots; ++i) {
+			mbar_init(&sh->full[i], 1);
+			mbar_init(&sh->empty[i], FUSED_NCW);
+			sh->cnt[i] = 0;
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+
+	// attention work item of this CTA: (unit, split) -> positions [t0, t1) of kv head `kvh`
+	const int units = a.n_kv_heads * a.attn_qgroups;
+	const int item = blockIdx.x;
+	const bool has_item = item < units * a.attn_nsplit;
+	const int unit = item / a.attn_nsplit, split = item % a.attn_nsplit;
+	const int kvh = unit / a.attn_qgroups;
+	const int chunk = (tp.kv_len + a.attn_nsplit - 1) / a.attn_nsplit;
+	const int t0 = split * chunk, t1 = min(tp.kv_len, t0 + chunk);
+	const int kvrow = a.head_dim * 2;                       // bytes per cached position
+	const int TP = a.slot_bytes / (2 * kvrow) < 64 ? a.slot_bytes / (2 * kvrow) : 64; // positions per tile (K + V)
+	const size_t kv_layer = (size_t)a.n_kv_heads * a.seq_len * a.head_dim;
+
+	// ================================================================= producer warp
+	if (warp == FUSED_NCW) {
+		if (lane != 0) return;
+		const int nv_dim = a.dim / VW, nv_q = a.q_dim / VW, nv_hid = a.hidden / VW;
+		const int rb_dim = nv_dim * 16, rb_q = nv_q * 16, rb_hid = nv_hid * 16; // bytes per row
+		const int R_qkv = tile_rows(a.slot_bytes, 1, rb_dim, 2);
+		const int R_wo = tile_rows(a.slot_bytes, 1, rb_q, 1);
+		const int R_up = tile_rows(a.slot_bytes, 2, rb_dim, 1);
+		const int R_down = tile_rows(a.slot_bytes, 1, rb_hid, 1);
+		const int R_out = tile_rows(a.slot_bytes, 1, rb_dim, 1);
+		int q0, q1, k0, k1, o0, o1, h0, h1, c0, c1;
+		cta_range(a.q_dim / 2, q0, q1), q0 *= 2, q1 *= 2;
+		cta_range(a.kv_dim / 2, k0, k1), k0 *= 2, k1 *= 2;
+		cta_range(a.dim, o0, o1);
+		cta_range(a.hidden, h0, h1);
+		cta_range(a.vocab, c0, c1);
+
+		Producer p;
+		p.sh = sh, p.ring = ring, p.slot_bytes = a.slot_bytes, p.err = a.err;
+		p.rp.init(a.nslots);
+		p.pol_w = l2_policy_evict_first();
+		p.pol_kv = l2_policy_evict_last();
+		for (int l = 0; l < a.n_layers; ++l) {
+			const FusedLayer& L = c_fused_layers[l];
+			p.matrix(L.wq, nullptr, rb_dim, q0, q1, R_qkv);
+			p.matrix(L.wk, nullptr, rb_dim, k0, k1, R_qkv);
+			p.matrix(L.wv, nullptr, rb_dim, k0, k1, R_qkv);
+			if (has_item) {
+				const char* kb = (const char*)(a.kc + l * kv_layer + (size_t)kvh * a.seq_len * a.head_dim);
+				const char* vb = (const char*)(a.vc + l * kv_layer + (size_t)kvh * a.seq_len * a.head_dim);
+				for (int t_ = t0; t_ < t1; t_ += TP) {
+					uint32_t bytes = (uint32_t)min(TP, t1 - t_) * kvrow;
+					SPIN_WAIT(mbar_try_wait(&sh->empty[p.rp.slot], p.rp.phase ^ 1), a.err, 102);
+					mbar_expect_tx(&sh->full[p.rp.slot], 2 * bytes);
+					char* dst = ring + (size_t)p.rp.slot * a.slot_bytes;
+					tma_load_1d(dst, kb + (size_t)t_ * kvrow, bytes, &sh->full[p.rp.slot], p.pol_kv);
+					tma_load_1d(dst + (size_t)TP * kvrow, vb + (size_t)t_ * kvrow, bytes, &sh->full[p.rp.slot], p.pol_kv);
+					p.rp.advance();
+				}
+			}
+			p.matrix(L.wo, nullptr, rb_q, o0, o1, R_wo);
+			p.matrix(L.w1, L.w3, rb_dim, h0, h1, R_up);
+			p.matrix(L.w2, nullptr, rb_hid, o0, o1, R_down);
+		}
+		if (a.mode != 0) p.matrix(a.wcls, nullptr, rb_dim, c0, c1, R_out);
+		return;
+	}
+
+	// ================================================================= consumer warps
+	StageCtx cx;
+	cx.sh = sh, cx.ring = ring, cx.attn_scratch = attn_scratch, cx.warp = warp, cx.lane = lane;
+	RingPos rp;
+	rp.init(a.nslots);
+
+	for (int l = 0; l < a.n_layers; ++l) {
+		rp = stage_qkv<DBITS, XR>(a, cx, rp, l, tp);
+
+		// stage 2: attention over the cache (K/V tiles from the ring)
+		if (has_item) {
+			const __half* kc_l = a.kc + l * kv_layer;
+			const __half* vc_l = a.vc + l * kv_layer;
+			switch (a.attn_hg) {
+			case 1: rp = fused_attention<1>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			case 2: rp = fused_attention<2>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			case 3: rp = fused_attention<3>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			case 4: rp = fused_attention<4>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			case 5: rp = fused_attention<5>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			case 6: rp = fused_attention<6>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			case 7: rp = fused_attention<7>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			default: rp = fused_attention<8>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			}
+		}
+		stage_barrier(a, 302);
+
+		rp = stage_wo<DBITS, XR>(a, cx, rp, l, tp.token);
+		rp = stage_up<DBITS, XR>(a, cx, rp, l);
+		rp = stage_down<DBITS, XR>(a, cx, rp);
+	}
+	if (a.mode != 0) rp = stage_out<DBITS, XR>(a, cx, rp);
+}
