@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--layers", type=int, default=None, help="(debug) override the layer count")
+    ap.add_argument("--pos0", type=int, default=None, help="(debug) first timed position instead of the end of the context")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -224,6 +225,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    os.environ.setdefault("CALM_B200_QUIET", "1")  # keep stdout to the one JSON line
     cbuild.build()
     L = lib.load()
     seq_len = 4096
@@ -231,7 +233,7 @@ def main():
     torch.cuda.synchronize()
     dm = lib.DeviceModel(spec, tensors, seq_len=seq_len, device=local, engine=args.engine)
     K, W = args.steps, args.warmup
-    pos0 = max(0, seq_len - (K + W))
+    pos0 = max(0, seq_len - (K + W)) if args.pos0 is None else args.pos0
     dm.fill_kv(min(pos0, seq_len), seed=1 + rank)
 
     alg_bytes = mg.algorithmic_bytes(spec)
@@ -273,7 +275,7 @@ def main():
 
     # ---- roofline of the dominant kernel
     peak, peak_src = measured_peak()
-    roof = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src)
+    roof = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src, ms / K, bytes_per_tok)
 
     out = {
         "metric": "tok/s single-batch decode", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -282,7 +284,7 @@ def main():
         "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": spec.vocab_size * 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         "algorithmic_gb_per_token": bytes_per_tok / 1e9, "hbm_gbs_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3),
-        "frac_of_peak_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3) / peak, "engine": os.environ.get("CALM_B200_ENGINE", args.engine),
+        "frac_of_peak_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3) / peak, "engine": "fused" if dm.uses_fused() else "staged",
     }
     dm.close()
 
@@ -301,17 +303,28 @@ def main():
         dist.destroy_process_group()
 
 
-def dm_roofline(dm, L, spec, pos, peak, peak_src):
-    """Dominant kernel = the stage with the largest share of the token's time.  Durations are measured
-    live with CUDA events around every launch on the library's stream (an eager pass of 8 tokens after the
-    timed legs); achieved = that stage's algorithmic bytes per launch (rows x cols x
-    dbits/8) / mean launch duration."""
-    stats = dm.profile(23, pos, 8)
-    total_ms = sum(v[0] for v in stats.values())
-    name, (ms, by, nl) = max(stats.items(), key=lambda kv: kv[1][0])
-    achieved = by / 1e9 / (ms / 1e3) if ms > 0 else None
-    table = {k: {"share": v[0] / total_ms, "us_per_launch": v[0] / max(v[2], 1) * 1e3, "gbs": (v[1] / 1e9 / (v[0] / 1e3)) if v[0] > 0 else None}
+def dm_roofline(dm, L, spec, pos, peak, peak_src, ms_per_tok, bytes_per_tok):
+    """Roofline of the dominant kernel.
+
+    Fused engine: ONE kernel (k_fused) runs the whole token, so the dominant kernel is that launch:
+    achieved = algorithmic bytes per launch (n_bandwidth + KV bytes, reference run.c:161-165, 523-532) /
+    mean launch duration, measured live with CUDA events over the timed region of leg 1.  The per-stage
+    table comes from %globaltimer stamps inside the kernel (8 extra tokens after the timed legs).
+    Staged engine: the dominant kernel is the stage with the largest share of the token's time, timed with
+    CUDA events around every launch (8 eager tokens)."""
+    fused = dm.uses_fused()
+    stats = dm.profile(23, pos, 8, mode=2 if fused else 1)
+    total_ms = sum(v[0] for v in stats.values()) or 1.0
+    table = {k: {"share": v[0] / total_ms, "us_per_launch": v[0] / max(v[2], 1) * 1e3, "gbs": (v[1] / 1e9 / (v[0] / 1e3)) if v[0] > 0 else None,
+                 "barrier_wait_us": v[3] / max(v[2], 1) * 1e3}
              for k, v in stats.items()}
+    if fused:
+        achieved = bytes_per_tok / 1e9 / (ms_per_tok / 1e3)
+        return {"bound": "hbm", "kernel": "k_fused (persistent: all layers + classifier of one token)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_tok, "us_per_launch": ms_per_tok * 1e3,
+                "stages": table}
+    name, (ms, by, nl, _) = max(stats.items(), key=lambda kv: kv[1][0])
+    achieved = by / 1e9 / (ms / 1e3) if ms > 0 else None
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
             "traffic": None, "peak_source": peak_src, "bytes_per_launch": by / max(nl, 1), "us_per_launch": ms / max(nl, 1) * 1e3, "stages": table}
 

@@ -69,6 +69,8 @@ struct Engine {
 	int fused_nsplit = 1;
 	unsigned* fused_bar = nullptr;
 	int* fused_err = nullptr; // pinned + mapped
+	unsigned long long* fused_perf_ns = nullptr; // device [16]
+	bool fused_perf = false;
 	cudaGraphExec_t fgraph[4] = {nullptr, nullptr, nullptr, nullptr};
 	int fgraph_launches[4] = {0, 0, 0, 0};
 
@@ -83,6 +85,7 @@ struct Engine {
 	double stage_ms[ST_COUNT] = {};
 	double stage_bytes[ST_COUNT] = {};
 	long stage_launches[ST_COUNT] = {};
+	double stage_wait_ms[ST_COUNT] = {}; // fused engine: part of stage_ms spent waiting in the grid barrier
 	int perf_runs = 0;
 	cudaEvent_t ev[2] = {nullptr, nullptr};
 	cudaEvent_t timer[2] = {nullptr, nullptr};
@@ -264,7 +267,7 @@ int run_token(int mode) {
 		k_output<DBITS><<<grid, 256, g.smem_dim, g.stream>>>(a);
 		++nl;
 		if (mode >= 2) {
-			k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, grid, g.tp, g.out_tokens, g.last_token, mode == 2);
+			k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, grid, g.tp, g.out_tokens, g.last_token, mode == 2, c.vocab_size);
 			++nl;
 		}
 	}
@@ -393,6 +396,8 @@ void fused_plan() {
 	CUDA_CHECK(cudaMemset(g.fused_bar, 0, sizeof(unsigned)));
 	CUDA_CHECK(cudaHostAlloc((void**)&g.fused_err, sizeof(int), cudaHostAllocMapped));
 	*g.fused_err = 0;
+	g.fused_perf_ns = (unsigned long long*)dev_alloc(16 * sizeof(unsigned long long));
+	CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 16 * sizeof(unsigned long long)));
 	g.fused_attr_set = false;
 	FusedArgs none = {};
 	fused_launch(none); // sets the shared-memory opt-in outside of any stream capture
@@ -411,8 +416,10 @@ int run_token_fused(int mode) {
 	fa.kc = (__half*)g.kc, fa.vc = (__half*)g.vc, fa.rope_freq = g.rope_freq;
 	fa.embed = g.w.token_embedding_table, fa.wcls = g.w.wcls, fa.rms_final = g.w.rms_final_weight;
 	fa.tp = g.tp, fa.bar = g.fused_bar, fa.err = g.fused_err;
+	fa.perf = g.fused_perf ? g.fused_perf_ns : nullptr;
 	fa.cand_val = (mode >= 2) ? g.cand_val : nullptr, fa.cand_idx = g.cand_idx;
 	fa.mode = mode;
+	fa.dbg = getenv("CALM_B200_FUSED_DBG") ? atoi(getenv("CALM_B200_FUSED_DBG")) : 0;
 	fa.slot_bytes = g.fused_slot_bytes, fa.nslots = g.fused_nslots;
 	fa.attn_nsplit = g.fused_nsplit, fa.attn_hg = g.attn_hg, fa.attn_qgroups = g.attn_qgroups, fa.attn_lpp = g.attn_lpp;
 	fa.attn_scratch_bytes = g.fused_scratch;
@@ -420,18 +427,33 @@ int run_token_fused(int mode) {
 	fused_launch(fa);
 	int nl = 1;
 	if (mode >= 2) {
-		k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, g.sms, g.tp, g.out_tokens, g.last_token, mode == 2);
+		k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, g.sms, g.tp, g.out_tokens, g.last_token, mode == 2, c.vocab_size);
 		++nl;
 	}
 	return nl;
 }
 
+// per-stage algorithmic bytes of one token (the reference's accounting, infer.cu:683-699)
+void account_fused_bytes(int mode) {
+	const Config& c = g.cfg;
+	const double wb = g.w.dbits / 8.0, L = c.n_layers;
+	g.stage_bytes[ST_QKV] += L * (g.q_dim + 2.0 * g.kv_dim) * c.dim * wb;
+	g.stage_bytes[ST_ATTN] += L * 2.0 * g.kv_dim * g.cur_kv_len * (g.kvbits / 8);
+	g.stage_bytes[ST_WO] += L * (double)c.dim * g.q_dim * wb;
+	g.stage_bytes[ST_FFN_UP] += L * 2.0 * g.nact * c.hidden_dim * c.dim * wb;
+	g.stage_bytes[ST_FFN_DOWN] += L * 1.0 * g.nact * c.hidden_dim * c.dim * wb;
+	g.stage_launches[ST_QKV] += c.n_layers, g.stage_launches[ST_ATTN] += c.n_layers, g.stage_launches[ST_WO] += c.n_layers;
+	g.stage_launches[ST_FFN_UP] += c.n_layers, g.stage_launches[ST_FFN_DOWN] += c.n_layers;
+	if (mode != 0) g.stage_bytes[ST_OUTPUT] += (double)c.vocab_size * c.dim * wb, g.stage_launches[ST_OUTPUT] += 1;
+}
+
 void launch_token(int mode) {
 	// the persistent kernel serves every token it can; the rest (MoE, fp8 KV, rolled-over cache,
 	// per-stage profiling) goes through the staged engine.  Both are CUDA paths over the same buffers.
-	const bool fused = g.engine == 1 && g.fused_ok && !g.perf && !g.debug_stages && g.cur_pos < g.cfg.seq_len;
+	const bool fused = g.engine == 1 && g.fused_ok && (!g.perf || g.fused_perf) && !g.debug_stages && g.cur_pos < g.cfg.seq_len;
 	if (fused) {
-		if (!g.use_graph) {
+		if (!g.use_graph || g.fused_perf) {
+			if (g.fused_perf) account_fused_bytes(mode);
 			g_launches += run_token_fused(mode);
 			CUDA_CHECK(cudaGetLastError());
 			return;
@@ -485,6 +507,10 @@ extern "C" void calm_b200_set_device(int device) {
 	g_device_override = device;
 }
 
+extern "C" int calm_b200_engine_in_use(void) {
+	return g.ready && g.engine == 1 && g.fused_ok ? 1 : 0;
+}
+
 extern "C" void calm_b200_set_engine(int engine) {
 	g_engine_kind = engine;
 }
@@ -536,6 +562,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
 	if (g.debug) g.use_graph = false, g.debug_stages = true;
 	g.perf = (getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF"))) || getenv("CUDA_INJECTION64_PATH");
+	const bool want_fused_perf = getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF")) == 2;
 
 	CUDA_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; ++i) {
@@ -608,6 +635,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
 
 	if (g.engine == 1) fused_plan();
+	g.fused_perf = want_fused_perf && g.fused_ok;
 
 	// what the reference backend publishes in RunState (infer.cu:99-112)
 	s->x = g.x, s->hb = g.hb, s->he = g.hb, s->q = g.q, s->att = g.att;
@@ -626,6 +654,7 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 		if (g.fgraph[i]) CUDA_CHECK(cudaGraphExecDestroy(g.fgraph[i]));
 	}
 	if (g.fused_bar) cudaFree(g.fused_bar);
+	if (g.fused_perf_ns) cudaFree(g.fused_perf_ns);
 	if (g.fused_err) cudaFreeHost(g.fused_err);
 	cudaFree(g.x), cudaFree(g.xb), cudaFree(g.q), cudaFree(g.att), cudaFree(g.hb), cudaFree(g.logits_dev);
 	cudaFreeHost(g.logits_host), cudaFreeHost(g.last_token);
@@ -795,8 +824,20 @@ extern "C" float calm_b200_matvec(int dbits, const void* w_device, const float* 
 	return 0.f;
 }
 
+// Pull the in-kernel stage timers of the fused engine into the host-side tables.
+static void fused_perf_collect() {
+	if (!g.fused_perf || !g.fused_perf_ns) return;
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	unsigned long long ns[16];
+	CUDA_CHECK(cudaMemcpy(ns, g.fused_perf_ns, sizeof(ns), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < ST_COUNT; ++i) g.stage_ms[i] = (double)(ns[i] + ns[8 + i]) / 1e6, g.stage_wait_ms[i] = (double)ns[8 + i] / 1e6;
+}
+
 extern "C" void calm_b200_set_perf(int on) {
+	if (!on) fused_perf_collect();
 	g.perf = on != 0;
+	g.fused_perf = on == 2 && g.fused_ok;
+	if (g.fused_perf_ns) CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 16 * sizeof(unsigned long long)));
 	if (!on) return;
 	for (int i = 0; i < ST_COUNT; ++i) g.stage_ms[i] = 0, g.stage_bytes[i] = 0, g.stage_launches[i] = 0;
 	g.perf_runs = 0;
@@ -808,18 +849,51 @@ extern "C" int calm_b200_stage_stats(int stage, char* name, int name_cap, double
 		strncpy(name, kStageNames[stage], name_cap - 1);
 		name[name_cap - 1] = 0;
 	}
+	if (g.fused_perf) fused_perf_collect();
 	*ms_total = g.stage_ms[stage], *bytes_total = g.stage_bytes[stage], *launches = g.stage_launches[stage];
 	return 1;
 }
 
+extern "C" double calm_b200_stage_wait_ms(int stage) {
+	if (stage < 0 || stage >= ST_COUNT) return 0;
+	if (g.fused_perf) fused_perf_collect();
+	return g.stage_wait_ms[stage];
+}
+
+extern "C" float calm_b200_barrier_bench(int rounds) {
+	select_device();
+	cudaDeviceProp prop;
+	CUDA_CHECK(cudaGetDeviceProperties(&prop, g.device));
+	unsigned* bar;
+	int* err;
+	unsigned long long* ns;
+	CUDA_CHECK(cudaMalloc(&bar, sizeof(unsigned)));
+	CUDA_CHECK(cudaMalloc(&err, sizeof(int)));
+	CUDA_CHECK(cudaMalloc(&ns, sizeof(unsigned long long)));
+	CUDA_CHECK(cudaMemset(bar, 0, sizeof(unsigned)));
+	CUDA_CHECK(cudaMemset(err, 0, sizeof(int)));
+	void* args[] = {&bar, &err, &rounds, &ns};
+	CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_barrier_bench, dim3(prop.multiProcessorCount), dim3(FUSED_THREADS), args, 0, 0));
+	CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_barrier_bench, dim3(prop.multiProcessorCount), dim3(FUSED_THREADS), args, 0, 0));
+	CUDA_CHECK(cudaDeviceSynchronize());
+	unsigned long long h = 0;
+	CUDA_CHECK(cudaMemcpy(&h, ns, sizeof(h), cudaMemcpyDeviceToHost));
+	cudaFree(bar), cudaFree(err), cudaFree(ns);
+	g_launches += 2;
+	return (float)((double)h / 1e3 / rounds); // microseconds per barrier
+}
+
 extern "C" void perf_cuda(void) {
 	if (!g.ready || !g.perf || g.perf_runs == 0) return;
+	fused_perf_collect();
 	double total = 0;
 	for (int i = 0; i < ST_COUNT; ++i) total += g.stage_ms[i];
 	printf("\nforward breakdown (over %d runs, avg %.1f usec/run):\n", g.perf_runs, total / g.perf_runs * 1e3);
 	for (int i = 0; i < ST_COUNT; ++i) {
 		if (g.stage_ms[i] == 0) continue;
-		printf("\t[%d] %16s: %4.1f%%; %8.1f usec/run, %6.1f GB/s\n", i, kStageNames[i], g.stage_ms[i] / total * 100, g.stage_ms[i] / g.perf_runs * 1e3,
+		printf("\t[%d] %16s: %4.1f%%; %8.1f usec/run, %6.1f GB/s", i, kStageNames[i], g.stage_ms[i] / total * 100, g.stage_ms[i] / g.perf_runs * 1e3,
 		       g.stage_bytes[i] / 1e9 / (g.stage_ms[i] / 1e3));
+		if (g.fused_perf) printf(" (grid-barrier wait %.1f usec/run)", g.stage_wait_ms[i] / g.perf_runs * 1e3);
+		printf("\n");
 	}
 }

@@ -53,9 +53,11 @@ struct FusedArgs {
 	const TokenParams* tp;
 	unsigned* bar; // grid barrier word
 	int* err;      // watchdog report: nonzero = which wait timed out
+	unsigned long long* perf; // optional [2][8] ns: per stage {busy, barrier wait} seen by CTA 0 (cf. reference coopstage, infer.cu:390-402)
 	float* cand_val;
 	int* cand_idx;
 	int mode;      // 0 kv only, >= 1 logits (cand_val != NULL: also greedy candidates)
+	int dbg;       // experiments (results are wrong): 1 = consumers skip the math, 2 = producer skips the copies
 	int slot_bytes, nslots;
 	int attn_nsplit, attn_hg, attn_qgroups, attn_lpp, attn_scratch_bytes;
 	float inv_sqrt_hd;
@@ -153,34 +155,54 @@ struct FusedShared {
 	uint64_t empty[FUSED_MAX_SLOTS]; // consumers -> producer: tile consumed (FUSED_NCW arrivals)
 	int cnt[FUSED_MAX_SLOTS];        // warps done with the tile in this slot (last one finalises)
 	float red[FUSED_MAX_SLOTS][32][FUSED_NCW]; // per-row, per-warp partial sums
+	float rope_cos[128], rope_sin[128];        // cos/sin(pos * freq[i]) of this token (head_dim <= 256)
 	float scratch[64];               // block reductions
-	float best_val[FUSED_NCW];       // greedy candidates per finalising warp
+	float best_val[FUSED_NCW];       // greedy candidates per warp
 	int best_idx[FUSED_NCW];
 	int flag;
 };
 
 // ---------------------------------------------------------------- tile schedule (shared by producer and consumers)
 
-struct Tile {
-	const char* src[2];
-	uint32_t seg_bytes; // bytes per segment
-	int nseg;
-	int rows;           // rows per segment
-	int row0;           // first row (index within its matrix)
-};
-
 __device__ __forceinline__ void cta_range(int units, int& u0, int& u1) {
 	u0 = (int)(((long long)blockIdx.x * units) / gridDim.x);
 	u1 = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x);
 }
 
-// rows per tile for a matrix stage
-__device__ __forceinline__ int tile_rows(int slot_bytes, int nseg, int rowbytes, int unit) {
+// How the 8 consumer warps share a row of `nvec` 16-byte vectors: the smallest power-of-two number of
+// warps per row (wg) that keeps the vectors per thread (it) within the register budget; the remaining
+// factor (ng = 8 / wg warp groups) works on different rows of a tile at the same time.
+struct RowMap {
+	int wg, ng, it, tg; // warps per group, groups, vectors per thread, threads per group
+};
+template <int DBITS, int XR>
+__device__ __forceinline__ RowMap row_map(int nvec) {
+	constexpr int ITMAX = XR / WFmt<DBITS>::VW;
+	RowMap m;
+	m.wg = 1;
+	while ((nvec + m.wg * 32 - 1) / (m.wg * 32) > ITMAX && m.wg < FUSED_NCW) m.wg *= 2;
+	m.ng = FUSED_NCW / m.wg;
+	m.tg = m.wg * 32;
+	m.it = (nvec + m.tg - 1) / m.tg;
+	return m;
+}
+
+// rows per tile (per segment): as many as fit the slot, at most FUSED_NP rows per warp group and tile,
+// at most 32 rows in all, a multiple of `unit`
+#define FUSED_NP 2
+__device__ __forceinline__ int tile_rows(int slot_bytes, int nseg, int rowbytes, int unit, int ng) {
 	int r = slot_bytes / (nseg * rowbytes);
 	if (r > 32 / nseg) r = 32 / nseg;
+	if (r > FUSED_NP * ng / nseg) r = FUSED_NP * ng / nseg;
 	r -= r % unit;
 	return r < unit ? unit : r;
 }
+
+// A matrix stage streams up to three row ranges (q | k | v) of matrices with the same row length.
+struct StageRanges {
+	int n;
+	int r0[3], r1[3];
+};
 
 // Ring bookkeeping common to both sides: slot index and phase of the k-th tile of this CTA.
 struct RingPos {
@@ -202,50 +224,32 @@ struct Producer {
 	RingPos rp;
 	uint64_t pol_w, pol_kv;
 	int* err;
+	int dbg;
 
-	__device__ __forceinline__ void push(const Tile& t) {
+	// one tile = one ring slot: `bytes` from src0 (and from src1, placed at dst + off1)
+	__device__ __forceinline__ void push(const char* src0, const char* src1, uint32_t bytes, uint32_t off1, uint64_t policy) {
 		SPIN_WAIT(mbar_try_wait(&sh->empty[rp.slot], rp.phase ^ 1), err, 101);
-		mbar_expect_tx(&sh->full[rp.slot], t.seg_bytes * t.nseg);
-		char* dst = ring + (size_t)rp.slot * slot_bytes;
-		tma_load_1d(dst, t.src[0], t.seg_bytes, &sh->full[rp.slot], pol_w);
-		if (t.nseg == 2) tma_load_1d(dst + t.seg_bytes, t.src[1], t.seg_bytes, &sh->full[rp.slot], pol_w);
+		if (dbg & 2) {
+			mbar_arrive(&sh->full[rp.slot]);
+		} else {
+			mbar_expect_tx(&sh->full[rp.slot], src1 ? 2 * bytes : bytes);
+			char* dst = ring + (size_t)rp.slot * slot_bytes;
+			tma_load_1d(dst, src0, bytes, &sh->full[rp.slot], policy);
+			if (src1) tma_load_1d(dst + off1, src1, bytes, &sh->full[rp.slot], policy);
+		}
 		rp.advance();
 	}
 
 	// all tiles of rows [r0, r1) of one matrix (or of two matrices read in lock step)
 	__device__ __forceinline__ void matrix(const void* w0, const void* w1, int rowbytes, int r0, int r1, int R) {
-		Tile t;
-		t.nseg = w1 ? 2 : 1;
 		for (int a = r0; a < r1; a += R) {
-			int rows = min(R, r1 - a);
-			t.src[0] = (const char*)w0 + (size_t)a * rowbytes;
-			t.src[1] = w1 ? (const char*)w1 + (size_t)a * rowbytes : nullptr;
-			t.seg_bytes = (uint32_t)rows * rowbytes;
-			t.rows = rows, t.row0 = a;
-			push(t);
+			uint32_t bytes = (uint32_t)min(R, r1 - a) * rowbytes;
+			push((const char*)w0 + (size_t)a * rowbytes, w1 ? (const char*)w1 + (size_t)a * rowbytes : nullptr, bytes, bytes, pol_w);
 		}
 	}
 };
 
 // ---------------------------------------------------------------- consumer: matvec over ring tiles
-
-// How the 8 consumer warps share a row of `nvec` 16-byte vectors: WG warps per row (power of two),
-// IT vectors per thread.
-struct RowMap {
-	int wg, ng, it, tg; // warps per group, groups, vectors per thread, threads per group
-};
-template <int DBITS, int XR>
-__device__ __forceinline__ RowMap row_map(int nvec) {
-	constexpr int ITMAX = XR / WFmt<DBITS>::VW;
-	RowMap m;
-	m.wg = 1;
-	while (m.wg < FUSED_NCW && (nvec + m.wg * 32 - 1) / (m.wg * 32) > ITMAX / 2) m.wg *= 2; // aim at half the register budget...
-	while ((nvec + m.wg * 32 - 1) / (m.wg * 32) > ITMAX && m.wg < FUSED_NCW) m.wg *= 2;         // ...but never exceed it
-	m.ng = FUSED_NCW / m.wg;
-	m.tg = m.wg * 32;
-	m.it = (nvec + m.tg - 1) / m.tg;
-	return m;
-}
 
 template <int DBITS, int XR>
 struct Consumer {
@@ -257,17 +261,24 @@ struct Consumer {
 	const char* ring;
 	int slot_bytes;
 	int* err;
+	int dbg;
 	int cw, lane; // consumer warp 0..7
-	float best_v;
-	int best_i;   // greedy candidate seen by this thread (classifier stage)
 	float xr[ITMAX][VW];
 
+	// sum over all 256 consumer threads (every thread gets it)
+	__device__ __forceinline__ float block_total(float v) {
+		v = warp_sum(v);
+		consumer_sync();
+		if (lane == 0) sh->scratch[cw] = v;
+		consumer_sync();
+		float r = lane < FUSED_NCW ? sh->scratch[lane] : 0.f;
+		return warp_sum(r);
+	}
+
 	// --- activation slice into registers -------------------------------------------------------
-	// xin: global vector written by other CTAs in this launch (read through L2), or, for layer 0, the
-	// embedding row (decoded here).  Optional norm (reference infer.c:183-207).
-	template <bool EMBED>
-	__device__ __forceinline__ void load_x(const RowMap& m, const float* xin, const void* table, int token, int n, const float* normw, float eps, bool ln,
-	                                       float* xb_out) {
+	// xin: global vector written by other CTAs in this launch (read through L2).  Optional norm
+	// (reference infer.c:183-207).
+	__device__ __forceinline__ void load_x(const RowMap& m, const float* xin, int n, const float* normw, float eps, bool ln, float* xb_out) {
 		const int nvec = n / VW;
 		const int tgi = (cw % m.wg) * 32 + lane;
 		float ssum = 0.f, ssq = 0.f;
@@ -278,15 +289,7 @@ struct Consumer {
 #pragma unroll
 			for (int q = 0; q < Q; ++q) {
 				float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (ok) {
-					if (EMBED) {
-						size_t base = (size_t)token * n + (size_t)v * VW + q * 4;
-						f.x = weight_at<DBITS>(table, base), f.y = weight_at<DBITS>(table, base + 1);
-						f.z = weight_at<DBITS>(table, base + 2), f.w = weight_at<DBITS>(table, base + 3);
-					} else {
-						f = __ldcg(reinterpret_cast<const float4*>(xin + (size_t)v * VW) + q);
-					}
-				}
+				if (ok) f = __ldcg(reinterpret_cast<const float4*>(xin + (size_t)v * VW) + q);
 				xr[it][q * 4 + 0] = f.x, xr[it][q * 4 + 1] = f.y, xr[it][q * 4 + 2] = f.z, xr[it][q * 4 + 3] = f.w;
 				ssum += (f.x + f.y) + (f.z + f.w);
 			}
@@ -323,94 +326,92 @@ struct Consumer {
 		}
 	}
 
-	// sum over all 256 consumer threads (every thread gets it)
-	__device__ __forceinline__ float block_total(float v) {
-		v = warp_sum(v);
-		consumer_sync();
-		if (lane == 0) sh->scratch[cw] = v;
-		consumer_sync();
-		float r = lane < FUSED_NCW ? sh->scratch[lane] : 0.f;
-		return warp_sum(r);
-	}
-
 	// --- one matrix stage ---------------------------------------------------------------------
-	// Consumes the tiles the producer pushed for rows [r0, r1) (R rows per tile, nseg segments).
-	// epi(row, v0, v1): called by one lane per row (v1 = second segment's value when nseg == 2); for
-	// PAIR stages it is called once per even row with (row, value(row), value(row + 1)).
-	template <int IT, bool PAIR, typename Epi>
-	__device__ __forceinline__ void matrix_it(RingPos& rp, const RowMap& m, int nvec, int nseg, int r0, int r1, int R, Epi epi) {
+	// Consumes the tiles the producer pushed for the row ranges of `rg` (R rows per tile, nseg segments).
+	// epi(range, row, v0, v1): called by one lane per row (v1 = second segment's value when nseg == 2); for
+	// PAIR stages it is called once per even row with (range, row, value(row), value(row + 1)).
+	template <typename Epi>
+	__device__ __forceinline__ void matrix(RingPos& rp, const RowMap& m, int nvec, int nseg, bool PAIR, const StageRanges& rg, int R, Epi epi) {
+		constexpr int NP = FUSED_NP;
 		const int grp = cw / m.wg, wig = cw % m.wg;
 		const int tgi = wig * 32 + lane;
 		const int rowbytes = nvec * 16;
-		for (int a = r0; a < r1; a += R) {
-			const int rows = min(R, r1 - a);
-			const int vrows = rows * nseg;
-			SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), err, 201);
-			const char* tile = ring + (size_t)rp.slot * slot_bytes;
-			for (int vr = grp; vr < vrows; vr += m.ng) {
-				const uint4* rowp = reinterpret_cast<const uint4*>(tile + (size_t)vr * rowbytes);
-				uint4 w[IT];
+		for (int ri = 0; ri < rg.n; ++ri) {
+			for (int a = rg.r0[ri]; a < rg.r1[ri]; a += R) {
+				const int rows = min(R, rg.r1[ri] - a);
+				const int vrows = rows * nseg; // <= NP * ng by construction of R
+				SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), err, 201);
+				const char* tile = ring + (size_t)rp.slot * slot_bytes;
+				if (!(dbg & 1)) {
+					// this group's rows of the tile: vr = grp + k * ng.  All loads first, then the math, then one
+					// transposing shuffle reduction for the NP row sums (zero weights contribute exactly 0).
+					uint4 w[NP][ITMAX];
 #pragma unroll
-				for (int it = 0; it < IT; ++it) { // all loads first (zero weights contribute exactly 0)
-					int v = tgi + it * m.tg;
-					w[it] = v < nvec ? lds128(rowp + v) : make_uint4(0, 0, 0, 0);
-				}
-				float acc0 = 0.f, acc1 = 0.f;
+					for (int k = 0; k < NP; ++k) {
+						const int vr = grp + k * m.ng;
+						const uint4* rowp = reinterpret_cast<const uint4*>(tile + (size_t)vr * rowbytes);
 #pragma unroll
-				for (int it = 0; it < IT; ++it) {
-					float4 xv[Q];
+						for (int it = 0; it < ITMAX; ++it) {
+							int v = tgi + it * m.tg;
+							w[k][it] = (vr < vrows && it < m.it && v < nvec) ? lds128(rowp + v) : make_uint4(0, 0, 0, 0);
+						}
+					}
+					float acc[NP];
 #pragma unroll
-					for (int q = 0; q < Q; ++q) xv[q] = make_float4(xr[it][q * 4], xr[it][q * 4 + 1], xr[it][q * 4 + 2], xr[it][q * 4 + 3]);
-					if (it & 1)
-						acc1 = dot_vec<DBITS>(w[it], xv, acc1);
-					else
-						acc0 = dot_vec<DBITS>(w[it], xv, acc0);
+					for (int k = 0; k < NP; ++k) acc[k] = 0.f;
+#pragma unroll
+					for (int it = 0; it < ITMAX; ++it) {
+						if (it < m.it) { // uniform
+							float4 xv[Q];
+#pragma unroll
+							for (int q = 0; q < Q; ++q) xv[q] = make_float4(xr[it][q * 4], xr[it][q * 4 + 1], xr[it][q * 4 + 2], xr[it][q * 4 + 3]);
+#pragma unroll
+							for (int k = 0; k < NP; ++k)
+								if (grp + k * m.ng < vrows) acc[k] = dot_vec<DBITS>(w[k][it], xv, acc[k]); // uniform
+						}
+					}
+					// two sums -> lanes 0 and 16 (5 shuffles instead of 10)
+					{
+						const bool hi = lane & 16;
+						float c = (hi ? acc[1] : acc[0]) + __shfl_xor_sync(0xffffffffu, hi ? acc[0] : acc[1], 16);
+						c += __shfl_xor_sync(0xffffffffu, c, 8);
+						c += __shfl_xor_sync(0xffffffffu, c, 4);
+						c += __shfl_xor_sync(0xffffffffu, c, 2);
+						c += __shfl_xor_sync(0xffffffffu, c, 1);
+						const int vr = grp + (lane >> 4) * m.ng;
+						if ((lane & 15) == 0 && vr < vrows) sh->red[rp.slot][vr][wig] = c;
+					}
 				}
-				float acc = warp_sum(acc0 + acc1);
-				if (lane == 0) sh->red[rp.slot][vr][wig] = acc;
-			}
-			// this warp is done reading the tile; find out whether it is the last one
-			__syncwarp();
-			int last = 0;
-			if (lane == 0) {
-				__threadfence_block();
-				last = atomicAdd(&sh->cnt[rp.slot], 1) == FUSED_NCW - 1;
-			}
-			last = __shfl_sync(0xffffffffu, last, 0);
-			if (last) {
-				__threadfence_block();
-				if (lane == 0) sh->cnt[rp.slot] = 0;
-				// fold the per-warp partials in a fixed order and run the epilogue
-				const int nrow_calls = PAIR ? rows / 2 : rows;
-				for (int i = lane; i < nrow_calls; i += 32) {
-					int r = PAIR ? 2 * i : i;
-					float v0 = 0.f, v1 = 0.f;
-					const int ra = r, rb = PAIR ? r + 1 : rows + r; // second value: next row, or same row of segment 2
-					for (int w_ = 0; w_ < m.wg; ++w_) v0 += sh->red[rp.slot][ra][w_];
-					if (PAIR || nseg == 2)
-						for (int w_ = 0; w_ < m.wg; ++w_) v1 += sh->red[rp.slot][rb][w_];
-					epi(a + r, v0, v1);
-				}
+				// this warp is done reading the tile; find out whether it is the last one
 				__syncwarp();
+				int last = 0;
+				if (lane == 0) {
+					__threadfence_block();
+					last = atomicAdd(&sh->cnt[rp.slot], 1) == FUSED_NCW - 1;
+				}
+				last = __shfl_sync(0xffffffffu, last, 0);
+				if (last) {
+					__threadfence_block();
+					if (lane == 0) sh->cnt[rp.slot] = 0;
+					if (!(dbg & 1)) {
+						// fold the per-warp partials in a fixed order and run the epilogue
+						const int ncalls = PAIR ? rows / 2 : rows;
+						for (int i = lane; i < ncalls; i += 32) {
+							int r = PAIR ? 2 * i : i;
+							float v0 = 0.f, v1 = 0.f;
+							const int rb = PAIR ? r + 1 : rows + r; // second value: next row, or same row of segment 2
+							for (int w_ = 0; w_ < m.wg; ++w_) v0 += sh->red[rp.slot][r][w_];
+							if (PAIR || nseg == 2)
+								for (int w_ = 0; w_ < m.wg; ++w_) v1 += sh->red[rp.slot][rb][w_];
+							epi(ri, a + r, v0, v1);
+						}
+					}
+					__syncwarp();
+				}
+				if (lane == 0) mbar_arrive(&sh->empty[rp.slot]);
+				rp.advance();
 			}
-			if (lane == 0) mbar_arrive(&sh->empty[rp.slot]);
-			rp.advance();
 		}
-	}
-
-	// dispatch on the (power-of-two) number of vectors per thread so the inner loops are fully unrolled
-	template <bool PAIR, typename Epi>
-	__device__ __forceinline__ void matrix(RingPos& rp, const RowMap& m, int nvec, int nseg, int r0, int r1, int R, Epi epi) {
-		if (m.it <= 1)
-			matrix_it<1, PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
-		else if (ITMAX >= 2 && m.it <= 2)
-			matrix_it<(ITMAX >= 2 ? 2 : 1), PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
-		else if (ITMAX >= 4 && m.it <= 4)
-			matrix_it<(ITMAX >= 4 ? 4 : 1), PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
-		else if (ITMAX >= 8 && m.it <= 8)
-			matrix_it<(ITMAX >= 8 ? 8 : 1), PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
-		else
-			matrix_it<ITMAX, PAIR>(rp, m, nvec, nseg, r0, r1, R, epi);
 	}
 };
 
@@ -418,7 +419,7 @@ struct Consumer {
 // Same arithmetic as k_attn (stages.cuh).  One work item = (unit of HG query heads sharing a kv head,
 // slice [t0, t1) of positions).  K and V of 'TP' positions arrive per ring slot (K at the slot base, V at
 // TP * kvrow); the entry of the current step (written by stage 1 of this launch, possibly after the tile was
-// prefetched) is skipped in the tile and read through L2 instead.
+// prefetched) is skipped in the tiles and read through L2 in one extra pass instead.
 
 __device__ __forceinline__ void halves8(const uint4& r, float (&o)[8]) {
 	float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
@@ -430,7 +431,7 @@ __device__ __forceinline__ void halves8(const uint4& r, float (&o)[8]) {
 
 template <int HG>
 __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, FusedShared* sh, const char* ring, float* scratch, const TokenParams& tp,
-                                             const __half* kc_l, const __half* vc_l, int unit, int split, int kvh, int t0, int t1, int TP, int warp, int lane) {
+                                                const __half* kc_l, const __half* vc_l, int unit, int split, int kvh, int t0, int t1, int TP, int warp, int lane) {
 	constexpr int P = HG > 4 ? 2 : 4;
 	const int hd = a.head_dim, lpp = a.attn_lpp;
 	const int G = 32 / lpp;
@@ -438,6 +439,7 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 	const bool dact = li * 8 < hd;
 	const int kvrow = hd * 2;
 	const int hbase = kvh * a.kv_mul + (unit % a.attn_qgroups) * HG;
+	const int tid = warp * 32 + lane;
 
 	float qr[HG][8], acc[HG][8], m[HG], l[HG];
 #pragma unroll
@@ -453,82 +455,75 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 		for (int d = 0; d < 8; ++d) acc[h][d] = 0.f;
 	}
 
-	// online-softmax update with P (position, K, V) triples held by this lane group
-	auto update = [&](const float (&kf)[P][8], const float (&vf)[P][8], const bool (&ok)[P]) {
-#pragma unroll
-		for (int h = 0; h < HG; ++h) {
-			float s[P], smax = m[h];
-#pragma unroll
-			for (int i = 0; i < P; ++i) {
-				float d = 0.f;
-#pragma unroll
-				for (int e = 0; e < 8; ++e) d = fmaf(qr[h][e], kf[i][e], d);
-				for (int o = 1; o < lpp; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-				s[i] = ok[i] ? d * a.inv_sqrt_hd : -FLT_MAX;
-				smax = fmaxf(smax, s[i]);
-			}
-			float corr = expf(m[h] - smax);
-			m[h] = smax;
-			float pw[P], ps = 0.f;
-#pragma unroll
-			for (int i = 0; i < P; ++i) {
-				pw[i] = ok[i] ? expf(s[i] - smax) : 0.f;
-				ps += pw[i];
-			}
-			l[h] = fmaf(l[h], corr, ps);
-#pragma unroll
-			for (int e = 0; e < 8; ++e) {
-				float v = acc[h][e] * corr;
-#pragma unroll
-				for (int i = 0; i < P; ++i) v = fmaf(pw[i], vf[i][e], v);
-				acc[h][e] = v;
-			}
+	const bool fresh_here = tp.kv_pos >= t0 && tp.kv_pos < t1;
+	const int ntiles = t1 > t0 ? (t1 - t0 + TP - 1) / TP : 0;
+	for (int ti = 0; ti < ntiles + (fresh_here ? 1 : 0); ++ti) {
+		const bool fresh = ti == ntiles; // extra pass: the entry appended this step, straight from L2
+		const int tb = t0 + ti * TP;
+		const int np = fresh ? 1 : min(TP, t1 - tb);
+		const char *kt = nullptr, *vt = nullptr;
+		if (!fresh) {
+			SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), a.err, 202);
+			kt = ring + (size_t)rp.slot * a.slot_bytes;
+			vt = kt + (size_t)TP * kvrow;
 		}
-	};
-
-	for (int tb = t0; tb < t1; tb += TP) {
-		const int np = min(TP, t1 - tb);
-		SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), a.err, 202);
-		const char* kt = ring + (size_t)rp.slot * a.slot_bytes;
-		const char* vt = kt + (size_t)TP * kvrow;
-		for (int pb = 0; pb < np; pb += FUSED_NCW * G * P) { // warp-uniform trip count
+		for (int pb = 0; pb < ((a.dbg & 1) ? 0 : np); pb += FUSED_NCW * G * P) { // warp-uniform trip count
 			float kf[P][8], vf[P][8];
 			bool ok[P];
 #pragma unroll
 			for (int i = 0; i < P; ++i) {
 				int p = pb + (i * FUSED_NCW + warp) * G + grp;
-				ok[i] = p < np && (tb + p) != tp.kv_pos;
+				ok[i] = p < np && (fresh || (tb + p) != tp.kv_pos);
 				if (ok[i] && dact) {
-					halves8(lds128(kt + (size_t)p * kvrow + li * 16), kf[i]);
-					halves8(lds128(vt + (size_t)p * kvrow + li * 16), vf[i]);
+					if (fresh) {
+						size_t off = ((size_t)kvh * a.seq_len + tp.kv_pos) * hd + li * 8;
+						halves8(__ldcg(reinterpret_cast<const uint4*>(kc_l + off)), kf[i]);
+						halves8(__ldcg(reinterpret_cast<const uint4*>(vc_l + off)), vf[i]);
+					} else {
+						halves8(lds128(kt + (size_t)p * kvrow + li * 16), kf[i]);
+						halves8(lds128(vt + (size_t)p * kvrow + li * 16), vf[i]);
+					}
 				} else {
 #pragma unroll
 					for (int d = 0; d < 8; ++d) kf[i][d] = 0.f, vf[i][d] = 0.f;
 				}
 			}
-			update(kf, vf, ok);
-		}
-		__syncwarp();
-		if (lane == 0) mbar_arrive(&sh->empty[rp.slot]);
-		rp.advance();
-	}
-
-	// the entry appended this step: fresh from L2 (warp 0 only; its first lane group holds it)
-	if (warp == 0 && tp.kv_pos >= t0 && tp.kv_pos < t1) {
-		float kf[P][8], vf[P][8];
-		bool ok[P];
+			// online-softmax update with P (position, K, V) triples held by this lane group
 #pragma unroll
-		for (int i = 0; i < P; ++i) {
-			ok[i] = i == 0 && grp == 0;
+			for (int h = 0; h < HG; ++h) {
+				float s[P], smax = m[h];
 #pragma unroll
-			for (int d = 0; d < 8; ++d) kf[i][d] = 0.f, vf[i][d] = 0.f;
+				for (int i = 0; i < P; ++i) {
+					float d = 0.f;
+#pragma unroll
+					for (int e = 0; e < 8; ++e) d = fmaf(qr[h][e], kf[i][e], d);
+					for (int o = 1; o < lpp; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+					s[i] = ok[i] ? d * a.inv_sqrt_hd : -FLT_MAX;
+					smax = fmaxf(smax, s[i]);
+				}
+				float corr = expf(m[h] - smax);
+				m[h] = smax;
+				float pw[P], ps = 0.f;
+#pragma unroll
+				for (int i = 0; i < P; ++i) {
+					pw[i] = ok[i] ? expf(s[i] - smax) : 0.f;
+					ps += pw[i];
+				}
+				l[h] = fmaf(l[h], corr, ps);
+#pragma unroll
+				for (int e = 0; e < 8; ++e) {
+					float v = acc[h][e] * corr;
+#pragma unroll
+					for (int i = 0; i < P; ++i) v = fmaf(pw[i], vf[i][e], v);
+					acc[h][e] = v;
+				}
+			}
 		}
-		if (grp == 0 && dact) {
-			size_t off = ((size_t)kvh * a.seq_len + tp.kv_pos) * hd + li * 8;
-			halves8(__ldcg(reinterpret_cast<const uint4*>(kc_l + off)), kf[0]);
-			halves8(__ldcg(reinterpret_cast<const uint4*>(vc_l + off)), vf[0]);
+		if (!fresh) {
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&sh->empty[rp.slot]);
+			rp.advance();
 		}
-		update(kf, vf, ok);
 	}
 
 	// merge lane groups of a warp
@@ -561,7 +556,6 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 		}
 	}
 	consumer_sync();
-	const int tid = warp * 32 + lane;
 	float* part = a.attn_partial + ((size_t)unit * a.attn_nsplit + split) * HG * rec;
 	for (int idx = tid; idx < HG * rec; idx += FUSED_NCW * 32) {
 		int h = idx / rec, e = idx % rec;
@@ -587,20 +581,45 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 	}
 	consumer_sync();
 	if (!sh->flag) return rp;
+
+	// Last slice of this unit to finish: fold all slices.  Two passes so that every global load is
+	// independent of the previous one: (1) maxima and sums of all slices -> coefficients in shared memory,
+	// (2) weighted sum of the accumulators, four slices in flight per thread.
 	__threadfence();
-	const float* pk = a.attn_partial + (size_t)unit * a.attn_nsplit * HG * rec;
+	const int ns = a.attn_nsplit;
+	const float* pk = a.attn_partial + (size_t)unit * ns * HG * rec;
+	float* coef = scratch;                  // [ns][HG]  exp(m_s - M) ...
+	float* msv = scratch + (size_t)ns * HG; // [ns][HG]  m_s, then l_s * coef
+	for (int i = tid; i < ns * HG; i += FUSED_NCW * 32) {
+		const float* r = pk + (size_t)i * rec; // i = s * HG + h
+		coef[i] = __ldcg(r + hd + 1);          // l_s
+		msv[i] = __ldcg(r + hd);               // m_s
+	}
+	consumer_sync();
+	if (tid < HG) {
+		float M = -FLT_MAX;
+		for (int s = 0; s < ns; ++s) M = fmaxf(M, msv[s * HG + tid]);
+		float L = 0.f;
+		for (int s = 0; s < ns; ++s) {
+			float c = expf(msv[s * HG + tid] - M);
+			L = fmaf(coef[s * HG + tid], c, L);
+			coef[s * HG + tid] = c;
+		}
+		sh->scratch[tid] = 1.0f / L; // HG <= 8
+	}
+	consumer_sync();
 	for (int idx = tid; idx < HG * hd; idx += FUSED_NCW * 32) {
 		int h = idx / hd, e = idx % hd;
-		float mn = -FLT_MAX;
-		for (int s = 0; s < a.attn_nsplit; ++s) mn = fmaxf(mn, __ldcg(pk + ((size_t)s * HG + h) * rec + hd));
-		float num = 0.f, den = 0.f;
-		for (int s = 0; s < a.attn_nsplit; ++s) {
-			const float* r = pk + ((size_t)s * HG + h) * rec;
-			float cf = expf(__ldcg(r + hd) - mn);
-			num = fmaf(__ldcg(r + e), cf, num);
-			den = fmaf(__ldcg(r + hd + 1), cf, den);
+		float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+		int s = 0;
+		for (; s + 4 <= ns; s += 4) {
+			float p0 = __ldcg(pk + ((size_t)(s + 0) * HG + h) * rec + e), p1 = __ldcg(pk + ((size_t)(s + 1) * HG + h) * rec + e);
+			float p2 = __ldcg(pk + ((size_t)(s + 2) * HG + h) * rec + e), p3 = __ldcg(pk + ((size_t)(s + 3) * HG + h) * rec + e);
+			n0 = fmaf(p0, coef[(s + 0) * HG + h], n0), n1 = fmaf(p1, coef[(s + 1) * HG + h], n1);
+			n2 = fmaf(p2, coef[(s + 2) * HG + h], n2), n3 = fmaf(p3, coef[(s + 3) * HG + h], n3);
 		}
-		__stcg(a.att + (size_t)(hbase + h) * hd + e, num / den);
+		for (; s < ns; ++s) n0 = fmaf(__ldcg(pk + ((size_t)s * HG + h) * rec + e), coef[s * HG + h], n0);
+		__stcg(a.att + (size_t)(hbase + h) * hd + e, ((n0 + n1) + (n2 + n3)) * sh->scratch[h]);
 	}
 	if (tid == 0) a.attn_counter[unit] = 0;
 	return rp;
@@ -616,148 +635,134 @@ struct StageCtx {
 	int warp, lane;
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__device__ __forceinline__ unsigned long long stage_begin(const FusedArgs& a) {
+	return (a.perf && blockIdx.x == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
+}
+__device__ __forceinline__ void stage_end(const FusedArgs& a, int st, unsigned long long t0) { // stage without a barrier
+	if (a.perf && blockIdx.x == 0 && threadIdx.x == 0) a.perf[st] += globaltimer_ns() - t0;
+}
+
 // all consumer warps finished the stage -> publish; then wait for every CTA
-__device__ __forceinline__ void stage_barrier(const FusedArgs& a, int code) {
+__device__ __forceinline__ void stage_barrier(const FusedArgs& a, int code, int st, unsigned long long t0) {
 	consumer_sync();
 	if (threadIdx.x == 0) {
+		unsigned long long t1 = (a.perf && blockIdx.x == 0) ? globaltimer_ns() : 0ull;
 		unsigned old = grid_arrive(a.bar);
 		grid_wait(a.bar, old, a.err, code);
+		if (a.perf && blockIdx.x == 0) {
+			unsigned long long t2 = globaltimer_ns();
+			a.perf[st] += t1 - t0;
+			a.perf[8 + st] += t2 - t1;
+		}
 	}
 	consumer_sync();
 }
 
-template <int DBITS, int XR>
-__device__ __forceinline__ Consumer<DBITS, XR> make_consumer(const FusedArgs& a, const StageCtx& cx) {
-	Consumer<DBITS, XR> c;
-	c.sh = cx.sh, c.ring = cx.ring, c.slot_bytes = a.slot_bytes, c.err = a.err;
-	c.cw = cx.warp, c.lane = cx.lane;
-	c.best_v = -FLT_MAX, c.best_i = 0x7fffffff;
-	return c;
-}
+// One function serves every matrix stage (the tile loop, the activation load and the epilogues exist
+// once in the instruction stream: the per-layer code footprint has to stay inside the instruction cache).
+enum StageKind { SK_QKV = 1, SK_WO = 3, SK_UP = 4, SK_DOWN = 5, SK_OUT = 6 };
 
-// stage 1: norm -> q,k,v (+bias, clip, RoPE) -> q vector / cache append   (reference infer.c:352-381)
 template <int DBITS, int XR>
-__device__ __noinline__ RingPos stage_qkv(const FusedArgs& a, const StageCtx cx, RingPos rp, int l, const TokenParams tp) {
+__device__ __noinline__ RingPos stage_matrix(const FusedArgs& a, const StageCtx cx, RingPos rp, const int kind, const int l, const TokenParams tp) {
 	constexpr int VW = WFmt<DBITS>::VW;
+	const unsigned long long t_begin = stage_begin(a);
 	const FusedLayer& L = c_fused_layers[l];
-	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
-	const int nv = a.dim / VW;
+	FusedShared* sh = cx.sh;
+	Consumer<DBITS, XR> c;
+	c.sh = cx.sh, c.ring = cx.ring, c.slot_bytes = a.slot_bytes, c.err = a.err, c.dbg = a.dbg;
+	c.cw = cx.warp, c.lane = cx.lane;
+
+	// what this stage reads, which rows it owns, how its tiles are cut
+	const float* xin = a.x;
+	const float* normw = nullptr;
+	int n = a.dim, nseg = 1, unit = 1;
+	StageRanges rg;
+	rg.n = 1;
+	switch (kind) {
+	case SK_QKV: // norm -> q,k,v (+bias, clip, RoPE) -> q vector / cache append   (reference infer.c:352-381)
+		normw = L.rms_att, unit = 2, rg.n = 3;
+		cta_range(a.q_dim / 2, rg.r0[0], rg.r1[0]), rg.r0[0] *= 2, rg.r1[0] *= 2;
+		cta_range(a.kv_dim / 2, rg.r0[1], rg.r1[1]), rg.r0[1] *= 2, rg.r1[1] *= 2;
+		rg.r0[2] = rg.r0[1], rg.r1[2] = rg.r1[1];
+		break;
+	case SK_WO: // x += wo . att   (reference infer.c:410-415)
+		xin = a.att, n = a.q_dim;
+		cta_range(a.dim, rg.r0[0], rg.r1[0]);
+		break;
+	case SK_UP: // norm -> act(w1 . xn) * (w3 . xn)   (reference infer.c:417-450)
+		if (a.norm_par)
+			xin = a.xb;
+		else
+			normw = L.rms_ffn;
+		nseg = 2;
+		cta_range(a.hidden, rg.r0[0], rg.r1[0]);
+		break;
+	case SK_DOWN: // x += w2 . hb   (reference infer.c:452-456)
+		xin = a.hb, n = a.hidden;
+		cta_range(a.dim, rg.r0[0], rg.r1[0]);
+		break;
+	default: // SK_OUT: logits = wcls . norm(x), greedy candidates   (reference infer.c:466-469, sampler.c:34-42)
+		normw = a.rms_final;
+		cta_range(a.vocab, rg.r0[0], rg.r1[0]);
+		break;
+	}
+	const int nv = n / VW;
 	const RowMap m = row_map<DBITS, XR>(nv);
-	const int R = tile_rows(a.slot_bytes, 1, nv * 16, 2);
-	int q0, q1, k0, k1;
-	cta_range(a.q_dim / 2, q0, q1), q0 *= 2, q1 *= 2;
-	cta_range(a.kv_dim / 2, k0, k1), k0 *= 2, k1 *= 2;
-	float* xb_out = a.norm_par && blockIdx.x == 0 ? a.xb : nullptr;
-	if (l == 0)
-		c.template load_x<true>(m, nullptr, a.embed, tp.token, a.dim, L.rms_att, a.eps, a.ln != 0, xb_out);
-	else
-		c.template load_x<false>(m, a.x, nullptr, 0, a.dim, L.rms_att, a.eps, a.ln != 0, xb_out);
+	const int R = tile_rows(a.slot_bytes, nseg, nv * 16, unit, m.ng);
+
+	c.load_x(m, xin, n, normw, a.eps, a.ln != 0, (kind == SK_QKV && a.norm_par && blockIdx.x == 0) ? a.xb : nullptr);
 
 	const size_t kv_layer = (size_t)a.n_kv_heads * a.seq_len * a.head_dim;
-	__half* kc_l = a.kc + l * kv_layer;
-	__half* vc_l = a.vc + l * kv_layer;
-	auto epi = [&](int which, int k, float v0, float v1) {
-		int j = which == 0 ? k : (which == 1 ? a.q_dim + k : a.q_dim + a.kv_dim + k);
-		if (L.bqkv) v0 += L.bqkv[j], v1 += L.bqkv[j + 1];
-		v0 = fminf(fmaxf(v0, -a.clip), a.clip);
-		v1 = fminf(fmaxf(v1, -a.clip), a.clip);
-		if (which < 2) {
-			float fcr, fci;
-			sincosf((float)tp.pos * a.rope_freq[(k % a.head_dim) >> 1], &fci, &fcr);
-			float r0 = v0 * fcr - v1 * fci, r1 = v0 * fci + v1 * fcr;
-			v0 = r0, v1 = r1;
+	float best_v = -FLT_MAX;
+	int best_i = 0x7fffffff;
+	c.matrix(rp, m, nv, nseg, kind == SK_QKV, rg, R, [&](int which, int r, float v0, float v1) {
+		switch (kind) {
+		case SK_QKV: {
+			int j = which == 0 ? r : (which == 1 ? a.q_dim + r : a.q_dim + a.kv_dim + r);
+			if (L.bqkv) v0 += L.bqkv[j], v1 += L.bqkv[j + 1];
+			v0 = fminf(fmaxf(v0, -a.clip), a.clip);
+			v1 = fminf(fmaxf(v1, -a.clip), a.clip);
+			if (which < 2) { // rotate the pair (reference infer.c:223-236); cos/sin of this position are in shared memory
+				int i = (r % a.head_dim) >> 1;
+				float fcr = sh->rope_cos[i], fci = sh->rope_sin[i];
+				float r0 = v0 * fcr - v1 * fci, r1 = v0 * fci + v1 * fcr;
+				v0 = r0, v1 = r1;
+			}
+			if (which == 0) {
+				__stcg(reinterpret_cast<float2*>(a.q + r), make_float2(v0, v1));
+			} else {
+				__half* cbase = (which == 1 ? a.kc : a.vc) + l * kv_layer;
+				int h = r / a.head_dim, d = r % a.head_dim;
+				*reinterpret_cast<__half2*>(cbase + ((size_t)h * a.seq_len + tp.kv_pos) * a.head_dim + d) = __floats2half2_rn(v0, v1);
+			}
+			break;
 		}
-		if (which == 0) {
-			__stcg(reinterpret_cast<float2*>(a.q + k), make_float2(v0, v1));
-		} else {
-			__half* cbase = which == 1 ? kc_l : vc_l;
-			int h = k / a.head_dim, d = k % a.head_dim;
-			*reinterpret_cast<__half2*>(cbase + ((size_t)h * a.seq_len + tp.kv_pos) * a.head_dim + d) = __floats2half2_rn(v0, v1);
+		case SK_WO:
+		case SK_DOWN:
+			__stcg(a.x + r, __ldcg(a.x + r) + v0);
+			break;
+		case SK_UP:
+			__stcg(a.hb + r, (a.gelu ? act_gelu(v0) : act_silu(v0)) * v1);
+			break;
+		default:
+			a.logits[r] = v0;
+			if (v0 > best_v || (v0 == best_v && r < best_i)) best_v = v0, best_i = r; // first maximum wins
+			break;
 		}
-	};
-	c.template matrix<true>(rp, m, nv, 1, q0, q1, R, [&](int r, float v0, float v1) { epi(0, r, v0, v1); });
-	c.template matrix<true>(rp, m, nv, 1, k0, k1, R, [&](int r, float v0, float v1) { epi(1, r, v0, v1); });
-	c.template matrix<true>(rp, m, nv, 1, k0, k1, R, [&](int r, float v0, float v1) { epi(2, r, v0, v1); });
-	stage_barrier(a, 301);
-	return rp;
-}
-
-// stage 3: x += wo . att   (reference infer.c:410-415)
-template <int DBITS, int XR>
-__device__ __noinline__ RingPos stage_wo(const FusedArgs& a, const StageCtx cx, RingPos rp, int l, int token) {
-	constexpr int VW = WFmt<DBITS>::VW;
-	const FusedLayer& L = c_fused_layers[l];
-	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
-	const int nv = a.q_dim / VW;
-	const RowMap m = row_map<DBITS, XR>(nv);
-	const int R = tile_rows(a.slot_bytes, 1, nv * 16, 1);
-	int o0, o1;
-	cta_range(a.dim, o0, o1);
-	c.template load_x<false>(m, a.att, nullptr, 0, a.q_dim, nullptr, 0.f, false, nullptr);
-	c.template matrix<false>(rp, m, nv, 1, o0, o1, R, [&](int r, float v0, float) {
-		float base = l == 0 ? weight_at<DBITS>(a.embed, (size_t)token * a.dim + r) : __ldcg(a.x + r);
-		__stcg(a.x + r, base + v0);
 	});
-	(void)L;
-	stage_barrier(a, 303);
-	return rp;
-}
 
-// stage 4: norm -> act(w1 . xn) * (w3 . xn)   (reference infer.c:417-450)
-template <int DBITS, int XR>
-__device__ __noinline__ RingPos stage_up(const FusedArgs& a, const StageCtx cx, RingPos rp, int l) {
-	constexpr int VW = WFmt<DBITS>::VW;
-	const FusedLayer& L = c_fused_layers[l];
-	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
-	const int nv = a.dim / VW;
-	const RowMap m = row_map<DBITS, XR>(nv);
-	const int R = tile_rows(a.slot_bytes, 2, nv * 16, 1);
-	int h0, h1;
-	cta_range(a.hidden, h0, h1);
-	if (a.norm_par)
-		c.template load_x<false>(m, a.xb, nullptr, 0, a.dim, nullptr, 0.f, false, nullptr);
-	else
-		c.template load_x<false>(m, a.x, nullptr, 0, a.dim, L.rms_ffn, a.eps, a.ln != 0, nullptr);
-	c.template matrix<false>(rp, m, nv, 2, h0, h1, R, [&](int r, float v1, float v3) { __stcg(a.hb + r, (a.gelu ? act_gelu(v1) : act_silu(v1)) * v3); });
-	stage_barrier(a, 304);
-	return rp;
-}
-
-// stage 5: x += w2 . hb   (reference infer.c:452-456)
-template <int DBITS, int XR>
-__device__ __noinline__ RingPos stage_down(const FusedArgs& a, const StageCtx cx, RingPos rp) {
-	constexpr int VW = WFmt<DBITS>::VW;
-	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
-	const int nv = a.hidden / VW;
-	const RowMap m = row_map<DBITS, XR>(nv);
-	const int R = tile_rows(a.slot_bytes, 1, nv * 16, 1);
-	int o0, o1;
-	cta_range(a.dim, o0, o1);
-	c.template load_x<false>(m, a.hb, nullptr, 0, a.hidden, nullptr, 0.f, false, nullptr);
-	c.template matrix<false>(rp, m, nv, 1, o0, o1, R, [&](int r, float v0, float) { __stcg(a.x + r, __ldcg(a.x + r) + v0); });
-	stage_barrier(a, 305);
-	return rp;
-}
-
-// classifier: logits = wcls . norm(x), greedy candidates   (reference infer.c:466-469, sampler.c:34-42)
-template <int DBITS, int XR>
-__device__ __noinline__ RingPos stage_out(const FusedArgs& a, const StageCtx cx, RingPos rp) {
-	constexpr int VW = WFmt<DBITS>::VW;
-	Consumer<DBITS, XR> c = make_consumer<DBITS, XR>(a, cx);
-	FusedShared* sh = cx.sh;
-	const int nv = a.dim / VW;
-	const RowMap m = row_map<DBITS, XR>(nv);
-	const int R = tile_rows(a.slot_bytes, 1, nv * 16, 1);
-	int c0, c1;
-	cta_range(a.vocab, c0, c1);
-	c.template load_x<false>(m, a.x, nullptr, 0, a.dim, a.rms_final, a.eps, a.ln != 0, nullptr);
-	c.template matrix<false>(rp, m, nv, 1, c0, c1, R, [&](int r, float v0, float) {
-		a.logits[r] = v0;
-		if (v0 > c.best_v || (v0 == c.best_v && r < c.best_i)) c.best_v = v0, c.best_i = r; // first maximum wins
-	});
+	if (kind != SK_OUT) {
+		stage_barrier(a, 300 + kind, kind, t_begin);
+		return rp;
+	}
 	if (a.cand_val) {
-		float bv = c.best_v;
-		int bi = c.best_i;
+		float bv = best_v;
+		int bi = best_i;
 		for (int o = 16; o > 0; o >>= 1) {
 			float ov = __shfl_xor_sync(0xffffffffu, bv, o);
 			int oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -772,6 +777,7 @@ __device__ __noinline__ RingPos stage_out(const FusedArgs& a, const StageCtx cx,
 			a.cand_val[blockIdx.x] = bv, a.cand_idx[blockIdx.x] = bi;
 		}
 	}
+	stage_end(a, 6, t_begin);
 	return rp;
 }
 
@@ -797,6 +803,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
+	// RoPE angles of this token, once (host-libm frequencies, reference infer.c:225-229)
+	for (int i = threadIdx.x; i < a.head_dim / 2; i += blockDim.x) sincosf((float)tp.pos * a.rope_freq[i], &sh->rope_sin[i], &sh->rope_cos[i]);
 	__syncthreads();
 
 	// attention work item of this CTA: (unit, split) -> positions [t0, t1) of kv head `kvh`
@@ -816,11 +824,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 		if (lane != 0) return;
 		const int nv_dim = a.dim / VW, nv_q = a.q_dim / VW, nv_hid = a.hidden / VW;
 		const int rb_dim = nv_dim * 16, rb_q = nv_q * 16, rb_hid = nv_hid * 16; // bytes per row
-		const int R_qkv = tile_rows(a.slot_bytes, 1, rb_dim, 2);
-		const int R_wo = tile_rows(a.slot_bytes, 1, rb_q, 1);
-		const int R_up = tile_rows(a.slot_bytes, 2, rb_dim, 1);
-		const int R_down = tile_rows(a.slot_bytes, 1, rb_hid, 1);
-		const int R_out = tile_rows(a.slot_bytes, 1, rb_dim, 1);
+		const int ng_dim = row_map<DBITS, XR>(nv_dim).ng, ng_q = row_map<DBITS, XR>(nv_q).ng, ng_hid = row_map<DBITS, XR>(nv_hid).ng;
+		const int R_qkv = tile_rows(a.slot_bytes, 1, rb_dim, 2, ng_dim);
+		const int R_wo = tile_rows(a.slot_bytes, 1, rb_q, 1, ng_q);
+		const int R_up = tile_rows(a.slot_bytes, 2, rb_dim, 1, ng_dim);
+		const int R_down = tile_rows(a.slot_bytes, 1, rb_hid, 1, ng_hid);
+		const int R_out = tile_rows(a.slot_bytes, 1, rb_dim, 1, ng_dim);
 		int q0, q1, k0, k1, o0, o1, h0, h1, c0, c1;
 		cta_range(a.q_dim / 2, q0, q1), q0 *= 2, q1 *= 2;
 		cta_range(a.kv_dim / 2, k0, k1), k0 *= 2, k1 *= 2;
@@ -829,7 +838,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 		cta_range(a.vocab, c0, c1);
 
 		Producer p;
-		p.sh = sh, p.ring = ring, p.slot_bytes = a.slot_bytes, p.err = a.err;
+		p.sh = sh, p.ring = ring, p.slot_bytes = a.slot_bytes, p.err = a.err, p.dbg = a.dbg;
 		p.rp.init(a.nslots);
 		p.pol_w = l2_policy_evict_first();
 		p.pol_kv = l2_policy_evict_last();
@@ -841,15 +850,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 			if (has_item) {
 				const char* kb = (const char*)(a.kc + l * kv_layer + (size_t)kvh * a.seq_len * a.head_dim);
 				const char* vb = (const char*)(a.vc + l * kv_layer + (size_t)kvh * a.seq_len * a.head_dim);
-				for (int t_ = t0; t_ < t1; t_ += TP) {
-					uint32_t bytes = (uint32_t)min(TP, t1 - t_) * kvrow;
-					SPIN_WAIT(mbar_try_wait(&sh->empty[p.rp.slot], p.rp.phase ^ 1), a.err, 102);
-					mbar_expect_tx(&sh->full[p.rp.slot], 2 * bytes);
-					char* dst = ring + (size_t)p.rp.slot * a.slot_bytes;
-					tma_load_1d(dst, kb + (size_t)t_ * kvrow, bytes, &sh->full[p.rp.slot], p.pol_kv);
-					tma_load_1d(dst + (size_t)TP * kvrow, vb + (size_t)t_ * kvrow, bytes, &sh->full[p.rp.slot], p.pol_kv);
-					p.rp.advance();
-				}
+				for (int t_ = t0; t_ < t1; t_ += TP)
+					p.push(kb + (size_t)t_ * kvrow, vb + (size_t)t_ * kvrow, (uint32_t)min(TP, t1 - t_) * kvrow, (uint32_t)TP * kvrow, p.pol_kv);
 			}
 			p.matrix(L.wo, nullptr, rb_q, o0, o1, R_wo);
 			p.matrix(L.w1, L.w3, rb_dim, h0, h1, R_up);
@@ -865,10 +867,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 	RingPos rp;
 	rp.init(a.nslots);
 
+	// x = decode(E[token]) (reference infer.c:335-347).  Every CTA writes the whole row (identical values), so
+	// it only ever reads back what it wrote itself: no grid barrier is needed before stage 1.
+	for (int i = threadIdx.x; i < a.dim; i += FUSED_NCW * 32) a.x[i] = weight_at<DBITS>(a.embed, (size_t)tp.token * a.dim + i);
+	__threadfence();
+	consumer_sync();
+
 	for (int l = 0; l < a.n_layers; ++l) {
-		rp = stage_qkv<DBITS, XR>(a, cx, rp, l, tp);
+		rp = stage_matrix<DBITS, XR>(a, cx, rp, SK_QKV, l, tp);
 
 		// stage 2: attention over the cache (K/V tiles from the ring)
+		const unsigned long long t_attn = stage_begin(a);
 		if (has_item) {
 			const __half* kc_l = a.kc + l * kv_layer;
 			const __half* vc_l = a.vc + l * kv_layer;
@@ -883,11 +892,29 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 			default: rp = fused_attention<8>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
 			}
 		}
-		stage_barrier(a, 302);
+		stage_barrier(a, 302, 2, t_attn);
 
-		rp = stage_wo<DBITS, XR>(a, cx, rp, l, tp.token);
-		rp = stage_up<DBITS, XR>(a, cx, rp, l);
-		rp = stage_down<DBITS, XR>(a, cx, rp);
+		rp = stage_matrix<DBITS, XR>(a, cx, rp, SK_WO, l, tp);
+		rp = stage_matrix<DBITS, XR>(a, cx, rp, SK_UP, l, tp);
+		rp = stage_matrix<DBITS, XR>(a, cx, rp, SK_DOWN, l, tp);
 	}
-	if (a.mode != 0) rp = stage_out<DBITS, XR>(a, cx, rp);
+	if (a.mode != 0) rp = stage_matrix<DBITS, XR>(a, cx, rp, SK_OUT, 0, tp);
+}
+
+// ---------------------------------------------------------------- micro-benchmark: cost of one grid barrier
+// (same arrive/wait code as the fused kernel, all SMs, 288 threads per CTA, no work in between)
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_barrier_bench(unsigned* bar, int* err, int rounds, unsigned long long* ns_out) {
+	const int warp = threadIdx.x >> 5;
+	if (warp == FUSED_NCW) return;
+	unsigned long long t0 = 0;
+	if (blockIdx.x == 0 && threadIdx.x == 0) t0 = globaltimer_ns();
+	for (int i = 0; i < rounds; ++i) {
+		consumer_sync();
+		if (threadIdx.x == 0) {
+			unsigned old = grid_arrive(bar);
+			grid_wait(bar, old, err, 900);
+		}
+		consumer_sync();
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) *ns_out = globaltimer_ns() - t0;
 }

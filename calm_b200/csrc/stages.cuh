@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
 
 // Fold the per-CTA candidates, publish the greedy token, and advance the token parameters so the
 // next replay of the graph consumes it (device-resident decode loop).
-__global__ void k_advance(const float* cand_val, const int* cand_idx, int ncand, TokenParams* tp, int* out_tokens, int* last_token, int advance) {
+__global__ void k_advance(const float* cand_val, const int* cand_idx, int ncand, TokenParams* tp, int* out_tokens, int* last_token, int advance, int vocab) {
 	__shared__ float sv[256];
 	__shared__ int si[256];
 	float best = -FLT_MAX;
@@ -599,6 +599,7 @@ __global__ void k_advance(const float* cand_val, const int* cand_idx, int ncand,
 	}
 	if (threadIdx.x == 0) {
 		int tok = si[0];
+		if (tok < 0 || tok >= vocab) tok = 0; // only reachable when every logit is NaN
 		*last_token = tok;
 		if (advance) {
 			out_tokens[tp->step] = tok;

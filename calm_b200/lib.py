@@ -26,7 +26,7 @@ SYMBOLS = [
     "calm_b200_abi_version", "calm_b200_set_device", "calm_b200_free", "calm_b200_release", "calm_b200_set_engine",
     "calm_b200_forward_argmax", "calm_b200_decode_greedy", "calm_b200_timer_start", "calm_b200_timer_stop",
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
-    "calm_b200_set_perf", "calm_b200_stage_stats",
+    "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_engine_in_use", "calm_b200_stage_wait_ms", "calm_b200_barrier_bench",
 ]
 
 _lib = None
@@ -63,6 +63,9 @@ def load() -> C.CDLL:
     L.calm_b200_set_perf.argtypes, L.calm_b200_set_perf.restype = [C.c_int], None
     L.calm_b200_stage_stats.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]
     L.calm_b200_stage_stats.restype = C.c_int
+    L.calm_b200_engine_in_use.argtypes, L.calm_b200_engine_in_use.restype = [], C.c_int
+    L.calm_b200_stage_wait_ms.argtypes, L.calm_b200_stage_wait_ms.restype = [C.c_int], C.c_double
+    L.calm_b200_barrier_bench.argtypes, L.calm_b200_barrier_bench.restype = [C.c_int], C.c_float
     _lib = L
     return L
 
@@ -136,9 +139,10 @@ class DeviceModel:
     def fill_kv(self, n_pos: int, seed: int = 1) -> None:
         self.lib.calm_b200_fill_kv(C.byref(self.transformer), n_pos, seed)
 
-    def profile(self, token: int, pos0: int, n: int):
-        """Run n tokens with per-stage CUDA events; returns {stage: (ms_total, bytes_total, launches)}."""
-        self.lib.calm_b200_set_perf(1)
+    def profile(self, token: int, pos0: int, n: int, mode: int = 1):
+        """Run n tokens with per-stage timing; returns {stage: (ms_total, bytes_total, launches)}.
+        mode 1: staged engine, CUDA events around every launch; mode 2: fused engine, in-kernel timers."""
+        self.lib.calm_b200_set_perf(mode)
         tok = token
         for i in range(n):
             tok = self.forward_argmax(tok, pos0 + i)
@@ -147,10 +151,14 @@ class DeviceModel:
         name = C.create_string_buffer(64)
         ms, by, nl = C.c_double(), C.c_double(), C.c_long()
         while self.lib.calm_b200_stage_stats(i, name, 64, C.byref(ms), C.byref(by), C.byref(nl)):
-            out[name.value.decode()] = (ms.value, by.value, nl.value)
+            out[name.value.decode()] = (ms.value, by.value, nl.value, self.lib.calm_b200_stage_wait_ms(i) if mode == 2 else 0.0)
             i += 1
         self.lib.calm_b200_set_perf(0)
         return out
+
+    def uses_fused(self) -> bool:
+        """True when the persistent fused kernel serves this model (else the staged engine does)."""
+        return bool(self.lib.calm_b200_engine_in_use())
 
     def close(self) -> None:
         if self.transformer is not None:

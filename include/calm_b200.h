@@ -80,6 +80,10 @@ void calm_b200_release(struct Transformer* transformer);
  * Must be called before prepare_cuda(). */
 void calm_b200_set_engine(int engine);
 
+/* 1 when the persistent fused kernel serves the prepared model, 0 when the staged engine does (MoE,
+ * fp8 KV cache, shapes whose rows do not fit the ring, or engine 0 requested). */
+int calm_b200_engine_in_use(void);
+
 /* forward + device-side greedy sample.  Returns argmax(logits) with the
  * reference's tie rule (lowest index, sampler.c:34-42).  The logits are still
  * written to state.logits. */
@@ -114,9 +118,16 @@ void calm_b200_fill_kv(struct Transformer* transformer, int n_pos, uint64_t seed
  * stage is launched eagerly and bracketed by CUDA events on the library's stream.  set_perf(1) also
  * clears the counters.  stage_stats() returns 0 past the last stage; totals are over all launches of
  * that stage since set_perf(1): milliseconds, algorithmic bytes (the reference's per-stage accounting,
- * infer.cu:683-699) and launch count. */
+ * infer.cu:683-699) and launch count.  set_perf(2) keeps the fused engine and times its stages INSIDE the
+ * persistent kernel with %globaltimer (what the reference's coopstage does, infer.cu:390-402). */
 void calm_b200_set_perf(int on);
 int calm_b200_stage_stats(int stage, char* name, int name_cap, double* ms_total, double* bytes_total, long* launches);
+
+/* Fused engine only: the part of stage_stats()'s ms_total that CTA 0 spent waiting in the grid barrier. */
+double calm_b200_stage_wait_ms(int stage);
+
+/* Micro-benchmark: microseconds per grid barrier of the fused engine (all SMs, no work in between). */
+float calm_b200_barrier_bench(int rounds);
 
 /* Stand-alone run of the production matvec kernel: y[d] = W[d,n] . x[n] with W
  * in the `dbits` format at device pointer `w_device`; x and y are HOST arrays.
