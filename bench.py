@@ -316,14 +316,14 @@ def dm_roofline(dm, L, spec, pos, peak, peak_src, ms_per_tok, bytes_per_tok):
     stats = dm.profile(23, pos, 8, mode=2 if fused else 1)
     total_ms = sum(v[0] for v in stats.values()) or 1.0
     table = {k: {"share": v[0] / total_ms, "us_per_launch": v[0] / max(v[2], 1) * 1e3, "gbs": (v[1] / 1e9 / (v[0] / 1e3)) if v[0] > 0 else None,
-                 "barrier_wait_us": v[3] / max(v[2], 1) * 1e3}
+                 "barrier_wait_us": v[3] / max(v[2], 1) * 1e3, "load_x_us": v[4] / max(v[2], 1) * 1e3, "tile_wait_us": v[5] / max(v[2], 1) * 1e3}
              for k, v in stats.items()}
     if fused:
         achieved = bytes_per_tok / 1e9 / (ms_per_tok / 1e3)
         return {"bound": "hbm", "kernel": "k_fused (persistent: all layers + classifier of one token)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_tok, "us_per_launch": ms_per_tok * 1e3,
                 "stages": table}
-    name, (ms, by, nl, _) = max(stats.items(), key=lambda kv: kv[1][0])
+    name, (ms, by, nl, *_) = max(stats.items(), key=lambda kv: kv[1][0])
     achieved = by / 1e9 / (ms / 1e3) if ms > 0 else None
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
             "traffic": None, "peak_source": peak_src, "bytes_per_launch": by / max(nl, 1), "us_per_launch": ms / max(nl, 1) * 1e3, "stages": table}

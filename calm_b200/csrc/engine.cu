@@ -64,12 +64,12 @@ struct Engine {
 	bool fused_ok = false;   // model/configuration is served by the persistent kernel
 	bool fused_attr_set = false;
 	int fused_xr = 64;
-	int fused_slot_bytes = 0, fused_nslots = 0, fused_scratch = 0;
+	int fused_slot_bytes = 0, fused_nslots = 0, fused_scratch = 0, fused_xbuf = 0, fused_nwbuf = 0;
 	size_t fused_smem = 0;
 	int fused_nsplit = 1;
 	unsigned* fused_bar = nullptr;
 	int* fused_err = nullptr; // pinned + mapped
-	unsigned long long* fused_perf_ns = nullptr; // device [16]
+	unsigned long long* fused_perf_ns = nullptr; // device [32]
 	bool fused_perf = false;
 	cudaGraphExec_t fgraph[4] = {nullptr, nullptr, nullptr, nullptr};
 	int fgraph_launches[4] = {0, 0, 0, 0};
@@ -86,6 +86,7 @@ struct Engine {
 	double stage_bytes[ST_COUNT] = {};
 	long stage_launches[ST_COUNT] = {};
 	double stage_wait_ms[ST_COUNT] = {}; // fused engine: part of stage_ms spent waiting in the grid barrier
+	double stage_loadx_ms[ST_COUNT] = {}, stage_tilewait_ms[ST_COUNT] = {}; // ... loading the activation slice / waiting for tiles
 	int perf_runs = 0;
 	cudaEvent_t ev[2] = {nullptr, nullptr};
 	cudaEvent_t timer[2] = {nullptr, nullptr};
@@ -336,12 +337,12 @@ void fused_launch_t(const FusedArgs& fa) {
 void fused_launch(const FusedArgs& fa) {
 	const int key = g.w.dbits * 1000 + g.fused_xr;
 	switch (key) {
+	case 8032: fused_launch_t<8, 32>(fa); break;
 	case 8064: fused_launch_t<8, 64>(fa); break;
-	case 8128: fused_launch_t<8, 128>(fa); break;
+	case 16032: fused_launch_t<16, 32>(fa); break;
 	case 16064: fused_launch_t<16, 64>(fa); break;
-	case 16128: fused_launch_t<16, 128>(fa); break;
+	case 4032: fused_launch_t<4, 32>(fa); break;
 	case 4064: fused_launch_t<4, 64>(fa); break;
-	case 4128: fused_launch_t<4, 128>(fa); break;
 	default: CALM_FATAL("fused engine: no kernel for dbits %d / xr %d", g.w.dbits, g.fused_xr);
 	}
 }
@@ -356,10 +357,10 @@ void fused_plan() {
 	if (c.dim > nvmax) nvmax = c.dim;
 	nvmax /= vw;
 	int need_it = cdiv(nvmax, FUSED_NCW * 32);
-	if (need_it <= 64 / vw)
+	if (need_it <= 32 / vw)
+		g.fused_xr = 32;
+	else if (need_it <= 64 / vw)
 		g.fused_xr = 64;
-	else if (need_it <= 128 / vw)
-		g.fused_xr = 128;
 	else
 		return;
 	// slot: must hold the smallest legal tile of every stage; prefer 32 KB
@@ -370,11 +371,27 @@ void fused_plan() {
 	if ((size_t)4 * c.head_dim > need) need = (size_t)4 * c.head_dim;
 	size_t slot = 32 * 1024;
 	if (need > slot) slot = (need + 1023) & ~(size_t)1023;
-	g.fused_scratch = (int)(((size_t)FUSED_NCW * g.attn_hg * (c.head_dim + 2) * sizeof(float) + 127) & ~(size_t)127);
-	size_t fixed = ((sizeof(FusedShared) + 127) & ~(size_t)127) + g.fused_scratch;
+	g.fused_scratch = (int)(((size_t)FUSED_AW * g.attn_hg * (c.head_dim + 2) * sizeof(float) + 127) & ~(size_t)127);
+	{ // the last CTA of an attention unit also keeps 2 * nsplit * hg floats there
+		size_t need2 = (size_t)2 * g.sms * g.attn_hg * sizeof(float);
+		if (need2 > (size_t)g.fused_scratch) g.fused_scratch = (int)((need2 + 127) & ~(size_t)127);
+	}
+	// shared staging of the activation vector for stages whose rows are shared by fewer than all warps
+	auto staged_floats = [&](int n) {
+		int nvec = n / vw, itmax = g.fused_xr / vw, wg = 1;
+		while ((nvec + wg * 32 - 1) / (wg * 32) > itmax && wg < FUSED_NCW) wg *= 2;
+		return wg < FUSED_NCW ? n : 0;
+	};
+	int xf = staged_floats(c.dim);
+	if (staged_floats(g.q_dim) > xf) xf = staged_floats(g.q_dim);
+	if (staged_floats(c.hidden_dim) > xf) xf = staged_floats(c.hidden_dim);
+	g.fused_xbuf = (int)(((size_t)xf * sizeof(float) + 127) & ~(size_t)127);
+	g.fused_nwbuf = (int)(((size_t)c.dim * sizeof(float) + 127) & ~(size_t)127);
+	size_t fixed = ((sizeof(FusedShared) + 127) & ~(size_t)127) + g.fused_scratch + g.fused_xbuf + g.fused_nwbuf;
 	size_t avail = 227 * 1024 - fixed;
 	int nslots = (int)(avail / slot);
 	if (nslots > FUSED_MAX_SLOTS) nslots = FUSED_MAX_SLOTS;
+	if (getenv("CALM_B200_FUSED_SLOTS") && atoi(getenv("CALM_B200_FUSED_SLOTS")) >= 2 && atoi(getenv("CALM_B200_FUSED_SLOTS")) < nslots) nslots = atoi(getenv("CALM_B200_FUSED_SLOTS"));
 	if (nslots < 2) return;
 	g.fused_slot_bytes = (int)slot, g.fused_nslots = nslots;
 	g.fused_smem = fixed + (size_t)nslots * slot;
@@ -396,8 +413,8 @@ void fused_plan() {
 	CUDA_CHECK(cudaMemset(g.fused_bar, 0, sizeof(unsigned)));
 	CUDA_CHECK(cudaHostAlloc((void**)&g.fused_err, sizeof(int), cudaHostAllocMapped));
 	*g.fused_err = 0;
-	g.fused_perf_ns = (unsigned long long*)dev_alloc(16 * sizeof(unsigned long long));
-	CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 16 * sizeof(unsigned long long)));
+	g.fused_perf_ns = (unsigned long long*)dev_alloc(32 * sizeof(unsigned long long));
+	CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 32 * sizeof(unsigned long long)));
 	g.fused_attr_set = false;
 	FusedArgs none = {};
 	fused_launch(none); // sets the shared-memory opt-in outside of any stream capture
@@ -421,8 +438,12 @@ int run_token_fused(int mode) {
 	fa.mode = mode;
 	fa.dbg = getenv("CALM_B200_FUSED_DBG") ? atoi(getenv("CALM_B200_FUSED_DBG")) : 0;
 	fa.slot_bytes = g.fused_slot_bytes, fa.nslots = g.fused_nslots;
+	fa.window = getenv("CALM_B200_FUSED_WINDOW") ? atoi(getenv("CALM_B200_FUSED_WINDOW")) : 3;
+	if (fa.window < 1) fa.window = 1;
+	if (fa.window > fa.nslots) fa.window = fa.nslots;
 	fa.attn_nsplit = g.fused_nsplit, fa.attn_hg = g.attn_hg, fa.attn_qgroups = g.attn_qgroups, fa.attn_lpp = g.attn_lpp;
 	fa.attn_scratch_bytes = g.fused_scratch;
+	fa.xbuf_bytes = g.fused_xbuf, fa.nwbuf_bytes = g.fused_nwbuf;
 	fa.inv_sqrt_hd = 1.0f / sqrtf((float)c.head_dim);
 	fused_launch(fa);
 	int nl = 1;
@@ -828,16 +849,19 @@ extern "C" float calm_b200_matvec(int dbits, const void* w_device, const float* 
 static void fused_perf_collect() {
 	if (!g.fused_perf || !g.fused_perf_ns) return;
 	CUDA_CHECK(cudaStreamSynchronize(g.stream));
-	unsigned long long ns[16];
+	unsigned long long ns[32];
 	CUDA_CHECK(cudaMemcpy(ns, g.fused_perf_ns, sizeof(ns), cudaMemcpyDeviceToHost));
-	for (int i = 0; i < ST_COUNT; ++i) g.stage_ms[i] = (double)(ns[i] + ns[8 + i]) / 1e6, g.stage_wait_ms[i] = (double)ns[8 + i] / 1e6;
+	for (int i = 0; i < ST_COUNT; ++i) {
+		g.stage_ms[i] = (double)(ns[i] + ns[8 + i]) / 1e6, g.stage_wait_ms[i] = (double)ns[8 + i] / 1e6;
+		g.stage_loadx_ms[i] = (double)ns[16 + i] / 1e6, g.stage_tilewait_ms[i] = (double)ns[24 + i] / 1e6;
+	}
 }
 
 extern "C" void calm_b200_set_perf(int on) {
 	if (!on) fused_perf_collect();
 	g.perf = on != 0;
 	g.fused_perf = on == 2 && g.fused_ok;
-	if (g.fused_perf_ns) CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 16 * sizeof(unsigned long long)));
+	if (g.fused_perf_ns) CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 32 * sizeof(unsigned long long)));
 	if (!on) return;
 	for (int i = 0; i < ST_COUNT; ++i) g.stage_ms[i] = 0, g.stage_bytes[i] = 0, g.stage_launches[i] = 0;
 	g.perf_runs = 0;
@@ -858,6 +882,13 @@ extern "C" double calm_b200_stage_wait_ms(int stage) {
 	if (stage < 0 || stage >= ST_COUNT) return 0;
 	if (g.fused_perf) fused_perf_collect();
 	return g.stage_wait_ms[stage];
+}
+
+extern "C" void calm_b200_stage_detail_ms(int stage, double* load_x_ms, double* tile_wait_ms) {
+	*load_x_ms = *tile_wait_ms = 0;
+	if (stage < 0 || stage >= ST_COUNT) return;
+	if (g.fused_perf) fused_perf_collect();
+	*load_x_ms = g.stage_loadx_ms[stage], *tile_wait_ms = g.stage_tilewait_ms[stage];
 }
 
 extern "C" float calm_b200_barrier_bench(int rounds) {

@@ -4,7 +4,7 @@
 // gaps, pipeline fill and wave tails -- not bandwidth -- decide the roofline fraction of a kernel-per-stage
 // design.  Here the weights never stop streaming:
 //
-//   * grid = one CTA per SM (cooperative launch), 1 producer warp + 8 consumer warps;
+//   * grid = one CTA per SM (cooperative launch), 1 producer warp + 16 consumer warps;
 //   * every CTA owns a fixed, contiguous row range of every matrix, so its share of the model is a
 //     STATIC list of contiguous byte ranges ("tiles");
 //   * the producer lane walks that list for the whole token and moves tile after tile into a ring of
@@ -28,7 +28,8 @@
 
 #include "stages.cuh"
 
-#define FUSED_NCW 8                          // consumer warps
+#define FUSED_NCW 16                         // consumer warps (4 per scheduler)
+#define FUSED_AW 8                           // attention: warps per half (each half serves half of the query heads)
 #define FUSED_THREADS ((FUSED_NCW + 1) * 32) // + 1 producer warp
 #define FUSED_MAX_SLOTS 16
 #define FUSED_SPIN_LIMIT (1u << 27)          // watchdog for every spin loop (~1 s)
@@ -53,13 +54,16 @@ struct FusedArgs {
 	const TokenParams* tp;
 	unsigned* bar; // grid barrier word
 	int* err;      // watchdog report: nonzero = which wait timed out
-	unsigned long long* perf; // optional [2][8] ns: per stage {busy, barrier wait} seen by CTA 0 (cf. reference coopstage, infer.cu:390-402)
+	unsigned long long* perf; // optional [4][8] ns per stage, seen by thread 0 of CTA 0: {busy, grid-barrier wait, activation load, waiting for tiles}
+	                          // (cf. reference coopstage, infer.cu:390-402)
 	float* cand_val;
 	int* cand_idx;
 	int mode;      // 0 kv only, >= 1 logits (cand_val != NULL: also greedy candidates)
 	int dbg;       // experiments (results are wrong): 1 = consumers skip the math, 2 = producer skips the copies
 	int slot_bytes, nslots;
+	int window;    // at most this many tiles requested but not yet landed (bounds the L2->SM queue that demand loads wait behind)
 	int attn_nsplit, attn_hg, attn_qgroups, attn_lpp, attn_scratch_bytes;
+	int xbuf_bytes, nwbuf_bytes; // shared staging: activation vector (stages whose rows are shared by < all warps), norm weights
 	float inv_sqrt_hd;
 };
 
@@ -115,6 +119,12 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
 	return r;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
 __device__ __noinline__ void fused_fail(int* err, int code) {
 	atomicCAS(err, 0, code);
 	__threadfence_system();
@@ -149,12 +159,13 @@ __device__ __forceinline__ void grid_wait(unsigned* bar, unsigned old, int* err,
 }
 
 // ---------------------------------------------------------------- shared-memory layout
+#define FUSED_NP_MAX 2
 
 struct FusedShared {
 	uint64_t full[FUSED_MAX_SLOTS];  // producer -> consumers: tile landed (tx bytes)
 	uint64_t empty[FUSED_MAX_SLOTS]; // consumers -> producer: tile consumed (FUSED_NCW arrivals)
 	int cnt[FUSED_MAX_SLOTS];        // warps done with the tile in this slot (last one finalises)
-	float red[FUSED_MAX_SLOTS][32][FUSED_NCW]; // per-row, per-warp partial sums
+	float red[FUSED_MAX_SLOTS][FUSED_NP_MAX * FUSED_NCW]; // per-row, per-warp partial sums: [vr * wg + warp_in_group]
 	float rope_cos[128], rope_sin[128];        // cos/sin(pos * freq[i]) of this token (head_dim <= 256)
 	float scratch[64];               // block reductions
 	float best_val[FUSED_NCW];       // greedy candidates per warp
@@ -189,7 +200,7 @@ __device__ __forceinline__ RowMap row_map(int nvec) {
 
 // rows per tile (per segment): as many as fit the slot, at most FUSED_NP rows per warp group and tile,
 // at most 32 rows in all, a multiple of `unit`
-#define FUSED_NP 2
+#define FUSED_NP FUSED_NP_MAX
 __device__ __forceinline__ int tile_rows(int slot_bytes, int nseg, int rowbytes, int unit, int ng) {
 	int r = slot_bytes / (nseg * rowbytes);
 	if (r > 32 / nseg) r = 32 / nseg;
@@ -222,12 +233,21 @@ struct Producer {
 	char* ring;
 	int slot_bytes;
 	RingPos rp;
+	RingPos lp;      // `window` tiles behind rp: the oldest tile that may still be in flight
+	int ahead;       // tiles issued since lp
+	int window;
 	uint64_t pol_w, pol_kv;
 	int* err;
 	int dbg;
 
 	// one tile = one ring slot: `bytes` from src0 (and from src1, placed at dst + off1)
 	__device__ __forceinline__ void push(const char* src0, const char* src1, uint32_t bytes, uint32_t off1, uint64_t policy) {
+		if (ahead == window) { // keep the request queue short: wait for the oldest outstanding tile to land
+			SPIN_WAIT(mbar_try_wait(&sh->full[lp.slot], lp.phase), err, 103);
+			lp.advance();
+			--ahead;
+		}
+		++ahead;
 		SPIN_WAIT(mbar_try_wait(&sh->empty[rp.slot], rp.phase ^ 1), err, 101);
 		if (dbg & 2) {
 			mbar_arrive(&sh->full[rp.slot]);
@@ -263,6 +283,9 @@ struct Consumer {
 	int* err;
 	int dbg;
 	int cw, lane; // consumer warp 0..7
+	unsigned long long* tile_wait; // thread 0 of CTA 0 only: accumulates ns spent waiting for tiles
+	float* xbuf;                   // shared: one coalesced copy of the activation vector per CTA
+	const float* nwbuf;            // shared: norm weights of this stage, prefetched before the previous barrier
 	float xr[ITMAX][VW];
 
 	// sum over all 256 consumer threads (every thread gets it)
@@ -276,11 +299,22 @@ struct Consumer {
 	}
 
 	// --- activation slice into registers -------------------------------------------------------
-	// xin: global vector written by other CTAs in this launch (read through L2).  Optional norm
-	// (reference infer.c:183-207).
-	__device__ __forceinline__ void load_x(const RowMap& m, const float* xin, int n, const float* normw, float eps, bool ln, float* xb_out) {
+	// xin: global vector written by other CTAs in this launch (read through L2).  When several warp groups
+	// need the same vector it is fetched ONCE per CTA with coalesced loads into shared memory and
+	// distributed from there (all SMs read the same few KB right after a barrier: every redundant or
+	// half-used sector costs microseconds).  Optional norm (reference infer.c:183-207) with weights that
+	// were prefetched into shared memory before the previous grid barrier.
+	__device__ __forceinline__ void load_x(const RowMap& m, const float* xin, int n, bool norm, float eps, bool ln, float* xb_out) {
 		const int nvec = n / VW;
 		const int tgi = (cw % m.wg) * 32 + lane;
+		const int tid = cw * 32 + lane;
+		const bool staged = m.ng > 1;
+		if (staged) {
+			const float4* src = reinterpret_cast<const float4*>(xin);
+			float4* dst = reinterpret_cast<float4*>(xbuf);
+			for (int i = tid; i < n / 4; i += FUSED_NCW * 32) dst[i] = __ldcg(src + i);
+			consumer_sync();
+		}
 		float ssum = 0.f, ssq = 0.f;
 #pragma unroll
 		for (int it = 0; it < ITMAX; ++it) {
@@ -289,12 +323,12 @@ struct Consumer {
 #pragma unroll
 			for (int q = 0; q < Q; ++q) {
 				float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (ok) f = __ldcg(reinterpret_cast<const float4*>(xin + (size_t)v * VW) + q);
+				if (ok) f = staged ? *(reinterpret_cast<const float4*>(xbuf + (size_t)v * VW) + q) : __ldcg(reinterpret_cast<const float4*>(xin + (size_t)v * VW) + q);
 				xr[it][q * 4 + 0] = f.x, xr[it][q * 4 + 1] = f.y, xr[it][q * 4 + 2] = f.z, xr[it][q * 4 + 3] = f.w;
 				ssum += (f.x + f.y) + (f.z + f.w);
 			}
 		}
-		if (!normw) return;
+		if (!norm) return;
 		float mean = 0.f;
 		if (ln) mean = block_total(ssum) / (float)(m.ng * n);
 #pragma unroll
@@ -316,7 +350,7 @@ struct Consumer {
 			if (ok) {
 #pragma unroll
 				for (int q = 0; q < Q; ++q) {
-					float4 w = __ldg(reinterpret_cast<const float4*>(normw + (size_t)v * VW) + q);
+					float4 w = *(reinterpret_cast<const float4*>(nwbuf + (size_t)v * VW) + q);
 					float* xp = &xr[it][q * 4];
 					xp[0] = (xp[0] - mean) * scale * w.x, xp[1] = (xp[1] - mean) * scale * w.y;
 					xp[2] = (xp[2] - mean) * scale * w.z, xp[3] = (xp[3] - mean) * scale * w.w;
@@ -340,7 +374,13 @@ struct Consumer {
 			for (int a = rg.r0[ri]; a < rg.r1[ri]; a += R) {
 				const int rows = min(R, rg.r1[ri] - a);
 				const int vrows = rows * nseg; // <= NP * ng by construction of R
-				SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), err, 201);
+				if (tile_wait) {
+					unsigned long long tw = globaltimer_ns();
+					SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), err, 201);
+					*tile_wait += globaltimer_ns() - tw;
+				} else {
+					SPIN_WAIT(mbar_try_wait(&sh->full[rp.slot], rp.phase), err, 201);
+				}
 				const char* tile = ring + (size_t)rp.slot * slot_bytes;
 				if (!(dbg & 1)) {
 					// this group's rows of the tile: vr = grp + k * ng.  All loads first, then the math, then one
@@ -356,30 +396,29 @@ struct Consumer {
 							w[k][it] = (vr < vrows && it < m.it && v < nvec) ? lds128(rowp + v) : make_uint4(0, 0, 0, 0);
 						}
 					}
-					float acc[NP];
+					// branch-free math (rows / vectors beyond the tile carry zero weights): NP * 2 independent FMA chains
+					float acc[NP][2];
 #pragma unroll
-					for (int k = 0; k < NP; ++k) acc[k] = 0.f;
+					for (int k = 0; k < NP; ++k) acc[k][0] = 0.f, acc[k][1] = 0.f;
 #pragma unroll
 					for (int it = 0; it < ITMAX; ++it) {
-						if (it < m.it) { // uniform
-							float4 xv[Q];
+						float4 xv[Q];
 #pragma unroll
-							for (int q = 0; q < Q; ++q) xv[q] = make_float4(xr[it][q * 4], xr[it][q * 4 + 1], xr[it][q * 4 + 2], xr[it][q * 4 + 3]);
+						for (int q = 0; q < Q; ++q) xv[q] = make_float4(xr[it][q * 4], xr[it][q * 4 + 1], xr[it][q * 4 + 2], xr[it][q * 4 + 3]);
 #pragma unroll
-							for (int k = 0; k < NP; ++k)
-								if (grp + k * m.ng < vrows) acc[k] = dot_vec<DBITS>(w[k][it], xv, acc[k]); // uniform
-						}
+						for (int k = 0; k < NP; ++k) acc[k][it & 1] = dot_vec<DBITS>(w[k][it], xv, acc[k][it & 1]);
 					}
 					// two sums -> lanes 0 and 16 (5 shuffles instead of 10)
 					{
 						const bool hi = lane & 16;
-						float c = (hi ? acc[1] : acc[0]) + __shfl_xor_sync(0xffffffffu, hi ? acc[0] : acc[1], 16);
+						const float a0 = acc[0][0] + acc[0][1], a1 = acc[1][0] + acc[1][1];
+						float c = (hi ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi ? a0 : a1, 16);
 						c += __shfl_xor_sync(0xffffffffu, c, 8);
 						c += __shfl_xor_sync(0xffffffffu, c, 4);
 						c += __shfl_xor_sync(0xffffffffu, c, 2);
 						c += __shfl_xor_sync(0xffffffffu, c, 1);
 						const int vr = grp + (lane >> 4) * m.ng;
-						if ((lane & 15) == 0 && vr < vrows) sh->red[rp.slot][vr][wig] = c;
+						if ((lane & 15) == 0 && vr < vrows) sh->red[rp.slot][vr * m.wg + wig] = c;
 					}
 				}
 				// this warp is done reading the tile; find out whether it is the last one
@@ -400,9 +439,9 @@ struct Consumer {
 							int r = PAIR ? 2 * i : i;
 							float v0 = 0.f, v1 = 0.f;
 							const int rb = PAIR ? r + 1 : rows + r; // second value: next row, or same row of segment 2
-							for (int w_ = 0; w_ < m.wg; ++w_) v0 += sh->red[rp.slot][r][w_];
+							for (int w_ = 0; w_ < m.wg; ++w_) v0 += sh->red[rp.slot][r * m.wg + w_];
 							if (PAIR || nseg == 2)
-								for (int w_ = 0; w_ < m.wg; ++w_) v1 += sh->red[rp.slot][rb][w_];
+								for (int w_ = 0; w_ < m.wg; ++w_) v1 += sh->red[rp.slot][rb * m.wg + w_];
 							epi(ri, a + r, v0, v1);
 						}
 					}
@@ -429,25 +468,32 @@ __device__ __forceinline__ void halves8(const uint4& r, float (&o)[8]) {
 	o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y, o[4] = c.x, o[5] = c.y, o[6] = d.x, o[7] = d.y;
 }
 
-template <int HG>
+// HH = query heads per warp.  The 16 consumer warps form two halves of 8: both halves walk the same
+// positions of a tile (position p belongs to warp p-slot `wq` of each half), half 0 serves the first HH
+// heads of the unit, half 1 the rest -- half the registers per thread, K/V read twice from shared memory.
+template <int HH>
 __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, FusedShared* sh, const char* ring, float* scratch, const TokenParams& tp,
                                                 const __half* kc_l, const __half* vc_l, int unit, int split, int kvh, int t0, int t1, int TP, int warp, int lane) {
-	constexpr int P = HG > 4 ? 2 : 4;
+	constexpr int P = 2;
+	const int HG = a.attn_hg;
 	const int hd = a.head_dim, lpp = a.attn_lpp;
 	const int G = 32 / lpp;
 	const int grp = lane / lpp, li = lane % lpp;
 	const bool dact = li * 8 < hd;
 	const int kvrow = hd * 2;
+	const int half = warp / FUSED_AW, wq = warp % FUSED_AW;
+	const int h0 = half * HH;                               // first head (within the unit) of this warp
+	const int nh = max(0, min(HH, HG - h0));                // heads this warp really has
 	const int hbase = kvh * a.kv_mul + (unit % a.attn_qgroups) * HG;
 	const int tid = warp * 32 + lane;
 
-	float qr[HG][8], acc[HG][8], m[HG], l[HG];
+	float qr[HH][8], acc[HH][8], m[HH], l[HH];
 #pragma unroll
-	for (int h = 0; h < HG; ++h) {
+	for (int h = 0; h < HH; ++h) {
 		m[h] = -FLT_MAX, l[h] = 0.f;
 		float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-		if (dact) {
-			const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)(hbase + h) * hd + li * 8);
+		if (dact && h < nh) {
+			const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)(hbase + h0 + h) * hd + li * 8);
 			q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
 		}
 		qr[h][0] = q0.x, qr[h][1] = q0.y, qr[h][2] = q0.z, qr[h][3] = q0.w, qr[h][4] = q1.x, qr[h][5] = q1.y, qr[h][6] = q1.z, qr[h][7] = q1.w;
@@ -467,12 +513,12 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 			kt = ring + (size_t)rp.slot * a.slot_bytes;
 			vt = kt + (size_t)TP * kvrow;
 		}
-		for (int pb = 0; pb < ((a.dbg & 1) ? 0 : np); pb += FUSED_NCW * G * P) { // warp-uniform trip count
+		for (int pb = 0; pb < ((a.dbg & 1) ? 0 : np); pb += FUSED_AW * G * P) { // warp-uniform trip count
 			float kf[P][8], vf[P][8];
 			bool ok[P];
 #pragma unroll
 			for (int i = 0; i < P; ++i) {
-				int p = pb + (i * FUSED_NCW + warp) * G + grp;
+				int p = pb + (i * FUSED_AW + wq) * G + grp;
 				ok[i] = p < np && (fresh || (tb + p) != tp.kv_pos);
 				if (ok[i] && dact) {
 					if (fresh) {
@@ -490,23 +536,23 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 			}
 			// online-softmax update with P (position, K, V) triples held by this lane group
 #pragma unroll
-			for (int h = 0; h < HG; ++h) {
-				float s[P], smax = m[h];
+			for (int h = 0; h < HH; ++h) {
+				float sc[P], smax = m[h];
 #pragma unroll
 				for (int i = 0; i < P; ++i) {
 					float d = 0.f;
 #pragma unroll
 					for (int e = 0; e < 8; ++e) d = fmaf(qr[h][e], kf[i][e], d);
 					for (int o = 1; o < lpp; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-					s[i] = ok[i] ? d * a.inv_sqrt_hd : -FLT_MAX;
-					smax = fmaxf(smax, s[i]);
+					sc[i] = ok[i] ? d * a.inv_sqrt_hd : -FLT_MAX;
+					smax = fmaxf(smax, sc[i]);
 				}
 				float corr = expf(m[h] - smax);
 				m[h] = smax;
 				float pw[P], ps = 0.f;
 #pragma unroll
 				for (int i = 0; i < P; ++i) {
-					pw[i] = ok[i] ? expf(s[i] - smax) : 0.f;
+					pw[i] = ok[i] ? expf(sc[i] - smax) : 0.f;
 					ps += pw[i];
 				}
 				l[h] = fmaf(l[h], corr, ps);
@@ -529,7 +575,7 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 	// merge lane groups of a warp
 	for (int o = lpp; o < 32; o <<= 1) {
 #pragma unroll
-		for (int h = 0; h < HG; ++h) {
+		for (int h = 0; h < HH; ++h) {
 			float mo = __shfl_xor_sync(0xffffffffu, m[h], o), lo = __shfl_xor_sync(0xffffffffu, l[h], o);
 			float mn = fmaxf(m[h], mo);
 			float ca = expf(m[h] - mn), cb = expf(mo - mn);
@@ -542,17 +588,19 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 			m[h] = mn;
 		}
 	}
-	// merge warps: scratch[warp][h][hd + 2]
+	// merge warps: scratch[wq][head][hd + 2] (the two halves write disjoint heads)
 	const int rec = hd + 2;
 	if (grp == 0) {
 #pragma unroll
-		for (int h = 0; h < HG; ++h) {
-			float* r = scratch + ((size_t)warp * HG + h) * rec;
-			if (dact) {
+		for (int h = 0; h < HH; ++h) {
+			if (h < nh) {
+				float* r = scratch + ((size_t)wq * HG + h0 + h) * rec;
+				if (dact) {
 #pragma unroll
-				for (int e = 0; e < 8; ++e) r[li * 8 + e] = acc[h][e];
+					for (int e = 0; e < 8; ++e) r[li * 8 + e] = acc[h][e];
+				}
+				if (li == 0) r[hd] = m[h], r[hd + 1] = l[h];
 			}
-			if (li == 0) r[hd] = m[h], r[hd + 1] = l[h];
 		}
 	}
 	consumer_sync();
@@ -560,13 +608,13 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 	for (int idx = tid; idx < HG * rec; idx += FUSED_NCW * 32) {
 		int h = idx / rec, e = idx % rec;
 		float mn = -FLT_MAX;
-		for (int w = 0; w < FUSED_NCW; ++w) mn = fmaxf(mn, scratch[((size_t)w * HG + h) * rec + hd]);
+		for (int w = 0; w < FUSED_AW; ++w) mn = fmaxf(mn, scratch[((size_t)w * HG + h) * rec + hd]);
 		float v;
 		if (e == hd) {
 			v = mn;
 		} else {
 			v = 0.f;
-			for (int w = 0; w < FUSED_NCW; ++w) {
+			for (int w = 0; w < FUSED_AW; ++w) {
 				const float* r = scratch + ((size_t)w * HG + h) * rec;
 				v += r[e] * expf(r[hd] - mn);
 			}
@@ -588,22 +636,22 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 	__threadfence();
 	const int ns = a.attn_nsplit;
 	const float* pk = a.attn_partial + (size_t)unit * ns * HG * rec;
-	float* coef = scratch;                  // [ns][HG]  exp(m_s - M) ...
-	float* msv = scratch + (size_t)ns * HG; // [ns][HG]  m_s, then l_s * coef
+	float* coef = scratch;                  // [ns][HG]  l_s, then exp(m_s - M)
+	float* msv = scratch + (size_t)ns * HG; // [ns][HG]  m_s
 	for (int i = tid; i < ns * HG; i += FUSED_NCW * 32) {
 		const float* r = pk + (size_t)i * rec; // i = s * HG + h
-		coef[i] = __ldcg(r + hd + 1);          // l_s
-		msv[i] = __ldcg(r + hd);               // m_s
+		coef[i] = __ldcg(r + hd + 1);
+		msv[i] = __ldcg(r + hd);
 	}
 	consumer_sync();
 	if (tid < HG) {
 		float M = -FLT_MAX;
-		for (int s = 0; s < ns; ++s) M = fmaxf(M, msv[s * HG + tid]);
+		for (int s_ = 0; s_ < ns; ++s_) M = fmaxf(M, msv[s_ * HG + tid]);
 		float L = 0.f;
-		for (int s = 0; s < ns; ++s) {
-			float c = expf(msv[s * HG + tid] - M);
-			L = fmaf(coef[s * HG + tid], c, L);
-			coef[s * HG + tid] = c;
+		for (int s_ = 0; s_ < ns; ++s_) {
+			float c = expf(msv[s_ * HG + tid] - M);
+			L = fmaf(coef[s_ * HG + tid], c, L);
+			coef[s_ * HG + tid] = c;
 		}
 		sh->scratch[tid] = 1.0f / L; // HG <= 8
 	}
@@ -611,14 +659,14 @@ __device__ __noinline__ RingPos fused_attention(const FusedArgs& a, RingPos rp, 
 	for (int idx = tid; idx < HG * hd; idx += FUSED_NCW * 32) {
 		int h = idx / hd, e = idx % hd;
 		float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-		int s = 0;
-		for (; s + 4 <= ns; s += 4) {
-			float p0 = __ldcg(pk + ((size_t)(s + 0) * HG + h) * rec + e), p1 = __ldcg(pk + ((size_t)(s + 1) * HG + h) * rec + e);
-			float p2 = __ldcg(pk + ((size_t)(s + 2) * HG + h) * rec + e), p3 = __ldcg(pk + ((size_t)(s + 3) * HG + h) * rec + e);
-			n0 = fmaf(p0, coef[(s + 0) * HG + h], n0), n1 = fmaf(p1, coef[(s + 1) * HG + h], n1);
-			n2 = fmaf(p2, coef[(s + 2) * HG + h], n2), n3 = fmaf(p3, coef[(s + 3) * HG + h], n3);
+		int s_ = 0;
+		for (; s_ + 4 <= ns; s_ += 4) {
+			float p0 = __ldcg(pk + ((size_t)(s_ + 0) * HG + h) * rec + e), p1 = __ldcg(pk + ((size_t)(s_ + 1) * HG + h) * rec + e);
+			float p2 = __ldcg(pk + ((size_t)(s_ + 2) * HG + h) * rec + e), p3 = __ldcg(pk + ((size_t)(s_ + 3) * HG + h) * rec + e);
+			n0 = fmaf(p0, coef[(s_ + 0) * HG + h], n0), n1 = fmaf(p1, coef[(s_ + 1) * HG + h], n1);
+			n2 = fmaf(p2, coef[(s_ + 2) * HG + h], n2), n3 = fmaf(p3, coef[(s_ + 3) * HG + h], n3);
 		}
-		for (; s < ns; ++s) n0 = fmaf(__ldcg(pk + ((size_t)s * HG + h) * rec + e), coef[s * HG + h], n0);
+		for (; s_ < ns; ++s_) n0 = fmaf(__ldcg(pk + ((size_t)s_ * HG + h) * rec + e), coef[s_ * HG + h], n0);
 		__stcg(a.att + (size_t)(hbase + h) * hd + e, ((n0 + n1) + (n2 + n3)) * sh->scratch[h]);
 	}
 	if (tid == 0) a.attn_counter[unit] = 0;
@@ -632,14 +680,20 @@ struct StageCtx {
 	FusedShared* sh;
 	const char* ring;
 	float* attn_scratch;
+	float* xbuf;
+	float* nwbuf;
 	int warp, lane;
 };
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
+// Norm weights of the NEXT normed stage -> shared memory; issued before a grid barrier so the loads are
+// off the critical path after it.
+__device__ __forceinline__ void prefetch_normw(const StageCtx& cx, const float* w, int n) {
+	if (!w) return;
+	const float4* src = reinterpret_cast<const float4*>(w);
+	float4* dst = reinterpret_cast<float4*>(cx.nwbuf);
+	for (int i = cx.warp * 32 + cx.lane; i < n / 4; i += FUSED_NCW * 32) dst[i] = __ldg(src + i);
 }
+
 __device__ __forceinline__ unsigned long long stage_begin(const FusedArgs& a) {
 	return (a.perf && blockIdx.x == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
 }
@@ -676,6 +730,8 @@ __device__ __noinline__ RingPos stage_matrix(const FusedArgs& a, const StageCtx 
 	Consumer<DBITS, XR> c;
 	c.sh = cx.sh, c.ring = cx.ring, c.slot_bytes = a.slot_bytes, c.err = a.err, c.dbg = a.dbg;
 	c.cw = cx.warp, c.lane = cx.lane;
+	c.xbuf = cx.xbuf, c.nwbuf = cx.nwbuf;
+	c.tile_wait = (a.perf && blockIdx.x == 0 && threadIdx.x == 0) ? a.perf + 24 + kind : nullptr;
 
 	// what this stage reads, which rows it owns, how its tiles are cut
 	const float* xin = a.x;
@@ -715,7 +771,8 @@ __device__ __noinline__ RingPos stage_matrix(const FusedArgs& a, const StageCtx 
 	const RowMap m = row_map<DBITS, XR>(nv);
 	const int R = tile_rows(a.slot_bytes, nseg, nv * 16, unit, m.ng);
 
-	c.load_x(m, xin, n, normw, a.eps, a.ln != 0, (kind == SK_QKV && a.norm_par && blockIdx.x == 0) ? a.xb : nullptr);
+	c.load_x(m, xin, n, normw != nullptr, a.eps, a.ln != 0, (kind == SK_QKV && a.norm_par && blockIdx.x == 0) ? a.xb : nullptr);
+	if (c.tile_wait) a.perf[16 + kind] += globaltimer_ns() - t_begin;
 
 	const size_t kv_layer = (size_t)a.n_kv_heads * a.seq_len * a.head_dim;
 	float best_v = -FLT_MAX;
@@ -757,6 +814,9 @@ __device__ __noinline__ RingPos stage_matrix(const FusedArgs& a, const StageCtx 
 	});
 
 	if (kind != SK_OUT) {
+		// norm weights of the next normed stage (this stage's copy was consumed by load_x above)
+		if (kind == SK_QKV && !a.norm_par) prefetch_normw(cx, L.rms_ffn, a.dim);
+		if (kind == SK_UP) prefetch_normw(cx, l + 1 < a.n_layers ? c_fused_layers[l + 1].rms_att : (a.mode != 0 ? a.rms_final : nullptr), a.dim);
 		stage_barrier(a, 300 + kind, kind, t_begin);
 		return rp;
 	}
@@ -788,7 +848,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 	extern __shared__ __align__(128) char smem_raw[];
 	FusedShared* sh = reinterpret_cast<FusedShared*>(smem_raw);
 	float* attn_scratch = reinterpret_cast<float*>(smem_raw + ((sizeof(FusedShared) + 127) & ~(size_t)127));
-	char* ring = reinterpret_cast<char*>(attn_scratch) + a.attn_scratch_bytes;
+	float* xbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(attn_scratch) + a.attn_scratch_bytes);
+	float* nwbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(xbuf) + a.xbuf_bytes);
+	char* ring = reinterpret_cast<char*>(nwbuf) + a.nwbuf_bytes;
 
 	constexpr int VW = WFmt<DBITS>::VW;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -840,6 +902,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 		Producer p;
 		p.sh = sh, p.ring = ring, p.slot_bytes = a.slot_bytes, p.err = a.err, p.dbg = a.dbg;
 		p.rp.init(a.nslots);
+		p.lp.init(a.nslots);
+		p.ahead = 0, p.window = a.window;
 		p.pol_w = l2_policy_evict_first();
 		p.pol_kv = l2_policy_evict_last();
 		for (int l = 0; l < a.n_layers; ++l) {
@@ -863,7 +927,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 
 	// ================================================================= consumer warps
 	StageCtx cx;
-	cx.sh = sh, cx.ring = ring, cx.attn_scratch = attn_scratch, cx.warp = warp, cx.lane = lane;
+	cx.sh = sh, cx.ring = ring, cx.attn_scratch = attn_scratch, cx.xbuf = xbuf, cx.nwbuf = nwbuf, cx.warp = warp, cx.lane = lane;
+	prefetch_normw(cx, c_fused_layers[0].rms_att, a.dim);
 	RingPos rp;
 	rp.init(a.nslots);
 
@@ -881,15 +946,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 		if (has_item) {
 			const __half* kc_l = a.kc + l * kv_layer;
 			const __half* vc_l = a.vc + l * kv_layer;
-			switch (a.attn_hg) {
+			switch ((a.attn_hg + 1) / 2) { // heads per warp
 			case 1: rp = fused_attention<1>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
 			case 2: rp = fused_attention<2>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
 			case 3: rp = fused_attention<3>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
-			case 4: rp = fused_attention<4>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
-			case 5: rp = fused_attention<5>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
-			case 6: rp = fused_attention<6>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
-			case 7: rp = fused_attention<7>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
-			default: rp = fused_attention<8>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
+			default: rp = fused_attention<4>(a, rp, sh, ring, attn_scratch, tp, kc_l, vc_l, unit, split, kvh, t0, t1, TP, warp, lane); break;
 			}
 		}
 		stage_barrier(a, 302, 2, t_attn);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "calm_b200_abi_version", "calm_b200_set_device", "calm_b200_free", "calm_b200_release", "calm_b200_set_engine",
     "calm_b200_forward_argmax", "calm_b200_decode_greedy", "calm_b200_timer_start", "calm_b200_timer_stop",
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
-    "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_engine_in_use", "calm_b200_stage_wait_ms", "calm_b200_barrier_bench",
+    "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_engine_in_use", "calm_b200_stage_wait_ms", "calm_b200_barrier_bench", "calm_b200_stage_detail_ms",
 ]
 
 _lib = None
@@ -66,6 +66,7 @@ def load() -> C.CDLL:
     L.calm_b200_engine_in_use.argtypes, L.calm_b200_engine_in_use.restype = [], C.c_int
     L.calm_b200_stage_wait_ms.argtypes, L.calm_b200_stage_wait_ms.restype = [C.c_int], C.c_double
     L.calm_b200_barrier_bench.argtypes, L.calm_b200_barrier_bench.restype = [C.c_int], C.c_float
+    L.calm_b200_stage_detail_ms.argtypes, L.calm_b200_stage_detail_ms.restype = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)], None
     _lib = L
     return L
 
@@ -151,7 +152,9 @@ class DeviceModel:
         name = C.create_string_buffer(64)
         ms, by, nl = C.c_double(), C.c_double(), C.c_long()
         while self.lib.calm_b200_stage_stats(i, name, 64, C.byref(ms), C.byref(by), C.byref(nl)):
-            out[name.value.decode()] = (ms.value, by.value, nl.value, self.lib.calm_b200_stage_wait_ms(i) if mode == 2 else 0.0)
+            lx, tw = C.c_double(), C.c_double()
+            self.lib.calm_b200_stage_detail_ms(i, C.byref(lx), C.byref(tw))
+            out[name.value.decode()] = (ms.value, by.value, nl.value, self.lib.calm_b200_stage_wait_ms(i) if mode == 2 else 0.0, lx.value, tw.value)
             i += 1
         self.lib.calm_b200_set_perf(0)
         return out

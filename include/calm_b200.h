@@ -125,6 +125,8 @@ int calm_b200_stage_stats(int stage, char* name, int name_cap, double* ms_total,
 
 /* Fused engine only: the part of stage_stats()'s ms_total that CTA 0 spent waiting in the grid barrier. */
 double calm_b200_stage_wait_ms(int stage);
+/* ... and the parts spent loading the stage's activation slice and waiting for weight tiles to land. */
+void calm_b200_stage_detail_ms(int stage, double* load_x_ms, double* tile_wait_ms);
 
 /* Micro-benchmark: microseconds per grid barrier of the fused engine (all SMs, no work in between). */
 float calm_b200_barrier_bench(int rounds);
