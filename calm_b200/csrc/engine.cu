@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "fused.cuh"
+#include "persist.cuh"
 #include "stages.cuh"
 
 namespace {
@@ -73,6 +74,11 @@ struct Engine {
 	bool fused_perf = false;
 	cudaGraphExec_t fgraph[4] = {nullptr, nullptr, nullptr, nullptr};
 	int fgraph_launches[4] = {0, 0, 0, 0};
+
+	// persistent engine (engine kind 2)
+	bool persist_ok = false;
+	size_t persist_smem = 0;
+	int persist_nsplit = 1;
 
 	// graphs: 0 = kv only, 1 = logits to host, 2 = logits to device + greedy advance, 3 = logits to host + argmax
 	cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -165,8 +171,10 @@ struct StageTimer {
 
 template <typename KVT, int HG>
 void launch_attn(const AttnArgs& a, int nunits, int* nl) {
-	size_t smem = (size_t)4 * HG * (a.head_dim + 2) * sizeof(float);
-	k_attn<KVT, HG><<<nunits * a.nsplit, 128, smem, g.stream>>>(a);
+	size_t smem = (size_t)(ATTN_THREADS / 32) * HG * (a.head_dim + 2) * sizeof(float);
+	size_t smem2 = (size_t)(2 * a.nsplit + 1) * HG * sizeof(float);
+	if (smem2 > smem) smem = smem2;
+	k_attn<KVT, HG><<<nunits * a.nsplit, ATTN_THREADS, smem, g.stream>>>(a);
 	++*nl;
 }
 
@@ -454,6 +462,110 @@ int run_token_fused(int mode) {
 	return nl;
 }
 
+// ---------------------------------------------------------------------------------------------
+// persistent engine: plan + launch
+
+template <int DBITS, int HH>
+void persist_launch_t(const PersistArgs& pa, bool attr_only) {
+	auto kern = k_persist<DBITS, __half, HH>;
+	if (attr_only) {
+		CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.persist_smem));
+		int per_sm = 0;
+		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PERSIST_THREADS, g.persist_smem));
+		if (per_sm < 1) g.persist_ok = false;
+		return;
+	}
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(g.sms), cfg.blockDim = dim3(PERSIST_THREADS), cfg.dynamicSmemBytes = g.persist_smem, cfg.stream = g.stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeCooperative;
+	at[0].val.cooperative = 1;
+	cfg.attrs = at, cfg.numAttrs = 1;
+	CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, pa));
+}
+
+template <int DBITS>
+void persist_launch_hh(const PersistArgs& pa, bool attr_only) {
+	switch ((g.attn_hg + 1) / 2) {
+	case 1: persist_launch_t<DBITS, 1>(pa, attr_only); break;
+	case 2: persist_launch_t<DBITS, 2>(pa, attr_only); break;
+	case 3: persist_launch_t<DBITS, 3>(pa, attr_only); break;
+	default: persist_launch_t<DBITS, 4>(pa, attr_only); break;
+	}
+}
+
+void persist_launch(const PersistArgs& pa, bool attr_only) {
+	switch (g.w.dbits) {
+	case 16: persist_launch_hh<16>(pa, attr_only); break;
+	case 8: persist_launch_hh<8>(pa, attr_only); break;
+	default: persist_launch_hh<4>(pa, attr_only); break;
+	}
+}
+
+void persist_plan() {
+	const Config& c = g.cfg;
+	g.persist_ok = false;
+	if (c.n_experts || g.kvbits != 16) return; // MoE and fp8 KV: staged engine
+	int units = c.n_kv_heads * g.attn_qgroups;
+	g.persist_nsplit = g.sms / units;
+	if (g.persist_nsplit < 1) return;
+	int maxsplit = cdiv(c.seq_len, 32);
+	if (g.persist_nsplit > maxsplit) g.persist_nsplit = maxsplit;
+	if (g.persist_nsplit > g.attn_nsplit_cap) g.persist_nsplit = g.attn_nsplit_cap;
+	size_t need = g.smem_dim > g.smem_hidden ? g.smem_dim : g.smem_hidden;
+	if (g.smem_qdim > need) need = g.smem_qdim;
+	size_t attn = (size_t)(PERSIST_WARPS / 2) * g.attn_hg * (c.head_dim + 2) * sizeof(float);
+	size_t attn2 = (size_t)(2 * g.persist_nsplit + 1) * g.attn_hg * sizeof(float);
+	if (attn > need) need = attn;
+	if (attn2 > need) need = attn2;
+	if (need > 220 * 1024) return;
+	g.persist_smem = need;
+	PersistLayer layers[MAX_LAYERS] = {};
+	for (int l = 0; l < c.n_layers; ++l) {
+		layers[l].wq = g.w.wq[l], layers[l].wk = g.w.wk[l], layers[l].wv = g.w.wv[l], layers[l].wo = g.w.wo[l];
+		layers[l].w1 = g.w.w1[l], layers[l].w2 = g.w.w2[l], layers[l].w3 = g.w.w3[l];
+		layers[l].rms_att = g.w.rms_att_weight[l], layers[l].rms_ffn = g.w.rms_ffn_weight[l], layers[l].bqkv = g.w.bqkv[l];
+	}
+	CUDA_CHECK(cudaMemcpyToSymbol(c_persist_layers, layers, sizeof(layers)));
+	if (!g.fused_bar) {
+		g.fused_bar = (unsigned*)dev_alloc(sizeof(unsigned));
+		CUDA_CHECK(cudaMemset(g.fused_bar, 0, sizeof(unsigned)));
+		CUDA_CHECK(cudaHostAlloc((void**)&g.fused_err, sizeof(int), cudaHostAllocMapped));
+		*g.fused_err = 0;
+		g.fused_perf_ns = (unsigned long long*)dev_alloc(32 * sizeof(unsigned long long));
+		CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 32 * sizeof(unsigned long long)));
+	}
+	g.persist_ok = true;
+	PersistArgs none = {};
+	persist_launch(none, true); // shared-memory opt-in + occupancy check, outside of any stream capture
+}
+
+int run_token_persist(int mode) {
+	const Config& c = g.cfg;
+	PersistArgs pa = {};
+	pa.dim = c.dim, pa.hidden = c.hidden_dim, pa.q_dim = g.q_dim, pa.kv_dim = g.kv_dim, pa.head_dim = c.head_dim;
+	pa.n_heads = c.n_heads, pa.n_kv_heads = c.n_kv_heads, pa.n_layers = c.n_layers, pa.vocab = c.vocab_size, pa.seq_len = c.seq_len, pa.kv_mul = g.kv_mul;
+	pa.eps = c.norm_eps, pa.clip = c.qkv_clip, pa.ln = c.norm_ln, pa.norm_par = c.norm_par, pa.gelu = c.act_gelu;
+	pa.x = g.x, pa.xb = g.xb, pa.q = g.q, pa.att = g.att, pa.hb = g.hb;
+	pa.logits = (mode == 2) ? g.logits_dev : g.logits_host;
+	pa.attn_partial = g.attn_partial, pa.attn_counter = g.attn_counter;
+	pa.kc = g.kc, pa.vc = g.vc, pa.rope_freq = g.rope_freq;
+	pa.embed = g.w.token_embedding_table, pa.wcls = g.w.wcls, pa.rms_final = g.w.rms_final_weight;
+	pa.tp = g.tp, pa.bar = g.fused_bar, pa.err = g.fused_err;
+	pa.perf = g.fused_perf ? g.fused_perf_ns : nullptr;
+	pa.cand_val = (mode >= 2) ? g.cand_val : nullptr, pa.cand_idx = g.cand_idx;
+	pa.mode = mode;
+	pa.attn_nsplit = g.persist_nsplit, pa.attn_hg = g.attn_hg, pa.attn_qgroups = g.attn_qgroups, pa.attn_lpp = g.attn_lpp;
+	pa.inv_sqrt_hd = 1.0f / sqrtf((float)c.head_dim);
+	persist_launch(pa, false);
+	int nl = 1;
+	if (mode >= 2) {
+		k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, g.sms, g.tp, g.out_tokens, g.last_token, mode == 2, c.vocab_size);
+		++nl;
+	}
+	return nl;
+}
+
 // per-stage algorithmic bytes of one token (the reference's accounting, infer.cu:683-699)
 void account_fused_bytes(int mode) {
 	const Config& c = g.cfg;
@@ -471,18 +583,20 @@ void account_fused_bytes(int mode) {
 void launch_token(int mode) {
 	// the persistent kernel serves every token it can; the rest (MoE, fp8 KV, rolled-over cache,
 	// per-stage profiling) goes through the staged engine.  Both are CUDA paths over the same buffers.
-	const bool fused = g.engine == 1 && g.fused_ok && (!g.perf || g.fused_perf) && !g.debug_stages && g.cur_pos < g.cfg.seq_len;
-	if (fused) {
+	const bool one_kernel = ((g.engine == 1 && g.fused_ok) || (g.engine == 2 && g.persist_ok)) && (!g.perf || g.fused_perf) && !g.debug_stages &&
+	                        g.cur_pos < g.cfg.seq_len;
+	if (one_kernel) {
+		auto run = [&](int m) { return g.engine == 2 ? run_token_persist(m) : run_token_fused(m); };
 		if (!g.use_graph || g.fused_perf) {
 			if (g.fused_perf) account_fused_bytes(mode);
-			g_launches += run_token_fused(mode);
+			g_launches += run(mode);
 			CUDA_CHECK(cudaGetLastError());
 			return;
 		}
 		if (!g.fgraph[mode]) {
 			cudaGraph_t graph;
 			CUDA_CHECK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
-			g.fgraph_launches[mode] = run_token_fused(mode);
+			g.fgraph_launches[mode] = run(mode);
 			CUDA_CHECK(cudaStreamEndCapture(g.stream, &graph));
 			CUDA_CHECK(cudaGraphInstantiate(&g.fgraph[mode], graph, 0));
 			CUDA_CHECK(cudaGraphDestroy(graph));
@@ -529,7 +643,7 @@ extern "C" void calm_b200_set_device(int device) {
 }
 
 extern "C" int calm_b200_engine_in_use(void) {
-	return g.ready && g.engine == 1 && g.fused_ok ? 1 : 0;
+	return g.ready && ((g.engine == 1 && g.fused_ok) || (g.engine == 2 && g.persist_ok)) ? g.engine : 0;
 }
 
 extern "C" void calm_b200_set_engine(int engine) {
@@ -625,7 +739,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.attn_lpp = 1;
 	while (g.attn_lpp * 8 < c.head_dim) g.attn_lpp *= 2;
 	int units = c.n_kv_heads * g.attn_qgroups;
-	int want = cdiv(2 * g.sms, units);                  // ~2 CTAs per SM
+	int want = g.sms / units;                           // about one 256-thread CTA per SM
 	int maxsplit = cdiv(c.seq_len, 64);                 // at least 64 positions per slice at full context
 	g.attn_nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
 	g.attn_partial = (float*)dev_alloc((size_t)units * g.attn_nsplit * g.attn_hg * (c.head_dim + 2) * sizeof(float));
@@ -643,7 +757,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.tp = (TokenParams*)dev_alloc(sizeof(TokenParams));
 	CUDA_CHECK(cudaMemset(g.tp, 0, sizeof(TokenParams)));
 
-	g.engine = g_engine_kind >= 0 ? g_engine_kind : (getenv("CALM_B200_ENGINE") ? atoi(getenv("CALM_B200_ENGINE")) : 1);
+	g.engine = g_engine_kind >= 0 ? g_engine_kind : (getenv("CALM_B200_ENGINE") ? atoi(getenv("CALM_B200_ENGINE")) : 2);
 	switch (w.dbits) {
 	case 16: make_plan_kv<16>(); break;
 	case 8: make_plan_kv<8>(); break;
@@ -656,7 +770,8 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
 
 	if (g.engine == 1) fused_plan();
-	g.fused_perf = want_fused_perf && g.fused_ok;
+	if (g.engine == 2) persist_plan();
+	g.fused_perf = want_fused_perf && (g.fused_ok || g.persist_ok);
 
 	// what the reference backend publishes in RunState (infer.cu:99-112)
 	s->x = g.x, s->hb = g.hb, s->he = g.hb, s->q = g.q, s->att = g.att;
@@ -860,7 +975,7 @@ static void fused_perf_collect() {
 extern "C" void calm_b200_set_perf(int on) {
 	if (!on) fused_perf_collect();
 	g.perf = on != 0;
-	g.fused_perf = on == 2 && g.fused_ok;
+	g.fused_perf = on == 2 && (g.fused_ok || g.persist_ok);
 	if (g.fused_perf_ns) CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 32 * sizeof(unsigned long long)));
 	if (!on) return;
 	for (int i = 0; i < ST_COUNT; ++i) g.stage_ms[i] = 0, g.stage_bytes[i] = 0, g.stage_launches[i] = 0;

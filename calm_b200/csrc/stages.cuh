@@ -61,20 +61,77 @@ __device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int n
 // Stage an activation vector into shared memory in the permuted layout of common.cuh, optionally
 // applying RMSNorm / LayerNorm-without-bias first (reference infer.c:183-207: mean only when ln,
 // variance around the mean, eps inside the sqrt, then * weight).  Ends with a __syncthreads().
+// Every thread requests all of its elements (16-byte loads, up to SV_MAX per thread) before it touches the
+// first one, so staging costs one L2 round trip instead of one per element; the vector is read through L2
+// (inside the persistent kernel other SMs wrote it during the same launch).
+#define SV_MAX 8
 template <int DBITS>
 __device__ __forceinline__ void stage_vector(float* xs, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln,
                                              float* xb_out) {
 	const int tid = threadIdx.x, nthr = blockDim.x;
+	const int n4 = n >> 2; // n is a multiple of 32
+	const int total4 = xs_floats<DBITS>(n) >> 2;
+	const float4* x4 = reinterpret_cast<const float4*>(x);
+	if (n4 <= nthr * SV_MAX) {
+		float4 v[SV_MAX];
+#pragma unroll
+		for (int k = 0; k < SV_MAX; ++k) {
+			int i = tid + k * nthr;
+			v[k] = i < n4 ? __ldcg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		if (normw) {
+			float4 w[SV_MAX];
+#pragma unroll
+			for (int k = 0; k < SV_MAX; ++k) {
+				int i = tid + k * nthr;
+				w[k] = i < n4 ? __ldg(reinterpret_cast<const float4*>(normw) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			float mean = 0.f;
+			if (ln) {
+				float s = 0.f;
+#pragma unroll
+				for (int k = 0; k < SV_MAX; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+				mean = block_sum(s, red) / n;
+			}
+			float ss = 0.f;
+#pragma unroll
+			for (int k = 0; k < SV_MAX; ++k) {
+				if (tid + k * nthr < n4) {
+					float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+					ss = fmaf(dx, dx, ss), ss = fmaf(dy, dy, ss), ss = fmaf(dz, dz, ss), ss = fmaf(dw, dw, ss);
+				}
+			}
+			ss = block_sum(ss, red);
+			const float scale = 1.0f / sqrtf(ss / n + eps);
+#pragma unroll
+			for (int k = 0; k < SV_MAX; ++k) {
+				v[k].x = (v[k].x - mean) * scale * w[k].x, v[k].y = (v[k].y - mean) * scale * w[k].y;
+				v[k].z = (v[k].z - mean) * scale * w[k].z, v[k].w = (v[k].w - mean) * scale * w[k].w;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < SV_MAX; ++k) {
+			int i = tid + k * nthr;
+			if (i < n4) {
+				if (xb_out) reinterpret_cast<float4*>(xb_out)[i] = v[k];
+				*reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = v[k]; // 4 consecutive elements stay consecutive
+			}
+		}
+		for (int i = n4 + tid; i < total4; i += nthr) *reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = make_float4(0.f, 0.f, 0.f, 0.f);
+		__syncthreads();
+		return;
+	}
+	// long vectors: same thing, element by element (two reads of x when normalising)
 	float mean = 0.f, scale = 1.f;
 	if (normw) {
 		if (ln) {
 			float s = 0.f;
-			for (int j = tid; j < n; j += nthr) s += x[j];
+			for (int j = tid; j < n; j += nthr) s += __ldcg(x + j);
 			mean = block_sum(s, red) / n;
 		}
 		float ss = 0.f;
 		for (int j = tid; j < n; j += nthr) {
-			float d = x[j] - mean;
+			float d = __ldcg(x + j) - mean;
 			ss = fmaf(d, d, ss);
 		}
 		ss = block_sum(ss, red);
@@ -84,7 +141,7 @@ __device__ __forceinline__ void stage_vector(float* xs, float* red, const float*
 	for (int j = tid; j < total; j += nthr) {
 		float v = 0.f;
 		if (j < n) {
-			v = x[j];
+			v = __ldcg(x + j);
 			if (normw) v = (v - mean) * scale * normw[j];
 			if (xb_out) xb_out[j] = v;
 		}
@@ -218,94 +275,125 @@ __global__ void __launch_bounds__(256) k_qkv(const QkvArgs<KVT> a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_attn: one CTA per (kv head, slice of positions).  All KVMUL query heads that share the kv head
-// are processed together so K and V are read once.  A group of LPP lanes owns one position at a time
-// (8 head dims per lane, one 16-byte load of K and of V); P positions are in flight per group.
-// Scores are scaled by 1/sqrt(head_dim) after the dot (reference infer.c:246), softmax is the
-// max-shifted one of infer.c:252-258 evaluated online, and the 1/sum is applied once at the end.
+// Attention (flash-decoding).  Work item = (unit, slice): a unit is one kv head together with a group of
+// HG query heads that share it (so K and V are read once for all of them), a slice is a contiguous range
+// of cached positions.  A group of LPP lanes owns one position at a time (8 head dims per lane: one
+// 16-byte load of K and one of V); P positions per group are in flight and the next P are requested
+// before the current ones are consumed.  Scores are scaled by 1/sqrt(head_dim) after the dot (reference
+// infer.c:246), the softmax is the max-shifted one of infer.c:252-258 evaluated online, and 1/sum is
+// applied once at the end.  Slices are merged through global partials (m, l, acc[head_dim]) by the last
+// CTA of the unit to arrive, in two passes whose loads are all independent.
 
 struct AttnArgs {
 	const float* q;   // [n_heads*head_dim] rotated queries
 	const void* kc;   // this layer
 	const void* vc;
-	float* partial;   // [units][nsplit][KVMUL][head_dim + 2], unit = (kv head, group of KVMUL query heads)
+	float* partial;   // [units][nsplit][HG][head_dim + 2]
 	unsigned* counter; // [units], zero between launches
 	float* out;       // [n_heads*head_dim]
 	const TokenParams* tp;
 	int head_dim, seq_len, nsplit, lpp; // lpp: lanes per position (power of two >= head_dim/8)
-	int kv_mul, qgroups;                // query heads per kv head; qgroups = kv_mul / KVMUL
+	int kv_mul, qgroups;                // query heads per kv head; qgroups = kv_mul / HG
 	float inv_sqrt_hd;
 };
 
-template <typename KVT, int KVMUL>
-__global__ void __launch_bounds__(128) k_attn(const AttnArgs a) {
-	constexpr int P = KVMUL > 4 ? 2 : 4;
-	extern __shared__ __align__(16) float smem[];
-	__shared__ int is_last;
+template <typename KVT>
+struct KvRaw;
+template <>
+struct KvRaw<__half> {
+	typedef uint4 type; // 8 halves
+	static __device__ __forceinline__ uint4 load(const __half* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+	static __device__ __forceinline__ uint4 zero() { return make_uint4(0, 0, 0, 0); }
+	static __device__ __forceinline__ void unpack(const uint4& r, float (&o)[8]) {
+		float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+		float2 c = __half22float2(*reinterpret_cast<const __half2*>(&r.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&r.w));
+		o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y, o[4] = c.x, o[5] = c.y, o[6] = d.x, o[7] = d.y;
+	}
+};
+template <>
+struct KvRaw<uint8_t> {
+	typedef uint2 type; // 8 e5m2 bytes
+	static __device__ __forceinline__ uint2 load(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint2*>(p)); }
+	static __device__ __forceinline__ uint2 zero() { return make_uint2(0, 0); }
+	static __device__ __forceinline__ void unpack(const uint2& r, float (&o)[8]) {
+		float2 a = e5m2x2_lo(r.x), b = e5m2x2_hi(r.x), c = e5m2x2_lo(r.y), d = e5m2x2_hi(r.y);
+		o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y, o[4] = c.x, o[5] = c.y, o[6] = d.x, o[7] = d.y;
+	}
+};
 
-	const int unit = blockIdx.x / a.nsplit, split = blockIdx.x % a.nsplit;
+// One work item, executed by all warps of the calling CTA.  The warps form `hsets` equal sets (1 or 2);
+// every set walks all positions of the slice and serves HH of the unit's HG query heads (set s: heads
+// s*HH ...), which halves the per-thread state when a CTA has many warps but few registers.
+// P positions per lane group are in flight; PIPE requests the next P before consuming the current ones.
+// scratch: shared, >= max((nwarps / hsets) * HG * (hd + 2), 2 * nsplit * HG) floats.  flag: shared int.
+template <typename KVT, int HH, int P, bool PIPE>
+__device__ __forceinline__ void attn_item(const AttnArgs& a, int HG, int hsets, int unit, int split, int kv_len, float* scratch, int* flag) {
+	typedef typename KvRaw<KVT>::type raw_t;
 	const int kvh = unit / a.qgroups;
-	const int hbase = kvh * a.kv_mul + (unit % a.qgroups) * KVMUL; // first query head of this unit
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const int hbase = kvh * a.kv_mul + (unit % a.qgroups) * HG; // first query head of this unit
+	const int lane = threadIdx.x & 31, nwarps = (blockDim.x >> 5) / hsets;
+	const int wset = (threadIdx.x >> 5) / nwarps, warp = (threadIdx.x >> 5) % nwarps;
+	const int h0 = wset * HH;                  // first head (within the unit) of this warp
+	const int nh = max(0, min(HH, HG - h0));   // heads this warp really has
 	const int hd = a.head_dim, lpp = a.lpp;
-	const int G = 32 / lpp;          // position groups per warp
+	const int G = 32 / lpp; // position groups per warp
 	const int grp = lane / lpp, li = lane % lpp;
-	const bool dact = li * 8 < hd;   // lane holds real head dims
+	const bool dact = li * 8 < hd; // lane holds real head dims
 
-	const int kv_len = a.tp->kv_len;
 	const int chunk = (kv_len + a.nsplit - 1) / a.nsplit;
 	const int t0 = split * chunk, t1 = min(kv_len, t0 + chunk);
 
 	const KVT* kbase = reinterpret_cast<const KVT*>(a.kc) + (size_t)kvh * a.seq_len * hd + li * 8;
 	const KVT* vbase = reinterpret_cast<const KVT*>(a.vc) + (size_t)kvh * a.seq_len * hd + li * 8;
 
-	float qr[KVMUL][8], acc[KVMUL][8], m[KVMUL], l[KVMUL];
+	float qr[HH][8], acc[HH][8], m[HH], l[HH];
 #pragma unroll
-	for (int h = 0; h < KVMUL; ++h) {
+	for (int h = 0; h < HH; ++h) {
 		m[h] = -FLT_MAX, l[h] = 0.f;
 #pragma unroll
 		for (int d = 0; d < 8; ++d) {
 			acc[h][d] = 0.f;
-			qr[h][d] = dact ? a.q[(size_t)(hbase + h) * hd + li * 8 + d] : 0.f;
+			qr[h][d] = (dact && h < nh) ? __ldcg(a.q + (size_t)(hbase + h0 + h) * hd + li * 8 + d) : 0.f;
 		}
 	}
 
-	const int stride = nwarps * G;
-	// the trip count must be warp-uniform: the score reduction below shuffles across the full warp
-	for (int tw = t0 + warp * G; tw < t1; tw += stride * P) {
-		const int tb = tw + grp;
+	const int stride = nwarps * G; // positions per step over all groups of a warp set
+	auto fetch = [&](int tw, raw_t (&kr)[P], raw_t (&vr)[P]) {
+#pragma unroll
+		for (int i = 0; i < P; ++i) {
+			int t = tw + grp + i * stride;
+			bool ok = t < t1 && dact;
+			kr[i] = ok ? KvRaw<KVT>::load(kbase + (size_t)t * hd) : KvRaw<KVT>::zero();
+			vr[i] = ok ? KvRaw<KVT>::load(vbase + (size_t)t * hd) : KvRaw<KVT>::zero();
+		}
+	};
+	auto update = [&](int tw, const raw_t (&kr)[P], const raw_t (&vr)[P]) {
 		float kf[P][8], vf[P][8];
 		bool ok[P];
 #pragma unroll
 		for (int i = 0; i < P; ++i) {
-			int t = tb + i * stride;
-			ok[i] = t < t1;
-			if (ok[i] && dact) {
-				kv_load8(kbase + (size_t)t * hd, kf[i]);
-				kv_load8(vbase + (size_t)t * hd, vf[i]);
-			} else {
-#pragma unroll
-				for (int d = 0; d < 8; ++d) kf[i][d] = 0.f, vf[i][d] = 0.f;
-			}
+			ok[i] = tw + grp + i * stride < t1;
+			KvRaw<KVT>::unpack(kr[i], kf[i]);
+			KvRaw<KVT>::unpack(vr[i], vf[i]);
 		}
 #pragma unroll
-		for (int h = 0; h < KVMUL; ++h) {
-			float s[P], smax = m[h];
+		for (int h = 0; h < HH; ++h) {
+			float sc[P], smax = m[h];
 #pragma unroll
 			for (int i = 0; i < P; ++i) {
 				float d = 0.f;
 #pragma unroll
 				for (int e = 0; e < 8; ++e) d = fmaf(qr[h][e], kf[i][e], d);
 				for (int o = 1; o < lpp; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-				s[i] = ok[i] ? d * a.inv_sqrt_hd : -FLT_MAX;
-				smax = fmaxf(smax, s[i]);
+				sc[i] = ok[i] ? d * a.inv_sqrt_hd : -FLT_MAX;
+				smax = fmaxf(smax, sc[i]);
 			}
 			float corr = expf(m[h] - smax);
 			m[h] = smax;
 			float pw[P], ps = 0.f;
 #pragma unroll
 			for (int i = 0; i < P; ++i) {
-				pw[i] = ok[i] ? expf(s[i] - smax) : 0.f;
+				pw[i] = ok[i] ? expf(sc[i] - smax) : 0.f;
 				ps += pw[i];
 			}
 			l[h] = fmaf(l[h], corr, ps);
@@ -317,12 +405,35 @@ __global__ void __launch_bounds__(128) k_attn(const AttnArgs a) {
 				acc[h][e] = v;
 			}
 		}
+	};
+
+	// software pipeline over steps of stride * P positions (warp-uniform trip count: the shuffles above are full-warp)
+	if (PIPE) {
+		raw_t ka[P], va[P], kb[P], vb[P];
+		const int step = stride * P;
+		int tw = t0 + warp * G;
+		if (tw < t1) fetch(tw, ka, va);
+		while (tw < t1) {
+			if (tw + step < t1) fetch(tw + step, kb, vb);
+			update(tw, ka, va);
+			tw += step;
+			if (tw >= t1) break;
+			if (tw + step < t1) fetch(tw + step, ka, va);
+			update(tw, kb, vb);
+			tw += step;
+		}
+	} else {
+		raw_t ka[P], va[P];
+		for (int tw = t0 + warp * G; tw < t1; tw += stride * P) {
+			fetch(tw, ka, va);
+			update(tw, ka, va);
+		}
 	}
 
 	// merge the position groups of a warp
 	for (int o = lpp; o < 32; o <<= 1) {
 #pragma unroll
-		for (int h = 0; h < KVMUL; ++h) {
+		for (int h = 0; h < HH; ++h) {
 			float mo = __shfl_xor_sync(0xffffffffu, m[h], o), lo = __shfl_xor_sync(0xffffffffu, l[h], o);
 			float mn = fmaxf(m[h], mo);
 			float ca = expf(m[h] - mn), cb = expf(mo - mn);
@@ -338,61 +449,94 @@ __global__ void __launch_bounds__(128) k_attn(const AttnArgs a) {
 
 	// merge warps through shared memory: rec[warp][h][hd+2]
 	const int rec = hd + 2;
+	__syncthreads(); // scratch may still be in use by a previous item
 	if (grp == 0) {
 #pragma unroll
-		for (int h = 0; h < KVMUL; ++h) {
-			float* r = smem + ((size_t)warp * KVMUL + h) * rec;
-			if (dact) {
+		for (int h = 0; h < HH; ++h) {
+			if (h < nh) { // the warp sets write disjoint heads
+				float* r = scratch + ((size_t)warp * HG + h0 + h) * rec;
+				if (dact) {
 #pragma unroll
-				for (int e = 0; e < 8; ++e) r[li * 8 + e] = acc[h][e];
+					for (int e = 0; e < 8; ++e) r[li * 8 + e] = acc[h][e];
+				}
+				if (li == 0) r[hd] = m[h], r[hd + 1] = l[h];
 			}
-			if (li == 0) r[hd] = m[h], r[hd + 1] = l[h];
 		}
 	}
 	__syncthreads();
-	float* part = a.partial + ((size_t)unit * a.nsplit + split) * KVMUL * rec;
-	for (int idx = threadIdx.x; idx < KVMUL * rec; idx += blockDim.x) {
+	float* part = a.partial + ((size_t)unit * a.nsplit + split) * HG * rec;
+	for (int idx = threadIdx.x; idx < HG * rec; idx += blockDim.x) {
 		int h = idx / rec, e = idx % rec;
 		float mn = -FLT_MAX;
-		for (int w = 0; w < nwarps; ++w) mn = fmaxf(mn, smem[((size_t)w * KVMUL + h) * rec + hd]);
+		for (int w = 0; w < nwarps; ++w) mn = fmaxf(mn, scratch[((size_t)w * HG + h) * rec + hd]);
 		float v;
 		if (e == hd) {
 			v = mn;
 		} else {
 			v = 0.f;
 			for (int w = 0; w < nwarps; ++w) {
-				const float* r = smem + ((size_t)w * KVMUL + h) * rec;
+				const float* r = scratch + ((size_t)w * HG + h) * rec;
 				v += r[e] * expf(r[hd] - mn); // e == hd+1 merges the sums the same way
 			}
 		}
-		part[idx] = v;
+		__stcg(part + idx, v);
 	}
 
-	// the last slice of this kv head to finish folds all slices and writes the normalised output
+	// the last slice of this unit to finish folds all slices and writes the normalised output
 	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned old = atomicAdd(a.counter + unit, 1u);
-		is_last = (old == (unsigned)a.nsplit - 1);
+		*flag = (old == (unsigned)a.nsplit - 1);
 	}
 	__syncthreads();
-	if (!is_last) return;
+	if (!*flag) return;
 	__threadfence();
-	const float* pk = a.partial + (size_t)unit * a.nsplit * KVMUL * rec;
-	for (int idx = threadIdx.x; idx < KVMUL * hd; idx += blockDim.x) {
-		int h = idx / hd, e = idx % hd;
-		float mn = -FLT_MAX;
-		for (int s = 0; s < a.nsplit; ++s) mn = fmaxf(mn, __ldcg(pk + ((size_t)s * KVMUL + h) * rec + hd));
-		float num = 0.f, den = 0.f;
-		for (int s = 0; s < a.nsplit; ++s) {
-			const float* r = pk + ((size_t)s * KVMUL + h) * rec;
-			float c = expf(__ldcg(r + hd) - mn);
-			num = fmaf(__ldcg(r + e), c, num);
-			den = fmaf(__ldcg(r + hd + 1), c, den);
+	const int ns = a.nsplit;
+	const float* pk = a.partial + (size_t)unit * ns * HG * rec;
+	float* coef = scratch;                  // [ns][HG]: l_s, then exp(m_s - M)
+	float* msv = scratch + (size_t)ns * HG; // [ns][HG]: m_s; msv[ns*HG + h]: 1 / L_h
+	for (int i = threadIdx.x; i < ns * HG; i += blockDim.x) {
+		const float* r = pk + (size_t)i * rec; // i = s * HG + h
+		coef[i] = __ldcg(r + hd + 1);
+		msv[i] = __ldcg(r + hd);
+	}
+	__syncthreads();
+	if ((int)threadIdx.x < HG) {
+		const int h = threadIdx.x;
+		float M = -FLT_MAX;
+		for (int s_ = 0; s_ < ns; ++s_) M = fmaxf(M, msv[s_ * HG + h]);
+		float L = 0.f;
+		for (int s_ = 0; s_ < ns; ++s_) {
+			float c = expf(msv[s_ * HG + h] - M);
+			L = fmaf(coef[s_ * HG + h], c, L);
+			coef[s_ * HG + h] = c;
 		}
-		a.out[(size_t)(hbase + h) * hd + e] = num / den;
+		msv[h] = 1.0f / L; // msv[0..HG) is dead by now (each thread only read its own column... see sync below)
+	}
+	__syncthreads();
+	for (int idx = threadIdx.x; idx < HG * hd; idx += blockDim.x) {
+		int h = idx / hd, e = idx % hd;
+		float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+		int s_ = 0;
+		for (; s_ + 4 <= ns; s_ += 4) {
+			float p0 = __ldcg(pk + ((size_t)(s_ + 0) * HG + h) * rec + e), p1 = __ldcg(pk + ((size_t)(s_ + 1) * HG + h) * rec + e);
+			float p2 = __ldcg(pk + ((size_t)(s_ + 2) * HG + h) * rec + e), p3 = __ldcg(pk + ((size_t)(s_ + 3) * HG + h) * rec + e);
+			n0 = fmaf(p0, coef[(s_ + 0) * HG + h], n0), n1 = fmaf(p1, coef[(s_ + 1) * HG + h], n1);
+			n2 = fmaf(p2, coef[(s_ + 2) * HG + h], n2), n3 = fmaf(p3, coef[(s_ + 3) * HG + h], n3);
+		}
+		for (; s_ < ns; ++s_) n0 = fmaf(__ldcg(pk + ((size_t)s_ * HG + h) * rec + e), coef[s_ * HG + h], n0);
+		__stcg(a.out + (size_t)(hbase + h) * hd + e, ((n0 + n1) + (n2 + n3)) * msv[h]);
 	}
 	if (threadIdx.x == 0) a.counter[unit] = 0;
+}
+
+#define ATTN_THREADS 256
+template <typename KVT, int HG>
+__global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnArgs a) {
+	extern __shared__ __align__(16) float smem[];
+	__shared__ int flag;
+	attn_item<KVT, HG, (HG > 4 ? 2 : 4), true>(a, HG, 1, blockIdx.x / a.nsplit, blockIdx.x % a.nsplit, a.tp->kv_len, smem, &flag);
 }
 
 // ------------------------------------------------------------------------------------------------

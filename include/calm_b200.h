@@ -75,13 +75,13 @@ void calm_b200_free(void* device_ptr);
  * never frees, run.c:636) so another model can be prepared in this process. */
 void calm_b200_release(struct Transformer* transformer);
 
-/* Which engine forward_cuda() uses: 0 = one kernel per stage (CUDA graph),
- * 1 = persistent fused kernel.  Default from env CALM_B200_ENGINE, else 1.
- * Must be called before prepare_cuda(). */
+/* Which engine forward_cuda() uses: 0 = one kernel per stage (CUDA graph), 1 = persistent kernel fed by a
+ * TMA ring (fused.cuh), 2 = persistent kernel with streaming loads and cross-barrier prefetch (persist.cuh).
+ * Default from env CALM_B200_ENGINE, else 2.  Must be called before prepare_cuda(). */
 void calm_b200_set_engine(int engine);
 
-/* 1 when the persistent fused kernel serves the prepared model, 0 when the staged engine does (MoE,
- * fp8 KV cache, shapes whose rows do not fit the ring, or engine 0 requested). */
+/* The engine that serves the prepared model: 1 or 2 (one persistent kernel per token), or 0 when the staged
+ * engine does (MoE, fp8 KV cache, unsupported shapes, or engine 0 requested). */
 int calm_b200_engine_in_use(void);
 
 /* forward + device-side greedy sample.  Returns argmax(logits) with the

@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 from make_golden import GOLDEN_SPECS, model_digest  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-ENGINES = [1, 0]  # 1 = persistent fused kernel (default), 0 = one kernel per stage
+ENGINES = [2, 0]  # 2 = persistent kernel (default), 0 = one kernel per stage; engine 1 (TMA ring) is covered by test_engines_agree
 
 
 def run_device(spec, seed, tokens, pos0=0, seq_len=None, engine=0, kvbits=16):
@@ -128,15 +128,16 @@ def test_device_argmax_and_greedy_loop(oracle_pkg, engine):
 
 
 def test_engines_agree():
-    """The two CUDA engines compute the same function with different summation trees: logits agree to a
+    """The three CUDA engines compute the same function with different summation trees: logits agree to a
     few fp32 ulps of the accumulations, greedy tokens are identical."""
     for name in ("tiny-llama", "tiny-qwen", "tiny-gf4"):
         spec = mg.SPECS[name]
         toks = mg.teacher_tokens(spec.vocab_size, 24)
         a = run_device(spec, 9, toks, engine=0)
-        b = run_device(spec, 9, toks, engine=1)
-        assert np.abs(a - b).max() <= 1e-3 * a.std(), name
-        assert (a.argmax(1) == b.argmax(1)).all()
+        for eng in (1, 2):
+            b = run_device(spec, 9, toks, engine=eng)
+            assert np.abs(a - b).max() <= 1e-3 * a.std(), (name, eng)
+            assert (a.argmax(1) == b.argmax(1)).all()
 
 
 @pytest.mark.parametrize("dbits,n,d", [(8, 4096, 512), (16, 896, 130), (4, 4096, 96), (8, 14336, 64), (16, 4096, 33), (4, 1792, 40), (8, 32, 8)])

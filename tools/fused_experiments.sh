@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 python -c "from calm_b200 import lib; L=lib.load(); print('grid barrier: %.2f us' % L.calm_b200_barrier_bench(2000))"
 for dbg in ${1:-0 1 2}; do
   for pos in 4000; do
-    CALM_B200_FUSED_DBG=$dbg timeout 200 python bench.py --steps 48 --warmup 6 --engine 1 --no-cpu-baseline --pos0 $pos > gpurun_out/exp_d${dbg}_p${pos}.json 2>gpurun_out/exp.err
+    CALM_B200_FUSED_DBG=$dbg timeout 200 python bench.py --steps 48 --warmup 6 --engine ${ENGINE:-2} --no-cpu-baseline --pos0 $pos > gpurun_out/exp_d${dbg}_p${pos}.json 2>gpurun_out/exp.err
     python - <<PY
 import json
 d=json.load(open("gpurun_out/exp_d${dbg}_p${pos}.json"))
