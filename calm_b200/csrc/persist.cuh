@@ -125,7 +125,18 @@ __device__ __noinline__ void persist_attention(const PersistArgs& a, const void*
 	aa.q = a.q, aa.kc = kc_l, aa.vc = vc_l, aa.partial = a.attn_partial, aa.counter = a.attn_counter, aa.out = a.att, aa.tp = a.tp;
 	aa.head_dim = a.head_dim, aa.seq_len = a.seq_len, aa.nsplit = a.attn_nsplit, aa.lpp = a.attn_lpp;
 	aa.kv_mul = a.kv_mul, aa.qgroups = a.attn_qgroups, aa.inv_sqrt_hd = a.inv_sqrt_hd;
-	attn_item<KVT, HH, 4, false>(aa, a.attn_hg, 2, blockIdx.x / a.attn_nsplit, blockIdx.x % a.attn_nsplit, kv_len, scratch, flag);
+	const int unit = blockIdx.x / a.attn_nsplit, split = blockIdx.x % a.attn_nsplit;
+	if constexpr (HH == 1 || HH == 2 || HH == 4) { // transposing score path (head_dim 128 / 64, even head groups)
+		if (a.attn_lpp == 16 && (a.attn_hg % 2 == 0 || a.attn_hg == 1)) {
+			attn_item<KVT, HH, (HH == 4 ? 2 : 4), false, 16>(aa, a.attn_hg, 2, unit, split, kv_len, scratch, flag);
+			return;
+		}
+		if (a.attn_lpp == 8 && (a.attn_hg % 2 == 0 || a.attn_hg == 1)) {
+			attn_item<KVT, HH, (HH == 4 ? 2 : 4), false, 8>(aa, a.attn_hg, 2, unit, split, kv_len, scratch, flag);
+			return;
+		}
+	}
+	attn_item<KVT, HH, 4, false>(aa, a.attn_hg, 2, unit, split, kv_len, scratch, flag);
 }
 
 // ---------------------------------------------------------------- the kernel

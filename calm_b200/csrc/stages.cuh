@@ -325,8 +325,12 @@ struct KvRaw<uint8_t> {
 // every set walks all positions of the slice and serves HH of the unit's HG query heads (set s: heads
 // s*HH ...), which halves the per-thread state when a CTA has many warps but few registers.
 // P positions per lane group are in flight; PIPE requests the next P before consuming the current ones.
+// LPPC > 0 (compile-time lanes per position, with HH * P == LPPC) selects the transposing score path: the
+// HH * P partial dot products of a step are reduced across the lane group so that every lane ends up with
+// ONE complete score (15 shuffles instead of 64 for 16 lanes), evaluates its two exponentials once, and
+// the probabilities are broadcast back for the value accumulation.
 // scratch: shared, >= max((nwarps / hsets) * HG * (hd + 2), 2 * nsplit * HG) floats.  flag: shared int.
-template <typename KVT, int HH, int P, bool PIPE>
+template <typename KVT, int HH, int P, bool PIPE, int LPPC = 0>
 __device__ __forceinline__ void attn_item(const AttnArgs& a, int HG, int hsets, int unit, int split, int kv_len, float* scratch, int* flag) {
 	typedef typename KvRaw<KVT>::type raw_t;
 	const int kvh = unit / a.qgroups;
@@ -367,6 +371,7 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int HG, int hsets, 
 			vr[i] = ok ? KvRaw<KVT>::load(vbase + (size_t)t * hd) : KvRaw<KVT>::zero();
 		}
 	};
+	float mh = -FLT_MAX, lh = 0.f; // transposing path: running max / sum of THIS lane's head (li / P)
 	auto update = [&](int tw, const raw_t (&kr)[P], const raw_t (&vr)[P]) {
 		float kf[P][8], vf[P][8];
 		bool ok[P];
@@ -375,6 +380,68 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int HG, int hsets, 
 			ok[i] = tw + grp + i * stride < t1;
 			KvRaw<KVT>::unpack(kr[i], kf[i]);
 			KvRaw<KVT>::unpack(vr[i], vf[i]);
+		}
+		if constexpr (LPPC > 0) {
+			constexpr int NC = HH * P; // scores per step; lane li ends up owning combo li % NC
+			static_assert(LPPC == 0 || (NC <= LPPC && LPPC % NC == 0), "combos must divide the lane group");
+			float part[NC]; // combo c = h * P + i
+#pragma unroll
+			for (int h = 0; h < HH; ++h)
+#pragma unroll
+				for (int i = 0; i < P; ++i) {
+					float d = 0.f;
+#pragma unroll
+					for (int e = 0; e < 8; ++e) d = fmaf(qr[h][e], kf[i][e], d);
+					part[h * P + i] = d;
+				}
+			// more lanes than combos: plain butterfly first
+#pragma unroll
+			for (int s_ = LPPC / 2; s_ >= NC; s_ >>= 1) {
+#pragma unroll
+				for (int k = 0; k < NC; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], s_);
+			}
+			// transposing reduction: after the step with stride s a lane keeps the half of its values selected by bit s
+#pragma unroll
+			for (int s_ = NC / 2; s_ >= 1; s_ >>= 1) {
+				const bool up = li & s_;
+#pragma unroll
+				for (int k = 0; k < s_; ++k) {
+					float send = up ? part[k] : part[k + s_];
+					float recv = __shfl_xor_sync(0xffffffffu, send, s_);
+					part[k] = (up ? part[k + s_] : part[k]) + recv;
+				}
+			}
+			// lane li now owns combo c = li % NC: head c / P, position c % P
+			const bool valid = tw + grp + (li % P) * stride < t1;
+			const float sc = valid ? part[0] * a.inv_sqrt_hd : -FLT_MAX;
+			float gmax = sc;
+#pragma unroll
+			for (int o = 1; o < P; o <<= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+			const float mnew = fmaxf(mh, gmax);
+			const float corr = __expf(mh - mnew);
+			const float pr = valid ? __expf(sc - mnew) : 0.f;
+			float ps = pr;
+#pragma unroll
+			for (int o = 1; o < P; o <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+			lh = fmaf(lh, corr, ps);
+			mh = mnew;
+			const int gbase = grp * LPPC;
+#pragma unroll
+			for (int h = 0; h < HH; ++h) {
+				const float ch = __shfl_sync(0xffffffffu, corr, gbase + h * P);
+				float pw[P];
+#pragma unroll
+				for (int i = 0; i < P; ++i) pw[i] = __shfl_sync(0xffffffffu, pr, gbase + h * P + i);
+#pragma unroll
+				for (int e = 0; e < 8; ++e) {
+					float v = acc[h][e] * ch;
+#pragma unroll
+					for (int i = 0; i < P; ++i) v = fmaf(pw[i], vf[i][e], v);
+					acc[h][e] = v;
+				}
+			}
+			(void)ok;
+			return;
 		}
 #pragma unroll
 		for (int h = 0; h < HH; ++h) {
@@ -427,6 +494,14 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int HG, int hsets, 
 		for (int tw = t0 + warp * G; tw < t1; tw += stride * P) {
 			fetch(tw, ka, va);
 			update(tw, ka, va);
+		}
+	}
+
+	if constexpr (LPPC > 0) { // running max / sum live in the lanes that own the head: hand them to every lane of the group
+#pragma unroll
+		for (int h = 0; h < HH; ++h) {
+			m[h] = __shfl_sync(0xffffffffu, mh, grp * LPPC + h * P);
+			l[h] = __shfl_sync(0xffffffffu, lh, grp * LPPC + h * P);
 		}
 	}
 
@@ -536,7 +611,19 @@ template <typename KVT, int HG>
 __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnArgs a) {
 	extern __shared__ __align__(16) float smem[];
 	__shared__ int flag;
-	attn_item<KVT, HG, (HG > 4 ? 2 : 4), true>(a, HG, 1, blockIdx.x / a.nsplit, blockIdx.x % a.nsplit, a.tp->kv_len, smem, &flag);
+	const int unit = blockIdx.x / a.nsplit, split = blockIdx.x % a.nsplit, kv_len = a.tp->kv_len;
+	// transposing score path when the lanes of a position are a small multiple of the heads (head_dim 128 / 64)
+	if constexpr (HG == 2 || HG == 4 || HG == 8) {
+		if (a.lpp == 16 && HG >= 4) {
+			attn_item<KVT, HG, 16 / HG, true, 16>(a, HG, 1, unit, split, kv_len, smem, &flag);
+			return;
+		}
+		if (a.lpp == 8) {
+			attn_item<KVT, HG, 8 / HG, true, 8>(a, HG, 1, unit, split, kv_len, smem, &flag);
+			return;
+		}
+	}
+	attn_item<KVT, HG, (HG > 4 ? 2 : 4), true>(a, HG, 1, unit, split, kv_len, smem, &flag);
 }
 
 // ------------------------------------------------------------------------------------------------
