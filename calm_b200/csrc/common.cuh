@@ -41,6 +41,15 @@ struct TokenParams {
 	int pad;
 };
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every staged kernel starts with pdl_enter(): it lets the NEXT kernel of the stream be launched right away
+// (its CTAs park in their own pdl_enter until this grid has completed and flushed), which takes the launch
+// latency off the critical path between the ~160 kernels of a token.  No-ops when launched without the attribute.
+__device__ __forceinline__ void pdl_enter() {
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- warp / block reductions
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -179,30 +188,41 @@ __device__ __forceinline__ float dot_vec<8>(const uint4& w, const float4 (&xv)[4
 	return acc;
 }
 
-// gf4 word: bits 0..7 e5m2 scale s, then eight 3-bit codes; w_k = (q_k - 4) * s / -4
-// (reference infer.c:37-40).  sum_k w_k x_k = (-s/4) * sum_k (q_k - 4) x_k; the integer
-// code is turned into a float with the 2^23 magic (0x4B000000 | q  ==  8388608 + q, exact).
-__device__ __forceinline__ float dot_gf4_word(uint32_t w, const float4& x0, const float4& x1, float acc) {
-	float sf = e5m2_to_float((uint8_t)(w & 0xff)) * -0.25f;
-	const float magic = 8388612.f; // 2^23 + 4
-	float g = 0.f;
-	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 8) & 7)) - magic, x0.x, g);
-	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 11) & 7)) - magic, x0.y, g);
-	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 14) & 7)) - magic, x0.z, g);
-	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 17) & 7)) - magic, x0.w, g);
-	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 20) & 7)) - magic, x1.x, g);
-	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 23) & 7)) - magic, x1.y, g);
-	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 26) & 7)) - magic, x1.z, g);
-	g = fmaf(__uint_as_float(0x4B000000u | ((w >> 29) & 7)) - magic, x1.w, g);
-	return fmaf(sf, g, acc);
+// gf4 word: bits 0..7 e5m2 scale s, then eight 3-bit codes; w_k = (q_k - 4) * s / -4 (reference infer.c:37-40).
+// A code is dropped into the top mantissa bits of 1.0f (0x3F800000 | q << 20 == 1 + q/8, exact): one shift and
+// one logic op per weight, no int->float conversion.  With S = sum_k (1 + q_k/8) x_k and X = sum_k x_k:
+//   sum_k w_k x_k = (-s/4) (sum_k q_k x_k - 4 X) = (-s/4) (8 S - 12 X) = s (3 X - 2 S).
+// `xsum` = X of this group of 8 activations (computed once per vector and shared by all rows).
+__device__ __forceinline__ float gf4_code(uint32_t w, int k) { // 1 + q_k / 8
+	const int sh = 8 + 3 * k - 20; // field k sits at bits 8+3k..10+3k; move it to bits 20..22
+	uint32_t f = sh >= 0 ? (w >> sh) : (w << -sh), r;
+	asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(f), "r"(0x00700000u), "r"(0x3F800000u)); // (f & mask) | one: a single LOP3
+	return __uint_as_float(r);
+}
+__device__ __forceinline__ float dot_gf4_word(uint32_t w, const float4& x0, const float4& x1, float xsum, float acc) {
+	float S = gf4_code(w, 0) * x0.x;
+	S = fmaf(gf4_code(w, 1), x0.y, S);
+	S = fmaf(gf4_code(w, 2), x0.z, S);
+	S = fmaf(gf4_code(w, 3), x0.w, S);
+	S = fmaf(gf4_code(w, 4), x1.x, S);
+	S = fmaf(gf4_code(w, 5), x1.y, S);
+	S = fmaf(gf4_code(w, 6), x1.z, S);
+	S = fmaf(gf4_code(w, 7), x1.w, S);
+	const float sc = e5m2_to_float((uint8_t)(w & 0xff));
+	return fmaf(sc, fmaf(3.f, xsum, -2.f * S), acc);
 }
 
 template <>
 __device__ __forceinline__ float dot_vec<4>(const uint4& w, const float4 (&xv)[8], float acc) {
-	acc = dot_gf4_word(w.x, xv[0], xv[1], acc);
-	acc = dot_gf4_word(w.y, xv[2], xv[3], acc);
-	acc = dot_gf4_word(w.z, xv[4], xv[5], acc);
-	acc = dot_gf4_word(w.w, xv[6], xv[7], acc);
+	// group sums of the activations (the compiler keeps them across the rows that share xv)
+	const float s0 = ((xv[0].x + xv[0].y) + (xv[0].z + xv[0].w)) + ((xv[1].x + xv[1].y) + (xv[1].z + xv[1].w));
+	const float s1 = ((xv[2].x + xv[2].y) + (xv[2].z + xv[2].w)) + ((xv[3].x + xv[3].y) + (xv[3].z + xv[3].w));
+	const float s2 = ((xv[4].x + xv[4].y) + (xv[4].z + xv[4].w)) + ((xv[5].x + xv[5].y) + (xv[5].z + xv[5].w));
+	const float s3 = ((xv[6].x + xv[6].y) + (xv[6].z + xv[6].w)) + ((xv[7].x + xv[7].y) + (xv[7].z + xv[7].w));
+	acc = dot_gf4_word(w.x, xv[0], xv[1], s0, acc);
+	acc = dot_gf4_word(w.y, xv[2], xv[3], s1, acc);
+	acc = dot_gf4_word(w.z, xv[4], xv[5], s2, acc);
+	acc = dot_gf4_word(w.w, xv[6], xv[7], s3, acc);
 	return acc;
 }
 

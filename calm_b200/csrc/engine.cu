@@ -84,6 +84,7 @@ struct Engine {
 	cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
 	int graph_launches[4] = {0, 0, 0, 0};
 	bool use_graph = true;
+	bool use_pdl = true;
 
 	// profiling (perf_cuda)
 	bool perf = false;
@@ -135,10 +136,29 @@ int max_ctas(F kernel, int block, size_t smem) {
 
 int imin(int a, int b) { return a < b ? a : b; }
 int cdiv(int a, int b) { return (a + b - 1) / b; }
+// grid for `units` equal CTA-sized work items when at most `cap` CTAs are resident: every CTA gets the same
+// number of rounds (a 3.03-rounds grid costs 4 rounds on some SMs and idles the rest)
+int balanced_grid(int units, int cap) {
+	if (units <= cap) return units < 1 ? 1 : units;
+	return cdiv(units, cdiv(units, cap));
+}
 
 template <int DBITS>
 size_t xs_bytes(int n) {
 	return (size_t)(32 + xs_floats<DBITS>(n)) * sizeof(float);
+}
+
+// Launch on the library's stream with programmatic stream serialization (PDL), so that consecutive kernels
+// of a token overlap their launch latency (the kernels order themselves with griddepcontrol.wait).
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, Args... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = g.stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
+	cfg.attrs = at, cfg.numAttrs = 1;
+	CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, args...));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -174,7 +194,7 @@ void launch_attn(const AttnArgs& a, int nunits, int* nl) {
 	size_t smem = (size_t)(ATTN_THREADS / 32) * HG * (a.head_dim + 2) * sizeof(float);
 	size_t smem2 = (size_t)(2 * a.nsplit + 1) * HG * sizeof(float);
 	if (smem2 > smem) smem = smem2;
-	k_attn<KVT, HG><<<nunits * a.nsplit, ATTN_THREADS, smem, g.stream>>>(a);
+	launch_pdl(k_attn<KVT, HG>, nunits * a.nsplit, ATTN_THREADS, smem, a);
 	++*nl;
 }
 
@@ -208,7 +228,7 @@ int run_token(int mode) {
 		a.embed_blocks = cdiv(dim, 256);
 		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq;
 		a.n_layers = c.n_layers, a.n_kv_heads = c.n_kv_heads, a.head_dim = hd, a.seq_len = c.seq_len;
-		k_embed<DBITS, KVT><<<a.embed_blocks + 8, 256, 0, g.stream>>>(a);
+		launch_pdl(k_embed<DBITS, KVT>, a.embed_blocks + 8, 256, 0, a);
 		++nl;
 	}
 
@@ -223,7 +243,7 @@ int run_token(int mode) {
 			a.rope_freq = g.rope_freq, a.xb_out = c.norm_par ? g.xb : nullptr, a.tp = g.tp;
 			a.dim = dim, a.q_dim = g.q_dim, a.kv_dim = g.kv_dim, a.head_dim = hd, a.seq_len = c.seq_len;
 			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln;
-			k_qkv<DBITS, KVT><<<g.grid_qkv, 256, g.smem_dim, g.stream>>>(a);
+			launch_pdl(k_qkv<DBITS, KVT>, g.grid_qkv, 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -240,7 +260,7 @@ int run_token(int mode) {
 			StageTimer t(ST_WO, (double)dim * g.q_dim * wb / 8);
 			MatResArgs a;
 			a.xin = g.att, a.w = w.wo[l], a.y = g.x, a.sel = nullptr, a.n = g.q_dim, a.d = dim, a.nact = 1, a.accumulate = 1;
-			k_matres<DBITS><<<g.grid_wo, 256, g.smem_qdim, g.stream>>>(a);
+			launch_pdl(k_matres<DBITS>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
 		}
 		{
@@ -250,7 +270,7 @@ int run_token(int mode) {
 			a.gate = c.n_experts ? w.moegate[l] : nullptr, a.w1 = w.w1[l], a.w3 = w.w3[l], a.hb = g.hb, a.sel = g.moe_sel;
 			a.dim = dim, a.hidden = hidden, a.n_experts = c.n_experts, a.nact = g.nact;
 			a.eps = c.norm_eps, a.ln = c.norm_ln, a.gelu = c.act_gelu;
-			k_ffn_up<DBITS><<<g.grid_up, 256, g.smem_dim, g.stream>>>(a);
+			launch_pdl(k_ffn_up<DBITS>, g.grid_up, 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -258,7 +278,7 @@ int run_token(int mode) {
 			MatResArgs a;
 			a.xin = g.hb, a.w = w.w2[l], a.y = g.x, a.sel = c.n_experts ? g.moe_sel : nullptr;
 			a.n = hidden, a.d = dim, a.nact = g.nact, a.accumulate = 1;
-			k_matres<DBITS><<<g.grid_down, 256, g.smem_hidden, g.stream>>>(a);
+			launch_pdl(k_matres<DBITS>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
 		}
 	}
@@ -273,10 +293,10 @@ int run_token(int mode) {
 		a.cand_val = (mode >= 2) ? g.cand_val : nullptr, a.cand_idx = g.cand_idx;
 		a.dim = dim, a.vocab = c.vocab_size, a.eps = c.norm_eps, a.ln = c.norm_ln;
 		int grid = g.grid_out;
-		k_output<DBITS><<<grid, 256, g.smem_dim, g.stream>>>(a);
+		launch_pdl(k_output<DBITS>, grid, 256, g.smem_dim, a);
 		++nl;
 		if (mode >= 2) {
-			k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, grid, g.tp, g.out_tokens, g.last_token, mode == 2, c.vocab_size);
+			launch_pdl(k_advance, 1, 256, 0, (const float*)g.cand_val, (const int*)g.cand_idx, grid, g.tp, g.out_tokens, g.last_token, (int)(mode == 2), c.vocab_size);
 			++nl;
 		}
 	}
@@ -292,12 +312,13 @@ void make_plan() {
 	g.smem_hidden = xs_bytes<DBITS>(c.hidden_dim);
 	size_t smem_res = g.smem_qdim > g.smem_hidden ? g.smem_qdim : g.smem_hidden;
 	if (smem_res > 227 * 1024 || g.smem_dim > 227 * 1024) CALM_FATAL("activation vector does not fit in shared memory (dim %d, hidden %d)", c.dim, c.hidden_dim);
-	g.grid_qkv = imin(max_ctas(k_qkv<DBITS, KVT>, 256, g.smem_dim), cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8));
+	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT>, 256, g.smem_dim));
 	max_ctas(k_matres<DBITS>, 256, smem_res); // opt in to the larger of the two sizes
-	g.grid_wo = imin(max_ctas(k_matres<DBITS>, 256, g.smem_qdim), cdiv(c.dim / 2, 8));
-	g.grid_down = imin(max_ctas(k_matres<DBITS>, 256, g.smem_hidden), cdiv(c.dim / 2, 8));
+	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_qdim));
+	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_hidden));
+	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
 	g.grid_up = imin(max_ctas(k_ffn_up<DBITS>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
-	g.grid_out = imin(max_ctas(k_output<DBITS>, 256, g.smem_dim), cdiv(c.vocab_size, 32));
+	g.grid_out = balanced_grid(cdiv(c.vocab_size, 32), max_ctas(k_output<DBITS>, 256, g.smem_dim));
 	g.ncand = g.grid_out;
 }
 
@@ -557,6 +578,8 @@ int run_token_persist(int mode) {
 	pa.mode = mode;
 	pa.attn_nsplit = g.persist_nsplit, pa.attn_hg = g.attn_hg, pa.attn_qgroups = g.attn_qgroups, pa.attn_lpp = g.attn_lpp;
 	pa.inv_sqrt_hd = 1.0f / sqrtf((float)c.head_dim);
+	pa.pf_pairs = getenv("CALM_B200_PF_PAIRS") ? atoi(getenv("CALM_B200_PF_PAIRS")) : 1;
+	pa.pf_bytes = getenv("CALM_B200_PF_BYTES") ? atoi(getenv("CALM_B200_PF_BYTES")) : 6144;
 	persist_launch(pa, false);
 	int nl = 1;
 	if (mode >= 2) {
@@ -694,6 +717,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.nact = c.n_experts ? c.n_experts_ac : 1;
 	g.q_dim = q_dim, g.kv_dim = kv_dim, g.kv_mul = c.n_heads / c.n_kv_heads;
 	g.use_graph = !(getenv("CALM_B200_GRAPH") && atoi(getenv("CALM_B200_GRAPH")) == 0);
+	g.use_pdl = !(getenv("CALM_B200_PDL") && atoi(getenv("CALM_B200_PDL")) == 0);
 	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
 	if (g.debug) g.use_graph = false, g.debug_stages = true;
 	g.perf = (getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF"))) || getenv("CUDA_INJECTION64_PATH");
@@ -757,7 +781,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.tp = (TokenParams*)dev_alloc(sizeof(TokenParams));
 	CUDA_CHECK(cudaMemset(g.tp, 0, sizeof(TokenParams)));
 
-	g.engine = g_engine_kind >= 0 ? g_engine_kind : (getenv("CALM_B200_ENGINE") ? atoi(getenv("CALM_B200_ENGINE")) : 2);
+	g.engine = g_engine_kind >= 0 ? g_engine_kind : (getenv("CALM_B200_ENGINE") ? atoi(getenv("CALM_B200_ENGINE")) : 0);
 	switch (w.dbits) {
 	case 16: make_plan_kv<16>(); break;
 	case 8: make_plan_kv<8>(); break;

@@ -4,11 +4,12 @@
 //   * grid = one CTA per SM, 16 warps; every warp owns a fixed, strided set of row pairs of every matrix;
 //   * weights are read with the same 16-byte streaming loads as the staged kernels (no staging of weights
 //     in shared memory: a warp's share of a row pair goes HBM -> registers -> FMA);
-//   * before a warp enters the grid barrier that ends a stage it asks the L2 for the first row pairs it will
-//     read in the NEXT stage (cp.async.bulk.prefetch.L2: fire-and-forget, no registers; weights and old KV
-//     entries never depend on this token's activations), so HBM keeps streaming -- up to ~200 KB per SM,
-//     ~30 MB chip-wide -- while the barrier and the activation staging of the next stage complete, and the
-//     first demand loads after the barrier hit L2;
+//   * the 126 MB L2 is the run-ahead buffer: before a warp enters the grid barrier that ends a stage it asks
+//     the L2 for ALL the rows it will read in the NEXT stage (cp.async.bulk.prefetch.L2, SASS UBLKPF:
+//     fire-and-forget, no registers; weights and old KV entries never depend on this token's activations),
+//     so HBM streams in program order straight through the barriers and the activation staging, and the
+//     demand loads of the next stage hit L2 (or a line already in flight); demand loads carry an
+//     evict-first policy so that consumed lines make room for the prefetched ones;
 //   * the activation vector of a stage is staged once per CTA in shared memory (permuted layout of
 //     common.cuh, RMSNorm applied on the way), exactly as the staged kernels do;
 //   * attention, epilogues and the arithmetic are those of stages.cuh (reference infer.c:311-472).
@@ -48,6 +49,7 @@ struct PersistArgs {
 	int mode;
 	int attn_nsplit, attn_hg, attn_qgroups, attn_lpp;
 	float inv_sqrt_hd;
+	int pf_pairs, pf_bytes; // L2 run-ahead per warp at a stage end: row pairs, bytes per row
 };
 
 __constant__ PersistLayer c_persist_layers[MAX_LAYERS];
@@ -60,13 +62,21 @@ struct RowBatch { // U vectors per lane of two rows: 2 * U * 512 bytes in flight
 	uint4 w[U][2];
 };
 
+// 16-byte weight load whose L2 line becomes the first candidate for eviction: the line was brought in by a
+// prefetch, is used exactly once, and should make room for the lines being prefetched for later stages
+__device__ __forceinline__ uint4 ldg_stream_ef(const uint4* p, uint64_t pol) {
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+	return r;
+}
+
 template <int DBITS>
-__device__ __forceinline__ void batch_issue(RowBatch<DBITS>& b, const uint4* r0, const uint4* r1, int nvec, int v0) {
+__device__ __forceinline__ void batch_issue(RowBatch<DBITS>& b, const uint4* r0, const uint4* r1, int nvec, int v0, uint64_t pol) {
 #pragma unroll
 	for (int u = 0; u < RowBatch<DBITS>::U; ++u) {
 		int v = v0 + 32 * u;
-		b.w[u][0] = v < nvec ? ldg_stream(r0 + v) : make_uint4(0, 0, 0, 0);
-		b.w[u][1] = v < nvec ? ldg_stream(r1 + v) : make_uint4(0, 0, 0, 0);
+		b.w[u][0] = v < nvec ? ldg_stream_ef(r0 + v, pol) : make_uint4(0, 0, 0, 0);
+		b.w[u][1] = v < nvec ? ldg_stream_ef(r1 + v, pol) : make_uint4(0, 0, 0, 0);
 	}
 }
 
@@ -92,27 +102,24 @@ __device__ __forceinline__ void batch_consume(const RowBatch<DBITS>& b, int nvec
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
 	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-#define PERSIST_PF_BYTES 6144u // per row and warp: two rows -> 12 KB per warp, ~190 KB per SM
-
-// lane 0 of a warp: prefetch the head of the two rows the warp will read first in the next stage
+// one lane: ask the L2 for the head of two rows (pieces of <= 16 KB)
 __device__ __forceinline__ void prefetch_pair(const void* r0, const void* r1, int rowbytes) {
-	uint32_t n = (uint32_t)rowbytes < PERSIST_PF_BYTES ? (uint32_t)rowbytes : PERSIST_PF_BYTES;
-	n &= ~15u;
-	if (n) {
-		l2_prefetch(r0, n);
-		l2_prefetch(r1, n);
+	for (int off = 0; off < rowbytes; off += 16384) {
+		uint32_t n = (uint32_t)min(16384, rowbytes - off);
+		l2_prefetch((const char*)r0 + off, n);
+		l2_prefetch((const char*)r1 + off, n);
 	}
 }
 
 // Two rows against the staged vector.
 template <int DBITS>
-__device__ __forceinline__ void warp_pair(const uint4* r0, const uint4* r1, int nvec, const float4* __restrict__ xs4, float& o0, float& o1) {
+__device__ __forceinline__ void warp_pair(const uint4* r0, const uint4* r1, int nvec, const float4* __restrict__ xs4, uint64_t pol, float& o0, float& o1) {
 	constexpr int U = RowBatch<DBITS>::U;
 	const int lane = threadIdx.x & 31;
 	float a0 = 0.f, a1 = 0.f;
 	for (int v0 = lane; v0 < nvec; v0 += 32 * U) {
 		RowBatch<DBITS> b;
-		batch_issue<DBITS>(b, r0, r1, nvec, v0);
+		batch_issue<DBITS>(b, r0, r1, nvec, v0, pol);
 		batch_consume<DBITS>(b, nvec, v0, xs4, a0, a1);
 	}
 	o0 = warp_sum(a0), o1 = warp_sum(a1);
@@ -203,13 +210,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persist(const __grid_con
 		r1 = r0 + nv_dim;
 	};
 
-	const int rb_dim = nv_dim * 16, rb_q = nv_q * 16, rb_hid = nv_hid * 16; // bytes per row
-	if (lane == 0 && gw < np_qkv) {
-		const uint4 *r0, *r1;
-		int which, k;
-		qkv_rows(c_persist_layers[0], gw, r0, r1, which, k);
-		prefetch_pair(r0, r1, rb_dim);
-	}
+	// bytes of a row / number of row pairs that a warp asks the L2 for ahead of a stage
+	const int rb_dim = min(nv_dim * 16, a.pf_bytes) & ~15, rb_q = min(nv_q * 16, a.pf_bytes) & ~15, rb_hid = min(nv_hid * 16, a.pf_bytes) & ~15;
+	const int pf_stop = gw + a.pf_pairs * NW; // first pair index beyond the run-ahead window
+	const uint64_t pol = l2_policy_evict_first();
+	if (lane == 0)
+		for (int p = gw; p < np_qkv && p < pf_stop; p += NW) {
+			const uint4 *r0, *r1;
+			int which, k;
+			qkv_rows(c_persist_layers[0], p, r0, r1, which, k);
+			prefetch_pair(r0, r1, rb_dim);
+		}
 
 	for (int l = 0; l < a.n_layers; ++l) {
 		const PersistLayer& L = c_persist_layers[l];
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persist(const __grid_con
 			int which, k;
 			qkv_rows(L, p, r0, r1, which, k);
 			float v0, v1;
-			warp_pair<DBITS>(r0, r1, nv_dim, xs4, v0, v1);
+			warp_pair<DBITS>(r0, r1, nv_dim, xs4, pol, v0, v1);
 			if (lane == 0) {
 				int j = 2 * p;
 				if (L.bqkv) v0 += L.bqkv[j], v1 += L.bqkv[j + 1];
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persist(const __grid_con
 		}
 		if (lane == 0) {
 			// next matrix stage: wo; and this CTA's slice of K/V for the attention stage (positions before this token)
-			if (gw < np_o) prefetch_pair(reinterpret_cast<const uint4*>(L.wo) + (size_t)(2 * gw) * nv_q, reinterpret_cast<const uint4*>(L.wo) + (size_t)(2 * gw + 1) * nv_q, rb_q);
+			for (int p = gw; p < np_o && p < pf_stop; p += NW) prefetch_pair(reinterpret_cast<const uint4*>(L.wo) + (size_t)(2 * p) * nv_q, reinterpret_cast<const uint4*>(L.wo) + (size_t)(2 * p + 1) * nv_q, rb_q);
 			const int units = a.n_kv_heads * a.attn_qgroups;
 			if ((int)blockIdx.x < units * a.attn_nsplit) {
 				const int unit = blockIdx.x / a.attn_nsplit, split = blockIdx.x % a.attn_nsplit, kvh = unit / a.attn_qgroups;
@@ -275,15 +286,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persist(const __grid_con
 		for (int p = gw; p < np_o; p += NW) {
 			const uint4* r0 = reinterpret_cast<const uint4*>(L.wo) + (size_t)(2 * p) * nv_q;
 			float v0, v1;
-			warp_pair<DBITS>(r0, r0 + nv_q, nv_q, xs4, v0, v1);
+			warp_pair<DBITS>(r0, r0 + nv_q, nv_q, xs4, pol, v0, v1);
 			if (lane == 0) {
 				float2* dst = reinterpret_cast<float2*>(a.x + 2 * p);
 				float2 cur = __ldcg(dst);
 				__stcg(dst, make_float2(cur.x + v0, cur.y + v1));
 			}
 		}
-		if (lane == 0 && gw < np_up) // next: w1 | w3
-			prefetch_pair(reinterpret_cast<const uint4*>(L.w1) + (size_t)gw * nv_dim, reinterpret_cast<const uint4*>(L.w3) + (size_t)gw * nv_dim, rb_dim);
+		if (lane == 0) // next: w1 | w3
+			for (int p = gw; p < np_up && p < pf_stop; p += NW) prefetch_pair(reinterpret_cast<const uint4*>(L.w1) + (size_t)p * nv_dim, reinterpret_cast<const uint4*>(L.w3) + (size_t)p * nv_dim, rb_dim);
 		barrier(3, 303);
 
 		// ---------------- stage 4: norm -> act(w1 . xn) * (w3 . xn) (infer.c:417-450)
@@ -294,11 +305,11 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persist(const __grid_con
 		if (timer) a.perf[16 + 4] += globaltimer_ns() - t_stage;
 		for (int p = gw; p < np_up; p += NW) {
 			float v1, v3;
-			warp_pair<DBITS>(reinterpret_cast<const uint4*>(L.w1) + (size_t)p * nv_dim, reinterpret_cast<const uint4*>(L.w3) + (size_t)p * nv_dim, nv_dim, xs4, v1, v3);
+			warp_pair<DBITS>(reinterpret_cast<const uint4*>(L.w1) + (size_t)p * nv_dim, reinterpret_cast<const uint4*>(L.w3) + (size_t)p * nv_dim, nv_dim, xs4, pol, v1, v3);
 			if (lane == 0) __stcg(a.hb + p, (a.gelu ? act_gelu(v1) : act_silu(v1)) * v3);
 		}
-		if (lane == 0 && gw < np_o) // next: w2
-			prefetch_pair(reinterpret_cast<const uint4*>(L.w2) + (size_t)(2 * gw) * nv_hid, reinterpret_cast<const uint4*>(L.w2) + (size_t)(2 * gw + 1) * nv_hid, rb_hid);
+		if (lane == 0) // next: w2
+			for (int p = gw; p < np_o && p < pf_stop; p += NW) prefetch_pair(reinterpret_cast<const uint4*>(L.w2) + (size_t)(2 * p) * nv_hid, reinterpret_cast<const uint4*>(L.w2) + (size_t)(2 * p + 1) * nv_hid, rb_hid);
 		barrier(4, 304);
 
 		// ---------------- stage 5: x += w2 . hb (infer.c:452-456)
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persist(const __grid_con
 		for (int p = gw; p < np_o; p += NW) {
 			const uint4* r0 = reinterpret_cast<const uint4*>(L.w2) + (size_t)(2 * p) * nv_hid;
 			float v0, v1;
-			warp_pair<DBITS>(r0, r0 + nv_hid, nv_hid, xs4, v0, v1);
+			warp_pair<DBITS>(r0, r0 + nv_hid, nv_hid, xs4, pol, v0, v1);
 			if (lane == 0) {
 				float2* dst = reinterpret_cast<float2*>(a.x + 2 * p);
 				float2 cur = __ldcg(dst);
@@ -317,15 +328,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persist(const __grid_con
 		// next: q|k|v of the next layer, or the classifier
 		if (lane == 0) {
 			if (l + 1 < a.n_layers) {
-				if (gw < np_qkv) {
+				for (int p = gw; p < np_qkv && p < pf_stop; p += NW) {
 					const uint4 *r0, *r1;
 					int which, k;
-					qkv_rows(c_persist_layers[l + 1], gw, r0, r1, which, k);
+					qkv_rows(c_persist_layers[l + 1], p, r0, r1, which, k);
 					prefetch_pair(r0, r1, rb_dim);
 				}
-			} else if (a.mode != 0 && gw < np_out) {
-				int ra = 2 * gw, rb = min(2 * gw + 1, a.vocab - 1);
-				prefetch_pair(reinterpret_cast<const uint4*>(a.wcls) + (size_t)ra * nv_dim, reinterpret_cast<const uint4*>(a.wcls) + (size_t)rb * nv_dim, rb_dim);
+			} else if (a.mode != 0) { // the classifier is larger than L2: only the first pairs of every warp
+				for (int p = gw; p < np_out && p < pf_stop; p += NW) {
+					int ra = 2 * p, rb = min(2 * p + 1, a.vocab - 1);
+					prefetch_pair(reinterpret_cast<const uint4*>(a.wcls) + (size_t)ra * nv_dim, reinterpret_cast<const uint4*>(a.wcls) + (size_t)rb * nv_dim, rb_dim);
+				}
 			}
 		}
 		barrier(5, 305);
@@ -340,7 +353,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persist(const __grid_con
 	for (int p = gw; p < np_out; p += NW) {
 		int ra = 2 * p, rb = min(2 * p + 1, a.vocab - 1);
 		float v0, v1;
-		warp_pair<DBITS>(reinterpret_cast<const uint4*>(a.wcls) + (size_t)ra * nv_dim, reinterpret_cast<const uint4*>(a.wcls) + (size_t)rb * nv_dim, nv_dim, xs4, v0, v1);
+		warp_pair<DBITS>(reinterpret_cast<const uint4*>(a.wcls) + (size_t)ra * nv_dim, reinterpret_cast<const uint4*>(a.wcls) + (size_t)rb * nv_dim, nv_dim, xs4, pol, v0, v1);
 		if (lane == 0) {
 			a.logits[ra] = v0;
 			if (v0 > best) best = v0, besti = ra;

@@ -23,10 +23,9 @@ struct MoeSel { // router decision of the current layer, written by k_ffn_up, re
 // Each lane owns every 32nd 16-byte vector of a row; U vectors per row are requested before the
 // first is consumed, so a warp keeps R*U*512 bytes in flight.
 
-template <int DBITS, int R>
+template <int DBITS, int R, int U = 4>
 __device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int nvec, const float4* __restrict__ xs4, float (&out)[R]) {
 	constexpr int Q = WFmt<DBITS>::VW / 4;
-	constexpr int U = DBITS == 4 ? 2 : 4;
 	const int lane = threadIdx.x & 31;
 
 	float acc[R];
@@ -64,8 +63,7 @@ __device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int n
 // Every thread requests all of its elements (16-byte loads, up to SV_MAX per thread) before it touches the
 // first one, so staging costs one L2 round trip instead of one per element; the vector is read through L2
 // (inside the persistent kernel other SMs wrote it during the same launch).
-#define SV_MAX 8
-template <int DBITS>
+template <int DBITS, int SV_MAX = 8>
 __device__ __forceinline__ void stage_vector(float* xs, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln,
                                              float* xb_out) {
 	const int tid = threadIdx.x, nthr = blockDim.x;
@@ -177,6 +175,7 @@ struct EmbedArgs {
 
 template <int DBITS, typename KVT>
 __global__ void k_embed(const EmbedArgs<KVT> a) {
+	pdl_enter();
 	if ((int)blockIdx.x < a.embed_blocks) {
 		int i = blockIdx.x * blockDim.x + threadIdx.x;
 		if (i < a.dim) a.x[i] = weight_at<DBITS>(a.table, (size_t)a.tp->token * a.dim + i);
@@ -224,6 +223,7 @@ struct QkvArgs {
 
 template <int DBITS, typename KVT>
 __global__ void __launch_bounds__(256) k_qkv(const QkvArgs<KVT> a) {
+	pdl_enter();
 	extern __shared__ __align__(16) float smem[];
 	float* red = smem;
 	float* xs = smem + 32;
@@ -609,6 +609,7 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int HG, int hsets, 
 #define ATTN_THREADS 256
 template <typename KVT, int HG>
 __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnArgs a) {
+	pdl_enter();
 	extern __shared__ __align__(16) float smem[];
 	__shared__ int flag;
 	const int unit = blockIdx.x / a.nsplit, split = blockIdx.x % a.nsplit, kv_len = a.tp->kv_len;
@@ -642,6 +643,7 @@ struct MatResArgs {
 
 template <int DBITS>
 __global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
+	pdl_enter();
 	extern __shared__ __align__(16) float smem[];
 	float* red = smem;
 	float* xs = smem + 32;
@@ -651,14 +653,17 @@ __global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
 
 	for (int e = 0; e < a.nact; ++e) {
 		if (e > 0) __syncthreads();
-		stage_vector<DBITS>(xs, red, a.xin + (size_t)e * a.n, a.n, nullptr, 0.f, false, nullptr);
+		stage_vector<DBITS, 16>(xs, red, a.xin + (size_t)e * a.n, a.n, nullptr, 0.f, false, nullptr);
 		const int ex = a.sel ? a.sel->expert[e] : 0;
 		const float ew = a.sel ? a.sel->weight[e] : 1.f;
 		const uint4* wb = reinterpret_cast<const uint4*>(a.w) + (size_t)ex * esize;
 		for (int p = blockIdx.x * nwarps + warp; p < a.d / 2; p += gridDim.x * nwarps) {
 			const uint4* rp[2] = {wb + (size_t)(2 * p) * nvec, wb + (size_t)(2 * p + 1) * nvec};
 			float v[2];
-			warp_dot_rows<DBITS, 2>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
+			if (nvec > 32 * 8 && DBITS != 4) // long rows (w2): a warp has one pair and is latency-bound; keep twice the loads in flight
+				warp_dot_rows<DBITS, 2, 8>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
+			else
+				warp_dot_rows<DBITS, 2>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
 			if (lane == 0) {
 				float2* dst = reinterpret_cast<float2*>(a.y + 2 * p);
 				float2 cur = (a.accumulate || e > 0) ? *dst : make_float2(0.f, 0.f);
@@ -690,6 +695,7 @@ struct FfnUpArgs {
 
 template <int DBITS>
 __global__ void __launch_bounds__(256) k_ffn_up(const FfnUpArgs a) {
+	pdl_enter();
 	extern __shared__ __align__(16) float smem[];
 	__shared__ float glog[64];
 	__shared__ MoeSel ssel;
@@ -760,6 +766,7 @@ struct OutputArgs {
 
 template <int DBITS>
 __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
+	pdl_enter();
 	constexpr int R = 4;
 	extern __shared__ __align__(16) float smem[];
 	__shared__ float outbuf[32]; // nwarps * R
@@ -809,6 +816,7 @@ __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
 // Fold the per-CTA candidates, publish the greedy token, and advance the token parameters so the
 // next replay of the graph consumes it (device-resident decode loop).
 __global__ void k_advance(const float* cand_val, const int* cand_idx, int ncand, TokenParams* tp, int* out_tokens, int* last_token, int advance, int vocab) {
+	pdl_enter();
 	__shared__ float sv[256];
 	__shared__ int si[256];
 	float best = -FLT_MAX;

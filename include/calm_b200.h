@@ -77,7 +77,8 @@ void calm_b200_release(struct Transformer* transformer);
 
 /* Which engine forward_cuda() uses: 0 = one kernel per stage (CUDA graph), 1 = persistent kernel fed by a
  * TMA ring (fused.cuh), 2 = persistent kernel with streaming loads and cross-barrier prefetch (persist.cuh).
- * Default from env CALM_B200_ENGINE, else 2.  Must be called before prepare_cuda(). */
+ * Default from env CALM_B200_ENGINE, else 0 (the fastest measured).  Must be called before
+ * prepare_cuda(). */
 void calm_b200_set_engine(int engine);
 
 /* The engine that serves the prepared model: 1 or 2 (one persistent kernel per token), or 0 when the staged
