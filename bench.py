@@ -182,7 +182,7 @@ def run_reference_arm(args, spec):
     tps, kind, threads, done = cpu_tokens_per_s(spec, args.seed, args.steps, args.warmup, pos0)
     out = {
         "impl": "reference", "metric": "tok/s single-batch decode", "value": tps, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / tps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp8 e5m2 weights)",
+        "warmup": args.warmup, "ms_per_step": 1e3 / tps, "higher_is_better": True, "scaling": "strong" if (args.parallel == "tp" and args.gpus > 1) else "weak", "vs_baseline": None, "dtype": "f32 (fp8 e5m2 weights)",
         "data": "synthetic", "config": workload_config(spec, pos0, args),
         "cpu_baseline": {"value": tps, "unit": "tok/s", "cores": threads, "kind": kind,
                          "sample": f"{done} tokens at pos {pos0 + args.warmup}.. of the same model, all {threads} host threads"},
@@ -196,7 +196,7 @@ def workload_config(spec, pos0, args):
     return {"workload": f"{spec.name}: {spec.n_layers} layers, dim {spec.dim}, hidden {spec.hidden_dim}, heads {spec.n_heads}/{spec.n_kv_heads}x{spec.head_dim}, "
                         f"vocab {spec.vocab_size}, {spec.dtype} weights, fp16 KV cache, context 4096, batch 1",
             "positions": f"{pos0}..{pos0 + args.steps + args.warmup - 1} (KV cache pre-filled to pos0)", "l2": "inputs (7.5 GB of weights per step) exceed the 126 MB L2; no flush",
-            "parallelism": "replicas" if args.gpus > 1 else "single GPU"}
+            "parallelism": "single GPU" if args.gpus <= 1 else (f"tp{args.gpus}" if args.parallel == "tp" else "replicas")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -212,6 +212,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--parallel", default="replicas", choices=["replicas", "tp"],
+                    help="N>1: independent replicas (weak scaling, no data-path collective; default) or ONE token stream "
+                         "tensor-parallel over the N GPUs (strong scaling; two NCCL all-reduces per layer)")
     ap.add_argument("--layers", type=int, default=None, help="(debug) override the layer count")
     ap.add_argument("--pos0", type=int, default=None, help="(debug) first timed position instead of the end of the context")
     args = ap.parse_args()
@@ -251,9 +254,19 @@ def main():
     cbuild.build()
     L = lib.load()
     seq_len = 4096
-    tensors = mg.generate(spec, args.seed + rank, device="cuda")
+    tp = None
+    if use_dist and args.parallel == "tp":
+        from calm_b200 import tp as ctp
+
+        ctp.shard_dims(spec, world)  # raises when the shape does not split
+        L.calm_b200_set_device(local)
+        ident = [lib.tp_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        tp = (rank, world, ident[0])
+    is_tp = tp is not None
+    tensors = mg.generate(spec, args.seed + (0 if is_tp else rank), device="cuda")  # TP ranks hold the SAME model
     torch.cuda.synchronize()
-    dm = lib.DeviceModel(spec, tensors, seq_len=seq_len, device=local, engine=args.engine)
+    dm = lib.DeviceModel(spec, tensors, seq_len=seq_len, device=local, engine=args.engine, tp=tp)
     K, W = args.steps, args.warmup
     pos0 = max(0, seq_len - (K + W)) if args.pos0 is None else args.pos0
     dm.fill_kv(min(pos0, seq_len), seed=1 + rank)
@@ -277,7 +290,7 @@ def main():
     launches = int(L.calm_b200_launch_count() - l0)
     clocks = sampler.stop(t_wall0, t_wall1)
     ms = max_over_ranks(ms)
-    value = agg.whole_job_rate(K, ms)
+    value = K / (ms / 1e3) if is_tp else agg.whole_job_rate(K, ms)  # TP: the N GPUs serve ONE token stream
 
     # ---- leg 2: end to end through forward_cuda with host buffers
     tok = 23
@@ -293,15 +306,23 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e = agg.whole_job_rate(K, e2e_s * 1e3)
+    e2e = K / e2e_s if is_tp else agg.whole_job_rate(K, e2e_s * 1e3)
 
     # ---- roofline of the dominant kernel
     peak, peak_src = measured_peak()
-    roof = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src, ms / K, bytes_per_tok)
+    if is_tp:
+        # per GPU: 1/N of every layer's weights and KV entries, the whole (replicated) classifier; the unit is the token
+        cls_b = spec.vocab_size * spec.dim * spec.dbits / 8
+        per_gpu = (bytes_per_tok - cls_b) / world + cls_b
+        roof = {"bound": "hbm", "kernel": f"whole token on one of {world} tensor-parallel GPUs (staged kernels + 2 all-reduces per layer)",
+                "achieved": per_gpu / 1e9 / (ms / K / 1e3), "peak": peak, "unit": "GB/s", "frac": per_gpu / 1e9 / (ms / K / 1e3) / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu}
+    else:
+        roof = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src, ms / K, bytes_per_tok)
 
     out = {
         "metric": "tok/s single-batch decode", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp8 e5m2 weights, f32 accumulate, fp16 KV)" if spec.dtype == "fp8" else f"f32 ({spec.dtype} weights)",
+        "higher_is_better": True, "scaling": "strong" if is_tp else "weak", "vs_baseline": None, "dtype": "f32 (fp8 e5m2 weights, f32 accumulate, fp16 KV)" if spec.dtype == "fp8" else f"f32 ({spec.dtype} weights)",
         "data": "synthetic", "config": workload_config(spec, pos0, args),
         "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": spec.vocab_size * 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,

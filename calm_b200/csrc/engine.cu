@@ -8,6 +8,7 @@
 
 #include "../../include/calm_b200.h"
 
+#include <dlfcn.h>
 #include <math.h>
 #include <string.h>
 
@@ -74,6 +75,12 @@ struct Engine {
 	bool fused_perf = false;
 	cudaGraphExec_t fgraph[4] = {nullptr, nullptr, nullptr, nullptr};
 	int fgraph_launches[4] = {0, 0, 0, 0};
+
+	// tensor parallelism (staged engine): this process owns 1/tp_world of the heads and of the FFN rows
+	int tp_rank = 0, tp_world = 1;
+	void* tp_comm = nullptr;         // ncclComm_t
+	float* xpart = nullptr;          // partial of wo / w2 before the all-reduce
+	std::vector<void*> tp_owned;     // shard copies made by prepare_cuda (wo / w2 column slices, packed biases)
 
 	// persistent engine (engine kind 2)
 	bool persist_ok = false;
@@ -146,6 +153,51 @@ int balanced_grid(int units, int cap) {
 template <int DBITS>
 size_t xs_bytes(int n) {
 	return (size_t)(32 + xs_floats<DBITS>(n)) * sizeof(float);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (the library stays loadable and linkable without it; only tensor-parallel runs need it)
+
+struct NcclApi {
+	void* lib = nullptr;
+	int (*GetUniqueId)(void*) = nullptr;
+	int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ struct Id128, int) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*CommDestroy)(void*) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+struct Id128 {
+	char bytes[128];
+};
+NcclApi g_nccl;
+Id128 g_tp_id;
+bool g_tp_pending = false;
+int g_tp_rank = 0, g_tp_world = 1;
+
+void nccl_load() {
+	if (g_nccl.lib) return;
+	const char* names[] = {"libnccl.so.2", "libnccl.so"};
+	for (const char* n : names)
+		if ((g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+	if (!g_nccl.lib) CALM_FATAL("tensor parallelism needs NCCL (libnccl.so.2): %s", dlerror());
+	g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+	g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+	g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+	g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+	g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) CALM_FATAL("libnccl lacks the expected entry points");
+}
+
+#define NCCL_CHECK(x)                                                                                              \
+	do {                                                                                                           \
+		int r_ = (x);                                                                                              \
+		if (r_ != 0) CALM_FATAL("NCCL error %d (%s) at %s:%d", r_, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?", __FILE__, __LINE__); \
+	} while (0)
+
+// sum over ranks of a float vector, in stream order (captured into the CUDA graph like any kernel)
+void tp_allreduce(float* buf, size_t count) {
+	NCCL_CHECK(g_nccl.AllReduce(buf, buf, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, g.tp_comm, g.stream));
 }
 
 // Launch on the library's stream with programmatic stream serialization (PDL), so that consecutive kernels
@@ -260,8 +312,14 @@ int run_token(int mode) {
 			StageTimer t(ST_WO, (double)dim * g.q_dim * wb / 8);
 			MatResArgs a;
 			a.xin = g.att, a.w = w.wo[l], a.y = g.x, a.sel = nullptr, a.n = g.q_dim, a.d = dim, a.nact = 1, a.accumulate = 1;
+			if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0; // partial over this rank's heads
 			launch_pdl(k_matres<DBITS>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
+			if (g.tp_world > 1) {
+				tp_allreduce(g.xpart, dim);
+				launch_pdl(k_addvec, cdiv(dim, 256), 256, 0, g.x, (const float*)g.xpart, dim);
+				++nl;
+			}
 		}
 		{
 			StageTimer t(ST_FFN_UP, (double)2 * g.nact * hidden * dim * wb / 8);
@@ -278,8 +336,14 @@ int run_token(int mode) {
 			MatResArgs a;
 			a.xin = g.hb, a.w = w.w2[l], a.y = g.x, a.sel = c.n_experts ? g.moe_sel : nullptr;
 			a.n = hidden, a.d = dim, a.nact = g.nact, a.accumulate = 1;
+			if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0; // partial over this rank's FFN rows
 			launch_pdl(k_matres<DBITS>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
+			if (g.tp_world > 1) {
+				tp_allreduce(g.xpart, dim);
+				launch_pdl(k_addvec, cdiv(dim, 256), 256, 0, g.x, (const float*)g.xpart, dim);
+				++nl;
+			}
 		}
 	}
 
@@ -301,6 +365,48 @@ int run_token(int mode) {
 		}
 	}
 	return nl;
+}
+
+
+// Tensor-parallel view of the model for rank r of N (Megatron split): query/kv heads and FFN rows
+// are divided, so wq/wk/wv/w1/w3 shards are contiguous row ranges of the uploaded tensors (no copy), while wo and w2
+// need their COLUMN range, packed once into a contiguous (dim x n/N) matrix.  Embedding, norms and the classifier
+// are replicated.  After this the engine runs unchanged on the "local" shapes; the two partial projections per layer
+// are summed with one all-reduce each.
+void tp_shard_model() {
+	Config& c = g.cfg;
+	Weights& w = g.w;
+	const int N = g.tp_world, r = g.tp_rank;
+	if (c.n_experts) CALM_FATAL("tensor parallelism: MoE models are not sharded yet");
+	if (c.n_heads % N || c.n_kv_heads % N || c.hidden_dim % (32 * N)) CALM_FATAL("tensor parallelism: %d ranks do not divide heads %d/%d or hidden %d", N, c.n_heads, c.n_kv_heads, c.hidden_dim);
+	const size_t wb = (size_t)w.dbits;
+	const int q_dim = c.head_dim * c.n_heads, kv_dim = c.head_dim * c.n_kv_heads;
+	const int ql = q_dim / N, kl = kv_dim / N, hl = c.hidden_dim / N;
+	auto rows = [&](void* base, size_t row0, size_t cols) { return (void*)((char*)base + row0 * cols * wb / 8); };
+	auto col_slice = [&](const void* base, int nrows, size_t cols, size_t col0, size_t ncols) {
+		void* dst = dev_alloc((size_t)nrows * ncols * wb / 8);
+		CUDA_CHECK(cudaMemcpy2D(dst, ncols * wb / 8, (const char*)base + col0 * wb / 8, cols * wb / 8, ncols * wb / 8, nrows, cudaMemcpyDeviceToDevice));
+		g.tp_owned.push_back(dst);
+		return dst;
+	};
+	for (int l = 0; l < c.n_layers; ++l) {
+		w.wq[l] = rows(w.wq[l], (size_t)r * ql, c.dim);
+		w.wk[l] = rows(w.wk[l], (size_t)r * kl, c.dim);
+		w.wv[l] = rows(w.wv[l], (size_t)r * kl, c.dim);
+		w.w1[l] = rows(w.w1[l], (size_t)r * hl, c.dim);
+		w.w3[l] = rows(w.w3[l], (size_t)r * hl, c.dim);
+		w.wo[l] = col_slice(w.wo[l], c.dim, q_dim, (size_t)r * ql, ql);
+		w.w2[l] = col_slice(w.w2[l], c.dim, c.hidden_dim, (size_t)r * hl, hl);
+		if (w.bqkv[l]) { // [q | k | v] -> this rank's [q_r | k_r | v_r]
+			float* b = (float*)dev_alloc((size_t)(ql + 2 * kl) * sizeof(float));
+			CUDA_CHECK(cudaMemcpy(b, w.bqkv[l] + (size_t)r * ql, ql * sizeof(float), cudaMemcpyDeviceToDevice));
+			CUDA_CHECK(cudaMemcpy(b + ql, w.bqkv[l] + q_dim + (size_t)r * kl, kl * sizeof(float), cudaMemcpyDeviceToDevice));
+			CUDA_CHECK(cudaMemcpy(b + ql + kl, w.bqkv[l] + q_dim + kv_dim + (size_t)r * kl, kl * sizeof(float), cudaMemcpyDeviceToDevice));
+			g.tp_owned.push_back(b);
+			w.bqkv[l] = b;
+		}
+	}
+	c.n_heads /= N, c.n_kv_heads /= N, c.hidden_dim = hl;
 }
 
 // Fix grid sizes and shared-memory opt-ins for this model (called once from prepare_cuda).
@@ -688,8 +794,8 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	select_device();
 	if (g.ready) CALM_FATAL("prepare_cuda called twice; call calm_b200_release() first (one model per process, as in the reference)");
 
-	const Config& c = transformer->config;
-	const Weights& w = transformer->weights;
+	Config c = transformer->config; // copies: under tensor parallelism they become this rank's shard view
+	Weights w = transformer->weights;
 	RunState* s = &transformer->state;
 
 	cudaDeviceProp prop;
@@ -715,7 +821,17 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.w = w;
 	g.kvbits = s->kvbits;
 	g.nact = c.n_experts ? c.n_experts_ac : 1;
-	g.q_dim = q_dim, g.kv_dim = kv_dim, g.kv_mul = c.n_heads / c.n_kv_heads;
+	g.tp_rank = g_tp_rank, g.tp_world = g_tp_world;
+	if (g.tp_world > 1) {
+		nccl_load();
+		NCCL_CHECK(g_nccl.CommInitRank(&g.tp_comm, g.tp_world, g_tp_id, g.tp_rank));
+		tp_shard_model(); // g.cfg / g.w now describe this rank's shard
+		c = g.cfg, w = g.w;
+		q_dim = c.head_dim * c.n_heads, kv_dim = c.head_dim * c.n_kv_heads;
+		if (kv_dim % 32 || c.hidden_dim % 32 || q_dim % 32) CALM_FATAL("tensor parallelism: per-rank q_dim, kv_dim and hidden_dim must be multiples of 32");
+		g.xpart = (float*)dev_alloc(c.dim * sizeof(float));
+	}
+	g.q_dim = q_dim, g.kv_dim = kv_dim, g.kv_mul = g.cfg.n_heads / g.cfg.n_kv_heads;
 	g.use_graph = !(getenv("CALM_B200_GRAPH") && atoi(getenv("CALM_B200_GRAPH")) == 0);
 	g.use_pdl = !(getenv("CALM_B200_PDL") && atoi(getenv("CALM_B200_PDL")) == 0);
 	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
@@ -727,6 +843,11 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	for (int i = 0; i < 2; ++i) {
 		CUDA_CHECK(cudaEventCreate(&g.ev[i]));
 		CUDA_CHECK(cudaEventCreate(&g.timer[i]));
+	}
+	if (g.tp_world > 1) { // first collective outside any graph capture: NCCL sets up its channels and buffers here
+		CUDA_CHECK(cudaMemsetAsync(g.xpart, 0, c.dim * sizeof(float), g.stream));
+		tp_allreduce(g.xpart, c.dim);
+		CUDA_CHECK(cudaStreamSynchronize(g.stream));
 	}
 
 	g.x = (float*)dev_alloc(c.dim * sizeof(float));
@@ -782,6 +903,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	CUDA_CHECK(cudaMemset(g.tp, 0, sizeof(TokenParams)));
 
 	g.engine = g_engine_kind >= 0 ? g_engine_kind : (getenv("CALM_B200_ENGINE") ? atoi(getenv("CALM_B200_ENGINE")) : 0);
+	if (g.tp_world > 1) g.engine = 0; // the all-reduce is a stream-ordered NCCL call between staged kernels
 	switch (w.dbits) {
 	case 16: make_plan_kv<16>(); break;
 	case 8: make_plan_kv<8>(); break;
@@ -806,6 +928,26 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	CUDA_CHECK(cudaDeviceSynchronize());
 }
 
+extern "C" void calm_b200_tp_unique_id(void* out128) {
+	select_device();
+	nccl_load();
+	Id128 id;
+	memset(&id, 0, sizeof(id));
+	NCCL_CHECK(g_nccl.GetUniqueId(&id));
+	memcpy(out128, &id, sizeof(id));
+}
+
+extern "C" void calm_b200_tp_init(int rank, int world, const void* id128) {
+	if (g.ready) CALM_FATAL("calm_b200_tp_init must precede prepare_cuda");
+	if (world < 1 || rank < 0 || rank >= world) CALM_FATAL("calm_b200_tp_init: bad rank %d of %d", rank, world);
+	g_tp_rank = rank, g_tp_world = world;
+	if (world > 1) memcpy(&g_tp_id, id128, sizeof(g_tp_id));
+}
+
+extern "C" int calm_b200_tp_world(void) {
+	return g.ready ? g.tp_world : g_tp_world;
+}
+
 extern "C" void calm_b200_release(struct Transformer* transformer) {
 	if (!g.ready) return;
 	CUDA_CHECK(cudaDeviceSynchronize());
@@ -820,6 +962,10 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 	cudaFreeHost(g.logits_host), cudaFreeHost(g.last_token);
 	cudaFree(g.kc), cudaFree(g.vc), cudaFree(g.rope_freq), cudaFree(g.attn_partial), cudaFree(g.attn_counter);
 	cudaFree(g.moe_sel), cudaFree(g.tp), cudaFree(g.cand_val), cudaFree(g.cand_idx), cudaFree(g.out_tokens);
+	if (g.tp_comm) g_nccl.CommDestroy(g.tp_comm);
+	if (g.xpart) cudaFree(g.xpart);
+	for (void* p : g.tp_owned) cudaFree(p);
+	g_tp_world = 1, g_tp_rank = 0; // a new communicator needs a new calm_b200_tp_init
 	for (int i = 0; i < 2; ++i) cudaEventDestroy(g.ev[i]), cudaEventDestroy(g.timer[i]);
 	cudaStreamDestroy(g.stream);
 	int dev = g.device;

@@ -865,6 +865,13 @@ __global__ void k_set_params(TokenParams* tp, int token, int pos, int seq_len, i
 	tp->seq_len = seq_len;
 }
 
+// x += p (tensor-parallel: the all-reduced partial of wo / w2 joins the residual stream)
+__global__ void k_addvec(float* x, const float* p, int n) {
+	pdl_enter();
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) x[i] += p[i];
+}
+
 // plain matvec (unit tests, per-kernel roofline bench): y = W . x
 struct MatvecArgs {
 	const float* x;

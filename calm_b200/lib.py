@@ -27,6 +27,7 @@ SYMBOLS = [
     "calm_b200_forward_argmax", "calm_b200_decode_greedy", "calm_b200_timer_start", "calm_b200_timer_stop",
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
     "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_engine_in_use", "calm_b200_stage_wait_ms", "calm_b200_barrier_bench", "calm_b200_stage_detail_ms",
+    "calm_b200_tp_unique_id", "calm_b200_tp_init", "calm_b200_tp_world",
 ]
 
 _lib = None
@@ -67,8 +68,18 @@ def load() -> C.CDLL:
     L.calm_b200_stage_wait_ms.argtypes, L.calm_b200_stage_wait_ms.restype = [C.c_int], C.c_double
     L.calm_b200_barrier_bench.argtypes, L.calm_b200_barrier_bench.restype = [C.c_int], C.c_float
     L.calm_b200_stage_detail_ms.argtypes, L.calm_b200_stage_detail_ms.restype = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)], None
+    L.calm_b200_tp_unique_id.argtypes, L.calm_b200_tp_unique_id.restype = [C.c_void_p], None
+    L.calm_b200_tp_init.argtypes, L.calm_b200_tp_init.restype = [C.c_int, C.c_int, C.c_void_p], None
+    L.calm_b200_tp_world.argtypes, L.calm_b200_tp_world.restype = [], C.c_int
     _lib = L
     return L
+
+
+def tp_unique_id() -> bytes:
+    """128-byte NCCL id for calm_b200_tp_init; rank 0 makes it, every rank of the group receives it."""
+    buf = C.create_string_buffer(128)
+    load().calm_b200_tp_unique_id(buf)
+    return buf.raw
 
 
 class DeviceModel:
@@ -83,11 +94,14 @@ class DeviceModel:
     """
 
     def __init__(self, spec: mg.ModelSpec, tensors: Dict[str, "object"], seq_len: Optional[int] = None, kvbits: int = 16,
-                 device: Optional[int] = None, engine: Optional[int] = None):
+                 device: Optional[int] = None, engine: Optional[int] = None, tp=None):
+        """tp = (rank, world, id128) turns on tensor parallelism (include/calm_b200.h); tensors stay the FULL model."""
         self.lib = load()
         self.spec = spec
         if device is not None:
             self.lib.calm_b200_set_device(device)
+        if tp is not None:
+            self.lib.calm_b200_tp_init(int(tp[0]), int(tp[1]), C.c_char_p(tp[2]) if tp[2] else None)
         if engine is not None:
             self.lib.calm_b200_set_engine(engine)
         self._uploaded = []

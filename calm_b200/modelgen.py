@@ -103,6 +103,8 @@ SPECS.update({
     "tiny-ln": replace(_T, name="tiny-ln", norm_type="layernorm", dtype="fp16"),
     "tiny-lnpar": replace(_T, name="tiny-lnpar", norm_type="layernorm_par", dtype="fp16"),
     "tiny-mha": replace(_T, name="tiny-mha", n_heads=8, n_kv_heads=8),
+    # QKV bias + tied classifier on a shape two tensor-parallel ranks can split (tiny-qwen has a single kv head)
+    "tiny-bias2": replace(_T, name="tiny-bias2", dtype="fp16", n_heads=4, n_kv_heads=2, head_dim=64, qkv_bias=True, tied=True),
 })
 
 

@@ -81,6 +81,20 @@ void calm_b200_release(struct Transformer* transformer);
  * prepare_cuda(). */
 void calm_b200_set_engine(int engine);
 
+/* Tensor parallelism for models that do not fit (or should not sit on) one GPU -- the 70B shape of
+ * BASELINE.json configs[4]; the reference has no counterpart (single device, infer.cu:79).  One process per GPU.
+ * Rank 0 obtains a 128-byte NCCL id with calm_b200_tp_unique_id() and hands it to the other ranks by any means
+ * (file, pipe, torch.distributed broadcast); every rank then calls calm_b200_tp_init(rank, world, id) BEFORE
+ * prepare_cuda() and afterwards drives the library exactly as a single-GPU host does: upload the FULL tensors,
+ * prepare, forward the same (token, pos) on every rank.  prepare_cuda() keeps this rank's 1/world of the query /
+ * kv heads and of the FFN rows (row ranges of wq/wk/wv/w1/w3 in place, packed column ranges of wo/w2); each
+ * forward sums the two partial projections per layer over NVLink (ncclAllReduce, in stream order inside the CUDA
+ * graph) and every rank returns the full, identical logits.  Requires world | n_heads, n_kv_heads and 32*world |
+ * hidden_dim; dense models; staged engine.  libnccl.so.2 is bound with dlopen on first use. */
+void calm_b200_tp_unique_id(void* out128);
+void calm_b200_tp_init(int rank, int world, const void* id128);
+int calm_b200_tp_world(void);
+
 /* The engine that serves the prepared model: 1 or 2 (one persistent kernel per token), or 0 when the staged
  * engine does (MoE, fp8 KV cache, unsupported shapes, or engine 0 requested). */
 int calm_b200_engine_in_use(void);

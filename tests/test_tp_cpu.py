@@ -1,0 +1,75 @@
+"""Tensor-parallel host logic on CPU: the shape rules, and that the slices prepare_cuda takes (calm_b200/tp.py
+shard_tensors restates them in numpy) really partition the model -- row shards reproduce the full q/k/v/w1/w3 rows bit for
+bit, column shards of wo/w2 sum to the full projection -- checked with the oracle's own decoders for all three formats."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from calm_b200 import modelgen as mg  # noqa: E402
+from calm_b200 import tp  # noqa: E402
+
+
+def test_shard_dims_rules():
+    d = tp.shard_dims(mg.SPECS["llama3-70b-fp8"], 8)
+    assert d == {"n_heads": 8, "n_kv_heads": 1, "hidden_dim": 3584, "q_dim": 1024, "kv_dim": 128}
+    assert tp.shard_dims(mg.SPECS["llama3-8b-fp8"], 2)["hidden_dim"] == 7168
+    assert tp.shard_dims(mg.SPECS["llama3-8b-fp8"], 1)["n_heads"] == 32
+    with pytest.raises(ValueError):
+        tp.shard_dims(mg.SPECS["llama3-70b-fp8"], 16)      # 8 kv heads
+    with pytest.raises(ValueError):
+        tp.shard_dims(mg.SPECS["mixtral-8x7b-fp8"], 2)     # MoE
+    with pytest.raises(ValueError):
+        tp.shard_dims(mg.SPECS["tiny-qwen"], 2)            # one kv head
+    with pytest.raises(ValueError):
+        tp.shard_dims(mg.SPECS["tiny-fp8"], 4)             # hidden 704 = 22 * 32, not a multiple of 128
+    assert tp.local_spec(mg.SPECS["tiny-fp8"], 2).kv_dim == 64
+
+
+@pytest.mark.parametrize("name", ["tiny-fp8", "tiny-fp16", "tiny-gf4", "tiny-bias2"])
+def test_shards_partition_the_model(oracle_pkg, name):
+    spec = mg.SPECS[name]
+    world = 2
+    model = mg.HostModel(spec, seed=0)
+    ck = oracle_pkg.Checker("port_f64")
+    rng = np.random.default_rng(5)
+    shards = [tp.shard_tensors(spec, model.tensors, r, world) for r in range(world)]
+    d = tp.shard_dims(spec, world)
+    p = "model.layers.1."
+    x = rng.standard_normal(spec.dim).astype(np.float32)
+
+    def mv(t, xin):
+        a = t.numpy()
+        n = a.shape[1] * (8 if spec.dbits == 4 else 1)
+        return ck.matvec(spec.dbits, a, xin, n, a.shape[0])
+
+    # row shards: concatenation of the ranks' outputs IS the full output
+    for leaf, rows in (("attn.wq", d["q_dim"]), ("attn.wk", d["kv_dim"]), ("attn.wv", d["kv_dim"]), ("mlp.w1", d["hidden_dim"]), ("mlp.w3", d["hidden_dim"])):
+        full = mv(model.tensors[p + leaf + ".weight"], x)
+        parts = [mv(s[p + leaf + ".weight"], x) for s in shards]
+        assert all(len(q) == rows for q in parts)
+        assert np.array_equal(np.concatenate(parts), full), leaf
+    # column shards: partials over each rank's slice of the input sum to the full projection
+    for leaf, n, nl in (("attn.wo", spec.q_dim, d["q_dim"]), ("mlp.w2", spec.hidden_dim, d["hidden_dim"])):
+        xin = rng.standard_normal(n).astype(np.float32)
+        full = mv(model.tensors[p + leaf + ".weight"], xin)
+        part = sum(mv(s[p + leaf + ".weight"], xin[r * nl:(r + 1) * nl]).astype(np.float64) for r, s in enumerate(shards))
+        assert np.allclose(part, full, rtol=1e-5, atol=1e-6), leaf
+    if spec.qkv_bias:
+        b = model.tensors[p + "attn.wqkv.bias"].numpy()
+        q = np.concatenate([s[p + "attn.wqkv.bias"].numpy()[:d["q_dim"]] for s in shards])
+        k = np.concatenate([s[p + "attn.wqkv.bias"].numpy()[d["q_dim"]:d["q_dim"] + d["kv_dim"]] for s in shards])
+        v = np.concatenate([s[p + "attn.wqkv.bias"].numpy()[d["q_dim"] + d["kv_dim"]:] for s in shards])
+        assert np.array_equal(np.concatenate([q, k, v]), b)
+
+
+def test_id_file_handoff(tmp_path):
+    path = str(tmp_path / "id")
+    ident = bytes(range(128))
+    tp.publish_id(path, ident)
+    assert tp.wait_id(path, 1.0) == ident
+    with pytest.raises(TimeoutError):
+        tp.wait_id(str(tmp_path / "missing"), 0.2)

@@ -1,0 +1,58 @@
+"""Tensor parallelism on two GPUs: one process per GPU, each given the FULL model through the reference
+boundary plus calm_b200_tp_init; every rank must return the full logits, equal to the single-device oracle / the
+reference fixtures within the stated tolerance, and all ranks must agree bit for bit (they sample independently)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from conftest import ROOT, TOL_SIGMA, golden  # noqa: E402
+
+from calm_b200 import modelgen as mg  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpus():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("name", ["tiny-fp8", "tiny-gf4", "tiny-bias2", "tiny-lnpar", "tiny-mha"])
+def test_two_rank_logits_match_single_device_reference(tmp_path, name):
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    spec = mg.SPECS[name]
+    g = golden(name)
+    out = str(tmp_path / "tp")
+    idfile = str(tmp_path / "nccl.id")
+    env = dict(os.environ, PYTHONPATH=ROOT, CALM_B200_QUIET="1")
+    procs = [subprocess.Popen([sys.executable, "-m", "calm_b200.tp", "--spec", name, "--rank", str(r), "--world", "2", "--idfile", idfile,
+                               "--tokens", str(len(g["tokens"])), "--out", out, "--greedy", "12"], cwd=ROOT, env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    logs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            pytest.fail("tensor-parallel worker hung")
+        logs.append(o)
+    assert all(p.returncode == 0 for p in procs), "\n".join(l[-1500:] for l in logs)
+    r0, r1 = (np.load(f"{out}.rank{r}.npz") for r in range(2))
+    assert int(r0["world"]) == 2
+    assert np.array_equal(r0["logits"], r1["logits"])      # every rank holds the same full logits
+    assert np.array_equal(r0["greedy"], r1["greedy"])      # so independent greedy sampling stays in lock step
+    steps = list(g["steps"])
+    ref = g["logits"]
+    sigma = float(ref.std())
+    err = float(np.abs(r0["logits"][steps] - ref).max())
+    assert err <= TOL_SIGMA * sigma, (err, sigma)
+    clear = g["margin"] > 2 * TOL_SIGMA * sigma
+    assert np.array_equal(r0["logits"].argmax(1)[clear], g["argmax"][clear])
+    assert spec.vocab_size == r0["logits"].shape[1]
