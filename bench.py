@@ -327,7 +327,7 @@ def main():
         "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": spec.vocab_size * 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         "algorithmic_gb_per_token": bytes_per_tok / 1e9, "hbm_gbs_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3),
-        "frac_of_peak_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3) / peak, "engine": "fused" if dm.uses_fused() else "staged",
+        "frac_of_peak_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3) / peak, "engine": "fused" if dm.uses_fused() else "staged", "tp_mode": {0: None, 1: "ncclAllReduce between kernels", 2: "all-reduce inside k_matres over peer memory"}[L.calm_b200_tp_mode()],
     }
     dm.close()
 

@@ -38,7 +38,7 @@ struct TokenParams {
 	int kv_sink; // 0, or KV_SINKS once the cache rolls over
 	int step;    // index into out_tokens (greedy decode)
 	int seq_len;
-	int pad;
+	int tp_seq;  // tokens started so far (tensor parallelism: epoch base of the peer-memory exchange; same on every rank)
 };
 
 // ---------------------------------------------------------------- programmatic dependent launch

@@ -79,7 +79,11 @@ struct Engine {
 	// tensor parallelism (staged engine): this process owns 1/tp_world of the heads and of the FFN rows
 	int tp_rank = 0, tp_world = 1;
 	void* tp_comm = nullptr;         // ncclComm_t
-	float* xpart = nullptr;          // partial of wo / w2 before the all-reduce
+	float* xpart = nullptr;          // partial of wo / w2 before the all-reduce (NCCL path)
+	bool tp_fused = false;           // wo / w2 sum their partials inside k_matres over peer memory (stages.cuh TpExchange)
+	void* tp_area = nullptr;         // this rank's exchange area: flags, then data
+	void* tp_peer[TP_MAX_WORLD] = {}; // every rank's area as mapped here (own entry == tp_area)
+	int* tp_err = nullptr;           // mapped host word for the exchange watchdog
 	std::vector<void*> tp_owned;     // shard copies made by prepare_cuda (wo / w2 column slices, packed biases)
 
 	// persistent engine (engine kind 2)
@@ -164,6 +168,7 @@ struct NcclApi {
 	int (*GetUniqueId)(void*) = nullptr;
 	int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ struct Id128, int) = nullptr;
 	int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
 	int (*CommDestroy)(void*) = nullptr;
 	const char* (*GetErrorString)(int) = nullptr;
 };
@@ -184,9 +189,10 @@ void nccl_load() {
 	g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
 	g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
 	g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+	g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
 	g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
 	g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
-	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) CALM_FATAL("libnccl lacks the expected entry points");
+	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy) CALM_FATAL("libnccl lacks the expected entry points");
 }
 
 #define NCCL_CHECK(x)                                                                                              \
@@ -198,6 +204,57 @@ void nccl_load() {
 // sum over ranks of a float vector, in stream order (captured into the CUDA graph like any kernel)
 void tp_allreduce(float* buf, size_t count) {
 	NCCL_CHECK(g_nccl.AllReduce(buf, buf, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, g.tp_comm, g.stream));
+}
+
+// Exchange areas for the fused matvec -> all-reduce (stages.cuh TpExchange): one cudaMalloc per rank, mapped into
+// every peer with CUDA IPC (one process per GPU); the 64-byte handles travel through an NCCL all-gather.  Falls
+// back to ncclAllReduce + k_addvec when peer mapping is unavailable on ANY rank (the ranks agree via an all-reduce).
+void tp_setup_exchange() {
+	const int W = g.tp_world, dim = g.cfg.dim;
+	const size_t flag_bytes = (size_t)TP_MAX_WORLD * TP_FLAG_CTAS * sizeof(int);
+	const size_t bytes = flag_bytes + (size_t)2 * W * dim * sizeof(float);
+	bool ok = W <= TP_MAX_WORLD && !(getenv("CALM_B200_TP_FUSED") && atoi(getenv("CALM_B200_TP_FUSED")) == 0);
+	g.tp_area = dev_alloc(bytes);
+	CUDA_CHECK(cudaMemset(g.tp_area, 0, bytes));
+	cudaIpcMemHandle_t mine;
+	if (cudaIpcGetMemHandle(&mine, g.tp_area) != cudaSuccess) ok = false, (void)cudaGetLastError();
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+	char* hdev = (char*)dev_alloc((size_t)W * 64 + sizeof(int));
+	CUDA_CHECK(cudaMemcpy(hdev + (size_t)g.tp_rank * 64, &mine, 64, cudaMemcpyHostToDevice));
+	NCCL_CHECK(g_nccl.AllGather(hdev + (size_t)g.tp_rank * 64, hdev, 64, /*ncclInt8*/ 0, g.tp_comm, g.stream));
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	std::vector<cudaIpcMemHandle_t> all(W);
+	CUDA_CHECK(cudaMemcpy(all.data(), hdev, (size_t)W * 64, cudaMemcpyDeviceToHost));
+	for (int p = 0; p < W && ok; ++p) {
+		if (p == g.tp_rank) {
+			g.tp_peer[p] = g.tp_area;
+			continue;
+		}
+		if (cudaIpcOpenMemHandle(&g.tp_peer[p], all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+			fprintf(stderr, "calm_b200: rank %d cannot map rank %d's exchange area (%s); using ncclAllReduce\n", g.tp_rank, p, cudaGetErrorString(cudaGetLastError()));
+			g.tp_peer[p] = nullptr;
+			ok = false;
+		}
+	}
+	// every rank must take the same path: min over ranks of `ok`
+	int* okdev = (int*)(hdev + (size_t)W * 64);
+	int okh = ok ? 1 : 0;
+	CUDA_CHECK(cudaMemcpy(okdev, &okh, sizeof(int), cudaMemcpyHostToDevice));
+	NCCL_CHECK(g_nccl.AllReduce(okdev, okdev, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, g.tp_comm, g.stream));
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	CUDA_CHECK(cudaMemcpy(&okh, okdev, sizeof(int), cudaMemcpyDeviceToHost));
+	CUDA_CHECK(cudaFree(hdev));
+	g.tp_fused = okh == 1;
+	if (g.tp_fused) {
+		CUDA_CHECK(cudaHostAlloc((void**)&g.tp_err, sizeof(int), cudaHostAllocMapped));
+		*g.tp_err = 0;
+	}
+}
+
+void tp_fill(TpExchange& t, int idx) {
+	t.world = g.tp_world, t.rank = g.tp_rank, t.idx = (unsigned)idx, t.stride = 2u * g.cfg.n_layers, t.tp = g.tp, t.err = g.tp_err;
+	const size_t flag_bytes = (size_t)TP_MAX_WORLD * TP_FLAG_CTAS * sizeof(int);
+	for (int p = 0; p < g.tp_world; ++p) t.flags[p] = (int*)g.tp_peer[p], t.data[p] = (float*)((char*)g.tp_peer[p] + flag_bytes);
 }
 
 // Launch on the library's stream with programmatic stream serialization (PDL), so that consecutive kernels
@@ -310,12 +367,13 @@ int run_token(int mode) {
 		}
 		{
 			StageTimer t(ST_WO, (double)dim * g.q_dim * wb / 8);
-			MatResArgs a;
+			MatResArgs a = {};
 			a.xin = g.att, a.w = w.wo[l], a.y = g.x, a.sel = nullptr, a.n = g.q_dim, a.d = dim, a.nact = 1, a.accumulate = 1;
-			if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0; // partial over this rank's heads
+			if (g.tp_fused) tp_fill(a.tpx, 2 * l); // partial over this rank's heads, summed over the ranks in the kernel
+			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
 			launch_pdl(k_matres<DBITS>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
-			if (g.tp_world > 1) {
+			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
 				launch_pdl(k_addvec, cdiv(dim, 256), 256, 0, g.x, (const float*)g.xpart, dim);
 				++nl;
@@ -333,13 +391,14 @@ int run_token(int mode) {
 		}
 		{
 			StageTimer t(ST_FFN_DOWN, (double)g.nact * hidden * dim * wb / 8);
-			MatResArgs a;
+			MatResArgs a = {};
 			a.xin = g.hb, a.w = w.w2[l], a.y = g.x, a.sel = c.n_experts ? g.moe_sel : nullptr;
 			a.n = hidden, a.d = dim, a.nact = g.nact, a.accumulate = 1;
-			if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0; // partial over this rank's FFN rows
+			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
+			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
 			launch_pdl(k_matres<DBITS>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
-			if (g.tp_world > 1) {
+			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
 				launch_pdl(k_addvec, cdiv(dim, 256), 256, 0, g.x, (const float*)g.xpart, dim);
 				++nl;
@@ -422,6 +481,10 @@ void make_plan() {
 	max_ctas(k_matres<DBITS>, 256, smem_res); // opt in to the larger of the two sizes
 	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_qdim));
 	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_hidden));
+	if (g.tp_fused) { // the in-kernel exchange needs co-resident grids (they are: balanced_grid stays under the cap) within its tables
+		for (int grid : {g.grid_wo, g.grid_down})
+			if (grid > TP_FLAG_CTAS || cdiv(c.dim / 2, grid * 8) > TP_MAX_ITERS) CALM_FATAL("tensor parallelism: grid %d outside the exchange tables for dim %d", grid, c.dim);
+	}
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
 	g.grid_up = imin(max_ctas(k_ffn_up<DBITS>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
 	g.grid_out = balanced_grid(cdiv(c.vocab_size, 32), max_ctas(k_output<DBITS>, 256, g.smem_dim));
@@ -848,6 +911,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 		CUDA_CHECK(cudaMemsetAsync(g.xpart, 0, c.dim * sizeof(float), g.stream));
 		tp_allreduce(g.xpart, c.dim);
 		CUDA_CHECK(cudaStreamSynchronize(g.stream));
+		tp_setup_exchange();
 	}
 
 	g.x = (float*)dev_alloc(c.dim * sizeof(float));
@@ -948,6 +1012,10 @@ extern "C" int calm_b200_tp_world(void) {
 	return g.ready ? g.tp_world : g_tp_world;
 }
 
+extern "C" int calm_b200_tp_mode(void) {
+	return !g.ready || g.tp_world <= 1 ? 0 : (g.tp_fused ? 2 : 1);
+}
+
 extern "C" void calm_b200_release(struct Transformer* transformer) {
 	if (!g.ready) return;
 	CUDA_CHECK(cudaDeviceSynchronize());
@@ -962,6 +1030,10 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 	cudaFreeHost(g.logits_host), cudaFreeHost(g.last_token);
 	cudaFree(g.kc), cudaFree(g.vc), cudaFree(g.rope_freq), cudaFree(g.attn_partial), cudaFree(g.attn_counter);
 	cudaFree(g.moe_sel), cudaFree(g.tp), cudaFree(g.cand_val), cudaFree(g.cand_idx), cudaFree(g.out_tokens);
+	for (int p = 0; p < TP_MAX_WORLD; ++p)
+		if (g.tp_peer[p] && g.tp_peer[p] != g.tp_area) cudaIpcCloseMemHandle(g.tp_peer[p]);
+	if (g.tp_area) cudaFree(g.tp_area);
+	if (g.tp_err) cudaFreeHost(g.tp_err);
 	if (g.tp_comm) g_nccl.CommDestroy(g.tp_comm);
 	if (g.xpart) cudaFree(g.xpart);
 	for (void* p : g.tp_owned) cudaFree(p);
@@ -982,6 +1054,7 @@ static void sync_stream() {
 	cudaError_t e = cudaStreamSynchronize(g.stream);
 	if (e != cudaSuccess) {
 		int code = g.fused_err ? *(volatile int*)g.fused_err : 0;
+		if (g.tp_err && *(volatile int*)g.tp_err) code = *(volatile int*)g.tp_err; // 9000 + rank never heard from
 		fprintf(stderr, "calm_b200: device failure: %s (%s); fused-engine watchdog code %d\n", cudaGetErrorString(e), cudaGetErrorName(e), code);
 		abort();
 	}

@@ -628,6 +628,84 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tensor parallelism: matvec -> all-reduce in ONE kernel over NVLink peer memory (one-shot, push).
+// Every rank owns an exchange area that all peers map (cudaIpc): flags[src rank][cta] and data[slot][src rank][dim].
+// CTA b of rank r computes the partial of its rows, stores it into slot (epoch & 1) of EVERY rank's area (16-byte
+// peer stores), publishes `epoch` in every rank's flags[r][b], waits until its own flags[*][b] carry the epoch --
+// CTA b of every peer owns the same rows, the grids being equal -- and then adds the partials in rank order, so all
+// ranks end up with bit-identical residual vectors.  A CTA signals before it waits and the grid is co-resident, so
+// ranks cannot deadlock; two slots suffice because a rank reaches epoch e+2 only after every peer has signalled
+// e+1, i.e. has finished the whole epoch-e kernel.  Costs one NVLink store latency instead of an NCCL kernel
+// plus a separate add kernel per projection.
+
+#define TP_MAX_WORLD 8
+#define TP_FLAG_CTAS 2048
+#define TP_MAX_ITERS 16
+
+struct TpExchange {
+	int world, rank;
+	unsigned idx, stride;      // epoch = tp_seq * stride + idx
+	const TokenParams* tp;
+	int* flags[TP_MAX_WORLD];  // rank p's flags  [TP_MAX_WORLD][TP_FLAG_CTAS]
+	float* data[TP_MAX_WORLD]; // rank p's data   [2][world][d]
+	int* err;                  // mapped host word: watchdog code
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const int* p) {
+	unsigned v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// part[it * 16 + k]: row 2 * ((it * gridDim.x + blockIdx.x) * 8) + k of this rank's partial.  All 256 threads call.
+__device__ __forceinline__ void tp_exchange_add(const TpExchange& t, const float* part, int niter, float* y, int d) {
+	const unsigned epoch = (unsigned)t.tp->tp_seq * t.stride + t.idx;
+	const int slot = epoch & 1;
+	const int W = t.world;
+	__syncthreads(); // part[] complete
+	const int pieces = niter * 4; // float4 pieces of this CTA per destination
+	for (int i = threadIdx.x; i < pieces * W; i += blockDim.x) {
+		const int peer = i / pieces, j = i - peer * pieces, it = j >> 2, q = j & 3;
+		const int row0 = 2 * ((it * gridDim.x + blockIdx.x) * 8) + q * 4;
+		if (row0 < d) {
+			float4 v = *reinterpret_cast<const float4*>(part + it * 16 + q * 4);
+			*reinterpret_cast<float4*>(t.data[peer] + ((size_t)slot * W + t.rank) * d + row0) = v;
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x < W) {
+		__threadfence_system(); // the CTA's peer stores (ordered before this thread by the barrier) precede the flag
+		*reinterpret_cast<volatile int*>(t.flags[threadIdx.x] + t.rank * TP_FLAG_CTAS + blockIdx.x) = (int)epoch;
+		const int* mine = t.flags[t.rank] + threadIdx.x * TP_FLAG_CTAS + blockIdx.x;
+		unsigned long long t0 = 0;
+		unsigned spins = 0;
+		while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+			if ((++spins & 1023) == 0) {
+				unsigned long long now;
+				asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+				if (!t0) t0 = now;
+				if (now - t0 > 20000000000ull) { // 20 s: a peer died or the ranks diverged -- fail loudly, never hang the GPU
+					if (t.err) *reinterpret_cast<volatile int*>(t.err) = 9000 + threadIdx.x;
+					__threadfence_system();
+					__trap();
+				}
+			}
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < niter * 16; i += blockDim.x) {
+		const int it = i >> 4, k = i & 15;
+		const int row = 2 * ((it * gridDim.x + blockIdx.x) * 8) + k;
+		if (row < d) {
+			const float* base = t.data[t.rank] + (size_t)slot * W * d + row;
+			float sum = 0.f;
+			for (int p = 0; p < W; ++p) sum += __ldcg(base + (size_t)p * d); // rank order: identical on every rank
+			y[row] += sum;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_matres: y[row] (+)= sum_e weight_e * (W_e[row] . xin_e)   -- wo (+ residual, infer.c:410-415) and
 // w2 (* router weight, + residual, infer.c:452-456).  Experts are visited in selection order by the
 // same lane, so the sum is deterministic (the reference CUDA path uses atomicAdd, infer.cu:618).
@@ -639,12 +717,14 @@ struct MatResArgs {
 	const MoeSel* sel; // NULL: one pass with expert 0, weight 1
 	int n, d, nact;
 	int accumulate;   // 1: y += ..., 0: y = ...
+	TpExchange tpx;   // world > 1: the partial is summed over the tensor-parallel ranks inside this kernel
 };
 
 template <int DBITS>
 __global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
 	pdl_enter();
 	extern __shared__ __align__(16) float smem[];
+	__shared__ __align__(16) float tp_part[TP_MAX_ITERS * 16];
 	float* red = smem;
 	float* xs = smem + 32;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -657,7 +737,8 @@ __global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
 		const int ex = a.sel ? a.sel->expert[e] : 0;
 		const float ew = a.sel ? a.sel->weight[e] : 1.f;
 		const uint4* wb = reinterpret_cast<const uint4*>(a.w) + (size_t)ex * esize;
-		for (int p = blockIdx.x * nwarps + warp; p < a.d / 2; p += gridDim.x * nwarps) {
+		int it = 0;
+		for (int p = blockIdx.x * nwarps + warp; p < a.d / 2; p += gridDim.x * nwarps, ++it) {
 			const uint4* rp[2] = {wb + (size_t)(2 * p) * nvec, wb + (size_t)(2 * p + 1) * nvec};
 			float v[2];
 			if (nvec > 32 * 8 && DBITS != 4) // long rows (w2): a warp has one pair and is latency-bound; keep twice the loads in flight
@@ -665,6 +746,10 @@ __global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
 			else
 				warp_dot_rows<DBITS, 2>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
 			if (lane == 0) {
+				if (a.tpx.world > 1) { // this rank's partial: summed over the ranks below
+					tp_part[it * 16 + warp * 2] = v[0], tp_part[it * 16 + warp * 2 + 1] = v[1];
+					continue;
+				}
 				float2* dst = reinterpret_cast<float2*>(a.y + 2 * p);
 				float2 cur = (a.accumulate || e > 0) ? *dst : make_float2(0.f, 0.f);
 				cur.x += v[0] * ew;
@@ -672,6 +757,10 @@ __global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
 				*dst = cur;
 			}
 		}
+	}
+	if (a.tpx.world > 1) { // dense models only (nact == 1); blockDim.x == 256, i.e. 16 rows per CTA and iteration
+		const int per = gridDim.x * 8;
+		tp_exchange_add(a.tpx, tp_part, (a.d / 2 - blockIdx.x * 8 + per - 1) / per, a.y, a.d);
 	}
 }
 
@@ -845,6 +934,7 @@ __global__ void k_advance(const float* cand_val, const int* cand_idx, int ncand,
 			int pos = tp->pos + 1, seq_len = tp->seq_len;
 			int sink = pos >= seq_len ? 2 : 0; // KV_SINKS
 			tp->token = tok;
+			tp->tp_seq += 1;
 			tp->pos = pos;
 			tp->kv_sink = sink;
 			tp->kv_pos = sink + (pos - sink) % (seq_len - sink);
@@ -863,6 +953,7 @@ __global__ void k_set_params(TokenParams* tp, int token, int pos, int seq_len, i
 	tp->kv_len = pos >= seq_len ? seq_len : pos + 1;
 	tp->step = step;
 	tp->seq_len = seq_len;
+	tp->tp_seq += 1;
 }
 
 // x += p (tensor-parallel: the all-reduced partial of wo / w2 joins the residual stream)

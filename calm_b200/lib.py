@@ -27,7 +27,7 @@ SYMBOLS = [
     "calm_b200_forward_argmax", "calm_b200_decode_greedy", "calm_b200_timer_start", "calm_b200_timer_stop",
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
     "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_engine_in_use", "calm_b200_stage_wait_ms", "calm_b200_barrier_bench", "calm_b200_stage_detail_ms",
-    "calm_b200_tp_unique_id", "calm_b200_tp_init", "calm_b200_tp_world",
+    "calm_b200_tp_unique_id", "calm_b200_tp_init", "calm_b200_tp_world", "calm_b200_tp_mode",
 ]
 
 _lib = None
@@ -71,6 +71,7 @@ def load() -> C.CDLL:
     L.calm_b200_tp_unique_id.argtypes, L.calm_b200_tp_unique_id.restype = [C.c_void_p], None
     L.calm_b200_tp_init.argtypes, L.calm_b200_tp_init.restype = [C.c_int, C.c_int, C.c_void_p], None
     L.calm_b200_tp_world.argtypes, L.calm_b200_tp_world.restype = [], C.c_int
+    L.calm_b200_tp_mode.argtypes, L.calm_b200_tp_mode.restype = [], C.c_int
     _lib = L
     return L
 

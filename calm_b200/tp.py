@@ -126,7 +126,7 @@ def main(argv=None):
     toks = mg.teacher_tokens(spec.vocab_size, a.tokens)
     logits = np.stack([dm.forward(int(t), i) for i, t in enumerate(toks)])
     greedy = dm.decode_greedy(int(toks[0]), 0, a.greedy) if a.greedy else np.zeros(0, np.int32)
-    np.savez(f"{a.out}.rank{a.rank}.npz", logits=logits, greedy=greedy, world=L.calm_b200_tp_world(), launches=L.calm_b200_launch_count())
+    np.savez(f"{a.out}.rank{a.rank}.npz", logits=logits, greedy=greedy, world=L.calm_b200_tp_world(), mode=L.calm_b200_tp_mode(), launches=L.calm_b200_launch_count())
     dm.close()
     return 0
 

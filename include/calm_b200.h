@@ -88,12 +88,15 @@ void calm_b200_set_engine(int engine);
  * prepare_cuda() and afterwards drives the library exactly as a single-GPU host does: upload the FULL tensors,
  * prepare, forward the same (token, pos) on every rank.  prepare_cuda() keeps this rank's 1/world of the query /
  * kv heads and of the FFN rows (row ranges of wq/wk/wv/w1/w3 in place, packed column ranges of wo/w2); each
- * forward sums the two partial projections per layer over NVLink (ncclAllReduce, in stream order inside the CUDA
- * graph) and every rank returns the full, identical logits.  Requires world | n_heads, n_kv_heads and 32*world |
- * hidden_dim; dense models; staged engine.  libnccl.so.2 is bound with dlopen on first use. */
+ * forward sums the two partial projections per layer over NVLink (inside the CUDA graph) and every rank returns the full, identical logits.  Requires world | n_heads, n_kv_heads and 32*world |
+ * hidden_dim; dense models; staged engine.  libnccl.so.2 is bound with dlopen on first use.
+ * calm_b200_tp_mode(): 0 = not tensor-parallel, 2 = the wo / w2 kernels sum their partials themselves through
+ * CUDA-IPC-mapped peer memory (one-shot push all-reduce inside k_matres; default), 1 = ncclAllReduce between
+ * kernels (peer mapping unavailable, or env CALM_B200_TP_FUSED=0). */
 void calm_b200_tp_unique_id(void* out128);
 void calm_b200_tp_init(int rank, int world, const void* id128);
 int calm_b200_tp_world(void);
+int calm_b200_tp_mode(void);
 
 /* The engine that serves the prepared model: 1 or 2 (one persistent kernel per token), or 0 when the staged
  * engine does (MoE, fp8 KV cache, unsupported shapes, or engine 0 requested). */

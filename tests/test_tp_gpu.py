@@ -22,15 +22,16 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("name", ["tiny-fp8", "tiny-gf4", "tiny-bias2", "tiny-lnpar", "tiny-mha"])
-def test_two_rank_logits_match_single_device_reference(tmp_path, name):
+@pytest.mark.parametrize("name,fused", [("tiny-fp8", 1), ("tiny-gf4", 1), ("tiny-bias2", 1), ("tiny-lnpar", 1), ("tiny-mha", 1), ("tiny-fp8", 0), ("tiny-bias2", 0)])
+def test_two_rank_logits_match_single_device_reference(tmp_path, name, fused):
+    """fused=1: partial sums exchanged inside k_matres over peer memory; fused=0: ncclAllReduce between kernels."""
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     spec = mg.SPECS[name]
     g = golden(name)
     out = str(tmp_path / "tp")
     idfile = str(tmp_path / "nccl.id")
-    env = dict(os.environ, PYTHONPATH=ROOT, CALM_B200_QUIET="1")
+    env = dict(os.environ, PYTHONPATH=ROOT, CALM_B200_QUIET="1", CALM_B200_TP_FUSED=str(fused))
     procs = [subprocess.Popen([sys.executable, "-m", "calm_b200.tp", "--spec", name, "--rank", str(r), "--world", "2", "--idfile", idfile,
                                "--tokens", str(len(g["tokens"])), "--out", out, "--greedy", "12"], cwd=ROOT, env=env,
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
@@ -46,6 +47,7 @@ def test_two_rank_logits_match_single_device_reference(tmp_path, name):
     assert all(p.returncode == 0 for p in procs), "\n".join(l[-1500:] for l in logs)
     r0, r1 = (np.load(f"{out}.rank{r}.npz") for r in range(2))
     assert int(r0["world"]) == 2
+    assert int(r0["mode"]) == int(r1["mode"]) == (2 if fused else 1), "peer-memory exchange not in use"
     assert np.array_equal(r0["logits"], r1["logits"])      # every rank holds the same full logits
     assert np.array_equal(r0["greedy"], r1["greedy"])      # so independent greedy sampling stays in lock step
     steps = list(g["steps"])
