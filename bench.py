@@ -317,6 +317,10 @@ def main():
         roof = {"bound": "hbm", "kernel": f"whole token on one of {world} tensor-parallel GPUs (staged kernels + 2 all-reduces per layer)",
                 "achieved": per_gpu / 1e9 / (ms / K / 1e3), "peak": peak, "unit": "GB/s", "frac": per_gpu / 1e9 / (ms / K / 1e3) / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu}
+        try:  # per-stage event timing of this rank's shard (eager launches; wo / w2 include the exchange wait)
+            roof["stages"] = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src, ms / K, bytes_per_tok)["stages"]
+        except Exception as e:
+            roof["stages"] = f"unavailable: {e}"
     else:
         roof = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src, ms / K, bytes_per_tok)
 
