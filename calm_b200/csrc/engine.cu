@@ -81,7 +81,7 @@ struct Engine {
 	void* tp_comm = nullptr;         // ncclComm_t
 	float* xpart = nullptr;          // partial of wo / w2 before the all-reduce (NCCL path)
 	bool tp_fused = false;           // wo / w2 sum their partials inside k_matres over peer memory (stages.cuh TpExchange)
-	void* tp_area = nullptr;         // this rank's exchange area: flags, then data
+	void* tp_area = nullptr;         // this rank's exchange area: {partial, epoch} cells
 	void* tp_peer[TP_MAX_WORLD] = {}; // every rank's area as mapped here (own entry == tp_area)
 	int* tp_err = nullptr;           // mapped host word for the exchange watchdog
 	std::vector<void*> tp_owned;     // shard copies made by prepare_cuda (wo / w2 column slices, packed biases)
@@ -211,8 +211,7 @@ void tp_allreduce(float* buf, size_t count) {
 // back to ncclAllReduce + k_addvec when peer mapping is unavailable on ANY rank (the ranks agree via an all-reduce).
 void tp_setup_exchange() {
 	const int W = g.tp_world, dim = g.cfg.dim;
-	const size_t flag_bytes = (size_t)TP_MAX_WORLD * TP_FLAG_CTAS * sizeof(int);
-	const size_t bytes = flag_bytes + (size_t)2 * W * dim * sizeof(float);
+	const size_t bytes = (size_t)2 * W * dim * sizeof(uint2); // cell[slot][src][row]
 	bool ok = W <= TP_MAX_WORLD && !(getenv("CALM_B200_TP_FUSED") && atoi(getenv("CALM_B200_TP_FUSED")) == 0);
 	g.tp_area = dev_alloc(bytes);
 	CUDA_CHECK(cudaMemset(g.tp_area, 0, bytes));
@@ -253,8 +252,7 @@ void tp_setup_exchange() {
 
 void tp_fill(TpExchange& t, int idx) {
 	t.world = g.tp_world, t.rank = g.tp_rank, t.idx = (unsigned)idx, t.stride = 2u * g.cfg.n_layers, t.tp = g.tp, t.err = g.tp_err;
-	const size_t flag_bytes = (size_t)TP_MAX_WORLD * TP_FLAG_CTAS * sizeof(int);
-	for (int p = 0; p < g.tp_world; ++p) t.flags[p] = (int*)g.tp_peer[p], t.data[p] = (float*)((char*)g.tp_peer[p] + flag_bytes);
+	for (int p = 0; p < g.tp_world; ++p) t.cell[p] = (uint2*)g.tp_peer[p];
 }
 
 // Launch on the library's stream with programmatic stream serialization (PDL), so that consecutive kernels
@@ -483,7 +481,7 @@ void make_plan() {
 	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_hidden));
 	if (g.tp_fused) { // the in-kernel exchange needs co-resident grids (they are: balanced_grid stays under the cap) within its tables
 		for (int grid : {g.grid_wo, g.grid_down})
-			if (grid > TP_FLAG_CTAS || cdiv(c.dim / 2, grid * 8) > TP_MAX_ITERS) CALM_FATAL("tensor parallelism: grid %d outside the exchange tables for dim %d", grid, c.dim);
+			if (cdiv(c.dim / 2, grid * 8) > TP_MAX_ITERS) CALM_FATAL("tensor parallelism: grid %d outside the exchange tables for dim %d", grid, c.dim);
 	}
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
 	g.grid_up = imin(max_ctas(k_ffn_up<DBITS>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));

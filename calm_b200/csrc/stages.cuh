@@ -628,34 +628,26 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tensor parallelism: matvec -> all-reduce in ONE kernel over NVLink peer memory (one-shot, push).
-// Every rank owns an exchange area that all peers map (cudaIpc): flags[src rank][cta] and data[slot][src rank][dim].
-// CTA b of rank r computes the partial of its rows, stores it into slot (epoch & 1) of EVERY rank's area (16-byte
-// peer stores), publishes `epoch` in every rank's flags[r][b], waits until its own flags[*][b] carry the epoch --
-// CTA b of every peer owns the same rows, the grids being equal -- and then adds the partials in rank order, so all
-// ranks end up with bit-identical residual vectors.  A CTA signals before it waits and the grid is co-resident, so
-// ranks cannot deadlock; two slots suffice because a rank reaches epoch e+2 only after every peer has signalled
-// e+1, i.e. has finished the whole epoch-e kernel.  Costs one NVLink store latency instead of an NCCL kernel
-// plus a separate add kernel per projection.
+// Tensor parallelism: matvec -> all-reduce in ONE kernel over NVLink peer memory (one-shot push, flag-in-data).
+// Every rank owns an exchange area that all peers map (cudaIpc): cell[slot][src rank][row] = {partial, epoch}, 8 bytes.
+// CTA b of rank r computes the partial of its rows and stores {value, epoch} cells into slot (epoch & 1) of every
+// PEER's area -- one 128-byte line per 16 rows, each cell a single 8-byte store, so a reader that sees the epoch
+// sees the value: no fence, no separate flag, one NVLink one-way latency.  It then polls its own area for the cells
+// CTA b of every peer pushes (same rows: the grids are equal) and adds the partials in rank order, so all ranks end
+// up with bit-identical residual vectors.  A CTA pushes before it polls and the grid is co-resident, so ranks cannot
+// deadlock; two slots suffice because a rank reaches epoch e+2 only after it has consumed every peer's cells of
+// e+1, i.e. after every peer has finished its whole epoch-e kernel.  Replaces an NCCL kernel + an add kernel.
 
 #define TP_MAX_WORLD 8
-#define TP_FLAG_CTAS 2048
 #define TP_MAX_ITERS 16
 
 struct TpExchange {
 	int world, rank;
-	unsigned idx, stride;      // epoch = tp_seq * stride + idx
+	unsigned idx, stride;      // epoch = tp_seq * stride + idx  (> 0; the areas start zeroed)
 	const TokenParams* tp;
-	int* flags[TP_MAX_WORLD];  // rank p's flags  [TP_MAX_WORLD][TP_FLAG_CTAS]
-	float* data[TP_MAX_WORLD]; // rank p's data   [2][world][d]
+	uint2* cell[TP_MAX_WORLD]; // rank p's area  [2][world][d]
 	int* err;                  // mapped host word: watchdog code
 };
-
-__device__ __forceinline__ unsigned ld_acquire_sys(const int* p) {
-	unsigned v;
-	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
 
 // part[it * 16 + k]: row 2 * ((it * gridDim.x + blockIdx.x) * 8) + k of this rank's partial.  All 256 threads call.
 __device__ __forceinline__ void tp_exchange_add(const TpExchange& t, const float* part, int niter, float* y, int d) {
@@ -663,45 +655,46 @@ __device__ __forceinline__ void tp_exchange_add(const TpExchange& t, const float
 	const int slot = epoch & 1;
 	const int W = t.world;
 	__syncthreads(); // part[] complete
-	const int pieces = niter * 4; // float4 pieces of this CTA per destination
-	for (int i = threadIdx.x; i < pieces * W; i += blockDim.x) {
-		const int peer = i / pieces, j = i - peer * pieces, it = j >> 2, q = j & 3;
-		const int row0 = 2 * ((it * gridDim.x + blockIdx.x) * 8) + q * 4;
-		if (row0 < d) {
-			float4 v = *reinterpret_cast<const float4*>(part + it * 16 + q * 4);
-			*reinterpret_cast<float4*>(t.data[peer] + ((size_t)slot * W + t.rank) * d + row0) = v;
+	const int cells = niter * 16;
+	for (int i = threadIdx.x; i < cells * (W - 1); i += blockDim.x) {
+		int peer = i / cells;
+		const int j = i - peer * cells;
+		peer += peer >= t.rank; // skip self
+		const int row = 2 * (((j >> 4) * gridDim.x + blockIdx.x) * 8) + (j & 15);
+		if (row < d) {
+			uint2* dst = t.cell[peer] + ((size_t)slot * W + t.rank) * d + row;
+			asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(part[j])), "r"(epoch) : "memory");
 		}
 	}
-	__syncthreads();
-	if (threadIdx.x < W) {
-		__threadfence_system(); // the CTA's peer stores (ordered before this thread by the barrier) precede the flag
-		*reinterpret_cast<volatile int*>(t.flags[threadIdx.x] + t.rank * TP_FLAG_CTAS + blockIdx.x) = (int)epoch;
-		const int* mine = t.flags[t.rank] + threadIdx.x * TP_FLAG_CTAS + blockIdx.x;
-		unsigned long long t0 = 0;
-		unsigned spins = 0;
-		while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-			if ((++spins & 1023) == 0) {
-				unsigned long long now;
-				asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-				if (!t0) t0 = now;
-				if (now - t0 > 20000000000ull) { // 20 s: a peer died or the ranks diverged -- fail loudly, never hang the GPU
-					if (t.err) *reinterpret_cast<volatile int*>(t.err) = 9000 + threadIdx.x;
-					__threadfence_system();
-					__trap();
+	for (int j = threadIdx.x; j < cells; j += blockDim.x) {
+		const int row = 2 * (((j >> 4) * gridDim.x + blockIdx.x) * 8) + (j & 15);
+		if (row >= d) continue;
+		const uint2* base = t.cell[t.rank] + (size_t)slot * W * d + row;
+		float sum = 0.f;
+		for (int p = 0; p < W; ++p) { // rank order: identical on every rank
+			if (p == t.rank) {
+				sum += part[j];
+				continue;
+			}
+			unsigned vx, vy, spins = 0;
+			unsigned long long t0 = 0;
+			for (;;) {
+				asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "l"(base + (size_t)p * d) : "memory");
+				if (vy == epoch) break;
+				if ((++spins & 1023) == 0) {
+					unsigned long long now;
+					asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+					if (!t0) t0 = now;
+					if (now - t0 > 20000000000ull) { // 20 s: a peer died or the ranks diverged -- fail loudly, never hang the GPU
+						if (t.err) *reinterpret_cast<volatile int*>(t.err) = 9000 + p;
+						__threadfence_system();
+						__trap();
+					}
 				}
 			}
+			sum += __uint_as_float(vx);
 		}
-	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < niter * 16; i += blockDim.x) {
-		const int it = i >> 4, k = i & 15;
-		const int row = 2 * ((it * gridDim.x + blockIdx.x) * 8) + k;
-		if (row < d) {
-			const float* base = t.data[t.rank] + (size_t)slot * W * d + row;
-			float sum = 0.f;
-			for (int p = 0; p < W; ++p) sum += __ldcg(base + (size_t)p * d); // rank order: identical on every rank
-			y[row] += sum;
-		}
+		y[row] += sum;
 	}
 }
 
