@@ -49,6 +49,21 @@ __device__ __forceinline__ void pdl_enter() {
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The two halves, for kernels that request their first weight vectors (immutable data, independent of the previous
+// grid) between them: the loads are in flight while the previous kernel drains and while the activations are staged.
+__device__ __forceinline__ void pdl_launch_next() {
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prev() {
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// L2 prefetch of a contiguous range (<= 16 KB, multiple of 16), issued by one thread; fire-and-forget (SASS UBLKPF)
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_row(const void* row, int rowbytes) {
+	for (int off = 0; off < rowbytes; off += 16384) l2_prefetch((const char*)row + off, (uint32_t)min(16384, rowbytes - off));
+}
 
 // ---------------------------------------------------------------- warp / block reductions
 

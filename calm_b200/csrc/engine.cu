@@ -96,6 +96,7 @@ struct Engine {
 	int graph_launches[4] = {0, 0, 0, 0};
 	bool use_graph = true;
 	bool use_pdl = true;
+	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 register loads
 
 	// profiling (perf_cuda)
 	bool perf = false;
@@ -320,7 +321,7 @@ void dispatch_attn(const AttnArgs& a, int nunits, int* nl) {
 }
 
 // mode: 0 kv only, 1 logits -> host, 2 logits -> device + advance (greedy loop), 3 logits -> host + argmax
-template <int DBITS, typename KVT>
+template <int DBITS, typename KVT, int EARLY>
 int run_token(int mode) {
 	const Config& c = g.cfg;
 	const Weights& w = g.w;
@@ -350,7 +351,7 @@ int run_token(int mode) {
 			a.rope_freq = g.rope_freq, a.xb_out = c.norm_par ? g.xb : nullptr, a.tp = g.tp;
 			a.dim = dim, a.q_dim = g.q_dim, a.kv_dim = g.kv_dim, a.head_dim = hd, a.seq_len = c.seq_len;
 			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln;
-			launch_pdl(k_qkv<DBITS, KVT>, g.grid_qkv, 256, g.smem_dim, a);
+			launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -369,7 +370,7 @@ int run_token(int mode) {
 			a.xin = g.att, a.w = w.wo[l], a.y = g.x, a.sel = nullptr, a.n = g.q_dim, a.d = dim, a.nact = 1, a.accumulate = 1;
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l); // partial over this rank's heads, summed over the ranks in the kernel
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			launch_pdl(k_matres<DBITS>, g.grid_wo, 256, g.smem_qdim, a);
+			launch_pdl(k_matres<DBITS, EARLY>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
@@ -384,7 +385,7 @@ int run_token(int mode) {
 			a.gate = c.n_experts ? w.moegate[l] : nullptr, a.w1 = w.w1[l], a.w3 = w.w3[l], a.hb = g.hb, a.sel = g.moe_sel;
 			a.dim = dim, a.hidden = hidden, a.n_experts = c.n_experts, a.nact = g.nact;
 			a.eps = c.norm_eps, a.ln = c.norm_ln, a.gelu = c.act_gelu;
-			launch_pdl(k_ffn_up<DBITS>, g.grid_up, 256, g.smem_dim, a);
+			launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -394,7 +395,7 @@ int run_token(int mode) {
 			a.n = hidden, a.d = dim, a.nact = g.nact, a.accumulate = 1;
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			launch_pdl(k_matres<DBITS>, g.grid_down, 256, g.smem_hidden, a);
+			launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
@@ -467,7 +468,7 @@ void tp_shard_model() {
 }
 
 // Fix grid sizes and shared-memory opt-ins for this model (called once from prepare_cuda).
-template <int DBITS, typename KVT>
+template <int DBITS, typename KVT, int EARLY>
 void make_plan() {
 	const Config& c = g.cfg;
 	g.smem_dim = xs_bytes<DBITS>(c.dim);
@@ -475,31 +476,36 @@ void make_plan() {
 	g.smem_hidden = xs_bytes<DBITS>(c.hidden_dim);
 	size_t smem_res = g.smem_qdim > g.smem_hidden ? g.smem_qdim : g.smem_hidden;
 	if (smem_res > 227 * 1024 || g.smem_dim > 227 * 1024) CALM_FATAL("activation vector does not fit in shared memory (dim %d, hidden %d)", c.dim, c.hidden_dim);
-	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT>, 256, g.smem_dim));
-	max_ctas(k_matres<DBITS>, 256, smem_res); // opt in to the larger of the two sizes
-	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_qdim));
-	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_hidden));
+	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT, EARLY>, 256, g.smem_dim));
+	max_ctas(k_matres<DBITS, EARLY>, 256, smem_res); // opt in to the larger of the two sizes
+	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_qdim));
+	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_hidden));
 	if (g.tp_fused) { // the in-kernel exchange needs co-resident grids (they are: balanced_grid stays under the cap) within its tables
 		for (int grid : {g.grid_wo, g.grid_down})
 			if (cdiv(c.dim / 2, grid * 8) > TP_MAX_ITERS) CALM_FATAL("tensor parallelism: grid %d outside the exchange tables for dim %d", grid, c.dim);
 	}
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
-	g.grid_up = imin(max_ctas(k_ffn_up<DBITS>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
+	g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
 	g.grid_out = balanced_grid(cdiv(c.vocab_size, 32), max_ctas(k_output<DBITS>, 256, g.smem_dim));
 	g.ncand = g.grid_out;
 }
 
 template <int DBITS>
 void make_plan_kv() {
-	if (g.kvbits == 8)
-		make_plan<DBITS, uint8_t>();
-	else
-		make_plan<DBITS, __half>();
+	switch (g.early) {
+	case 1: g.kvbits == 8 ? make_plan<DBITS, uint8_t, 1>() : make_plan<DBITS, __half, 1>(); break;
+	case 2: g.kvbits == 8 ? make_plan<DBITS, uint8_t, 2>() : make_plan<DBITS, __half, 2>(); break;
+	default: g.kvbits == 8 ? make_plan<DBITS, uint8_t, 0>() : make_plan<DBITS, __half, 0>(); break;
+	}
 }
 
 template <int DBITS>
 int run_token_kv(int mode) {
-	return g.kvbits == 8 ? run_token<DBITS, uint8_t>(mode) : run_token<DBITS, __half>(mode);
+	switch (g.early) {
+	case 1: return g.kvbits == 8 ? run_token<DBITS, uint8_t, 1>(mode) : run_token<DBITS, __half, 1>(mode);
+	case 2: return g.kvbits == 8 ? run_token<DBITS, uint8_t, 2>(mode) : run_token<DBITS, __half, 2>(mode);
+	default: return g.kvbits == 8 ? run_token<DBITS, uint8_t, 0>(mode) : run_token<DBITS, __half, 0>(mode);
+	}
 }
 
 int run_token_any(int mode) {
@@ -895,6 +901,8 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.q_dim = q_dim, g.kv_dim = kv_dim, g.kv_mul = g.cfg.n_heads / g.cfg.n_kv_heads;
 	g.use_graph = !(getenv("CALM_B200_GRAPH") && atoi(getenv("CALM_B200_GRAPH")) == 0);
 	g.use_pdl = !(getenv("CALM_B200_PDL") && atoi(getenv("CALM_B200_PDL")) == 0);
+	if (getenv("CALM_B200_EARLY")) g.early = atoi(getenv("CALM_B200_EARLY"));
+	if (g.early < 0 || g.early > 2) g.early = 0;
 	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
 	if (g.debug) g.use_graph = false, g.debug_stages = true;
 	g.perf = (getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF"))) || getenv("CUDA_INJECTION64_PATH");

@@ -98,10 +98,6 @@ __device__ __forceinline__ void batch_consume(const RowBatch<DBITS>& b, int nvec
 	}
 }
 
-// L2 prefetch of a contiguous range (<= 16 KB pieces), issued by one thread
-__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
-	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 // one lane: ask the L2 for the head of two rows (pieces of <= 16 KB)
 __device__ __forceinline__ void prefetch_pair(const void* r0, const void* r1, int rowbytes) {
 	for (int off = 0; off < rowbytes; off += 16384) {

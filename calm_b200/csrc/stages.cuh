@@ -23,16 +23,57 @@ struct MoeSel { // router decision of the current layer, written by k_ffn_up, re
 // Each lane owns every 32nd 16-byte vector of a row; U vectors per row are requested before the
 // first is consumed, so a warp keeps R*U*512 bytes in flight.
 
-template <int DBITS, int R, int U = 4>
-__device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int nvec, const float4* __restrict__ xs4, float (&out)[R]) {
+// First batch of a warp's rows, requested ahead of time (see pdl_launch_next): U vectors of each of R rows per lane.
+template <int R, int U>
+struct RowHead {
+	uint4 w[U][R];
+};
+
+template <int R, int U>
+__device__ __forceinline__ void rows_request(const uint4* const (&rp)[R], int nvec, RowHead<R, U>& h) {
+	const int lane = threadIdx.x & 31;
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		int v = lane + 32 * u;
+#pragma unroll
+		for (int r = 0; r < R; ++r) h.w[u][r] = v < nvec ? ldg_stream(rp[r] + v) : make_uint4(0, 0, 0, 0);
+	}
+}
+
+template <int DBITS, int R, int U>
+__device__ __forceinline__ void rows_consume(const uint4 (&w)[U][R], int v0, int nvec, const float4* __restrict__ xs4, float (&acc)[R]) {
 	constexpr int Q = WFmt<DBITS>::VW / 4;
+	const int lane = threadIdx.x & 31;
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		int v = v0 + 32 * u;
+		if (v < nvec) {
+			float4 xv[Q];
+			const float4* xp = xs4 + (size_t)(v >> 5) * Q * 32 + lane;
+#pragma unroll
+			for (int q = 0; q < Q; ++q) xv[q] = xp[q * 32];
+#pragma unroll
+			for (int r = 0; r < R; ++r) acc[r] = dot_vec<DBITS>(w[u][r], xv, acc[r]);
+		}
+	}
+}
+
+// `head`: the vectors rows_request() already fetched for these rows, or NULL.
+template <int DBITS, int R, int U = 4, int HU = U>
+__device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int nvec, const float4* __restrict__ xs4, float (&out)[R],
+                                              const RowHead<R, HU>* head = nullptr) {
 	const int lane = threadIdx.x & 31;
 
 	float acc[R];
 #pragma unroll
 	for (int r = 0; r < R; ++r) acc[r] = 0.f;
 
-	for (int v0 = lane; v0 < nvec; v0 += 32 * U) {
+	int v0 = lane;
+	if (head) {
+		rows_consume<DBITS, R, HU>(head->w, v0, nvec, xs4, acc);
+		v0 += 32 * HU;
+	}
+	for (; v0 < nvec; v0 += 32 * U) {
 		uint4 w[U][R];
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
@@ -40,18 +81,7 @@ __device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int n
 #pragma unroll
 			for (int r = 0; r < R; ++r) w[u][r] = v < nvec ? ldg_stream(rp[r] + v) : make_uint4(0, 0, 0, 0);
 		}
-#pragma unroll
-		for (int u = 0; u < U; ++u) {
-			int v = v0 + 32 * u;
-			if (v < nvec) {
-				float4 xv[Q];
-				const float4* xp = xs4 + (size_t)(v >> 5) * Q * 32 + lane;
-#pragma unroll
-				for (int q = 0; q < Q; ++q) xv[q] = xp[q * 32];
-#pragma unroll
-				for (int r = 0; r < R; ++r) acc[r] = dot_vec<DBITS>(w[u][r], xv, acc[r]);
-			}
-		}
+		rows_consume<DBITS, R, U>(w, v0, nvec, xs4, acc);
 	}
 #pragma unroll
 	for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
@@ -221,24 +251,22 @@ struct QkvArgs {
 	int ln;
 };
 
-template <int DBITS, typename KVT>
-__global__ void __launch_bounds__(256) k_qkv(const QkvArgs<KVT> a) {
-	pdl_enter();
+// EARLY: what a warp does about its first row pair BEFORE waiting for the previous kernel and staging the activations
+// (weights are immutable, so this is always legal): 0 nothing, 1 ask the L2 for the rows (no registers), 2 issue the
+// first loads into registers.
+template <int DBITS, typename KVT, int EARLY>
+__global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_qkv(const QkvArgs<KVT> a) {
+	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	float* red = smem;
 	float* xs = smem + 32;
-	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, blockIdx.x == 0 ? a.xb_out : nullptr);
-
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	const int nvec = a.dim / WFmt<DBITS>::VW;
 	const size_t rowvecs = (size_t)nvec; // 16-byte vectors per row
 	const int npairs = (a.q_dim + 2 * a.kv_dim) / 2;
-	const int pos = a.tp->pos, kv_pos = a.tp->kv_pos;
-
-	for (int p = blockIdx.x * nwarps + warp; p < npairs; p += gridDim.x * nwarps) {
-		int j = 2 * p; // row in the concatenated [wq; wk; wv]
+	auto rows_of = [&](int p, const uint4* (&rp)[2], int& j, int& k) {
+		j = 2 * p; // row in the concatenated [wq; wk; wv]
 		const void* w;
-		int k;
 		if (j < a.q_dim) {
 			w = a.wq, k = j;
 		} else if (j < a.q_dim + a.kv_dim) {
@@ -246,9 +274,32 @@ __global__ void __launch_bounds__(256) k_qkv(const QkvArgs<KVT> a) {
 		} else {
 			w = a.wv, k = j - a.q_dim - a.kv_dim;
 		}
-		const uint4* rp[2] = {reinterpret_cast<const uint4*>(w) + (size_t)k * rowvecs, reinterpret_cast<const uint4*>(w) + (size_t)(k + 1) * rowvecs};
+		rp[0] = reinterpret_cast<const uint4*>(w) + (size_t)k * rowvecs, rp[1] = rp[0] + rowvecs;
+	};
+	// weights first: they do not depend on the previous kernel, so their latency hides its tail and the staging of x
+	const int p0 = blockIdx.x * nwarps + warp;
+	RowHead<2, 4> head;
+	if (EARLY != 0 && p0 < npairs) {
+		const uint4* rp[2];
+		int j, k;
+		rows_of(p0, rp, j, k);
+		if constexpr (EARLY == 2) rows_request<2, 4>(rp, nvec, head);
+		if constexpr (EARLY == 1)
+			if (lane == 0) l2_prefetch_row(rp[0], nvec * 16), l2_prefetch_row(rp[1], nvec * 16);
+	}
+	pdl_wait_prev();
+	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, blockIdx.x == 0 ? a.xb_out : nullptr);
+	const int pos = a.tp->pos, kv_pos = a.tp->kv_pos;
+
+	for (int p = p0; p < npairs; p += gridDim.x * nwarps) {
+		const uint4* rp[2];
+		int j, k;
+		rows_of(p, rp, j, k);
 		float v[2];
-		warp_dot_rows<DBITS, 2>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
+		if (EARLY == 2 && p == p0)
+			warp_dot_rows<DBITS, 2, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v, &head);
+		else
+			warp_dot_rows<DBITS, 2, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
 
 		if (lane == 0) {
 			float v0 = v[0], v1 = v[1];
@@ -713,9 +764,9 @@ struct MatResArgs {
 	TpExchange tpx;   // world > 1: the partial is summed over the tensor-parallel ranks inside this kernel
 };
 
-template <int DBITS>
-__global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
-	pdl_enter();
+template <int DBITS, int EARLY>
+__global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
+	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	__shared__ __align__(16) float tp_part[TP_MAX_ITERS * 16];
 	float* red = smem;
@@ -723,6 +774,18 @@ __global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	const int nvec = a.n / WFmt<DBITS>::VW;
 	const size_t esize = (size_t)a.d * nvec; // 16-byte vectors per expert
+	const bool long_rows = nvec > 32 * 8 && DBITS != 4; // w2: a warp has one pair and is latency-bound; keep twice the loads in flight
+	// dense models: request the first row pair before waiting for the previous kernel (the expert of a MoE layer is its result)
+	const int p0 = blockIdx.x * nwarps + warp;
+	const bool early = EARLY != 0 && a.sel == nullptr && p0 < a.d / 2;
+	RowHead<2, 4> head4; // (half a batch of the long rows: the other half would spill at 2 CTAs per SM)
+	if (early) {
+		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w) + (size_t)(2 * p0) * nvec, reinterpret_cast<const uint4*>(a.w) + (size_t)(2 * p0 + 1) * nvec};
+		if constexpr (EARLY == 2) rows_request<2, 4>(rp, nvec, head4);
+		if constexpr (EARLY == 1)
+			if (lane == 0) l2_prefetch_row(rp[0], nvec * 16), l2_prefetch_row(rp[1], nvec * 16);
+	}
+	pdl_wait_prev();
 
 	for (int e = 0; e < a.nact; ++e) {
 		if (e > 0) __syncthreads();
@@ -734,10 +797,19 @@ __global__ void __launch_bounds__(256) k_matres(const MatResArgs a) {
 		for (int p = blockIdx.x * nwarps + warp; p < a.d / 2; p += gridDim.x * nwarps, ++it) {
 			const uint4* rp[2] = {wb + (size_t)(2 * p) * nvec, wb + (size_t)(2 * p + 1) * nvec};
 			float v[2];
-			if (nvec > 32 * 8 && DBITS != 4) // long rows (w2): a warp has one pair and is latency-bound; keep twice the loads in flight
-				warp_dot_rows<DBITS, 2, 8>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
-			else
-				warp_dot_rows<DBITS, 2>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
+			const bool pre = EARLY == 2 && early && p == p0;
+			const float4* xs4 = reinterpret_cast<const float4*>(xs);
+			if (long_rows) {
+				if (pre)
+					warp_dot_rows<DBITS, 2, 8, 4>(rp, nvec, xs4, v, &head4);
+				else
+					warp_dot_rows<DBITS, 2, 8>(rp, nvec, xs4, v);
+			} else {
+				if (pre)
+					warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v, &head4);
+				else
+					warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
+			}
 			if (lane == 0) {
 				if (a.tpx.world > 1) { // this rank's partial: summed over the ranks below
 					tp_part[it * 16 + warp * 2] = v[0], tp_part[it * 16 + warp * 2 + 1] = v[1];
@@ -775,19 +847,29 @@ struct FfnUpArgs {
 	int ln, gelu;
 };
 
-template <int DBITS>
-__global__ void __launch_bounds__(256) k_ffn_up(const FfnUpArgs a) {
-	pdl_enter();
+template <int DBITS, int EARLY>
+__global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpArgs a) {
+	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	__shared__ float glog[64];
 	__shared__ MoeSel ssel;
 	float* red = smem;
 	float* xs = smem + 32;
-	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
-
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	const int nvec = a.dim / WFmt<DBITS>::VW;
 	const float4* xs4 = reinterpret_cast<const float4*>(xs);
+	// dense models: the first (w1, w3) row pair is requested before the previous kernel has finished and x is staged
+	const int p0 = blockIdx.x * nwarps + warp;
+	const bool early = EARLY != 0 && a.n_experts == 0 && p0 < a.hidden;
+	RowHead<2, 4> head;
+	if (early) {
+		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w1) + (size_t)p0 * nvec, reinterpret_cast<const uint4*>(a.w3) + (size_t)p0 * nvec};
+		if constexpr (EARLY == 2) rows_request<2, 4>(rp, nvec, head);
+		if constexpr (EARLY == 1)
+			if (lane == 0) l2_prefetch_row(rp[0], nvec * 16), l2_prefetch_row(rp[1], nvec * 16);
+	}
+	pdl_wait_prev();
+	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
 
 	if (a.n_experts) {
 		for (int e = warp; e < a.n_experts; e += nwarps) {
@@ -824,7 +906,10 @@ __global__ void __launch_bounds__(256) k_ffn_up(const FfnUpArgs a) {
 		size_t off = (a.n_experts ? (size_t)ssel.expert[e] * esize : 0) + (size_t)i * nvec;
 		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w1) + off, reinterpret_cast<const uint4*>(a.w3) + off};
 		float v[2];
-		warp_dot_rows<DBITS, 2>(rp, nvec, xs4, v);
+		if (EARLY == 2 && early && p == p0)
+			warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v, &head);
+		else
+			warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
 		if (lane == 0) a.hb[p] = (a.gelu ? act_gelu(v[0]) : act_silu(v[0])) * v[1];
 	}
 }
