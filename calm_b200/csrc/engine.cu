@@ -96,7 +96,7 @@ struct Engine {
 	int graph_launches[4] = {0, 0, 0, 0};
 	bool use_graph = true;
 	bool use_pdl = true;
-	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 register loads
+	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + 64-register k_ffn_up
 
 	// profiling (perf_cuda)
 	bool perf = false;

@@ -23,31 +23,14 @@ struct MoeSel { // router decision of the current layer, written by k_ffn_up, re
 // Each lane owns every 32nd 16-byte vector of a row; U vectors per row are requested before the
 // first is consumed, so a warp keeps R*U*512 bytes in flight.
 
-// First batch of a warp's rows, requested ahead of time (see pdl_launch_next): U vectors of each of R rows per lane.
-template <int R, int U>
-struct RowHead {
-	uint4 w[U][R];
-};
-
-template <int R, int U>
-__device__ __forceinline__ void rows_request(const uint4* const (&rp)[R], int nvec, RowHead<R, U>& h) {
-	const int lane = threadIdx.x & 31;
-#pragma unroll
-	for (int u = 0; u < U; ++u) {
-		int v = lane + 32 * u;
-#pragma unroll
-		for (int r = 0; r < R; ++r) h.w[u][r] = v < nvec ? ldg_stream(rp[r] + v) : make_uint4(0, 0, 0, 0);
-	}
-}
-
-template <int DBITS, int R, int U>
+template <int DBITS, int R, int U, bool CHECK = true>
 __device__ __forceinline__ void rows_consume(const uint4 (&w)[U][R], int v0, int nvec, const float4* __restrict__ xs4, float (&acc)[R]) {
 	constexpr int Q = WFmt<DBITS>::VW / 4;
 	const int lane = threadIdx.x & 31;
 #pragma unroll
 	for (int u = 0; u < U; ++u) {
 		int v = v0 + 32 * u;
-		if (v < nvec) {
+		if (!CHECK || v < nvec) {
 			float4 xv[Q];
 			const float4* xp = xs4 + (size_t)(v >> 5) * Q * 32 + lane;
 #pragma unroll
@@ -58,33 +41,93 @@ __device__ __forceinline__ void rows_consume(const uint4 (&w)[U][R], int v0, int
 	}
 }
 
-// `head`: the vectors rows_request() already fetched for these rows, or NULL.
-template <int DBITS, int R, int U = 4, int HU = U>
-__device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int nvec, const float4* __restrict__ xs4, float (&out)[R],
-                                              const RowHead<R, HU>* head = nullptr) {
+template <int DBITS, int R, int U = 4>
+__device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int nvec, const float4* __restrict__ xs4, float (&out)[R]) {
 	const int lane = threadIdx.x & 31;
 
 	float acc[R];
 #pragma unroll
 	for (int r = 0; r < R; ++r) acc[r] = 0.f;
 
-	int v0 = lane;
-	if (head) {
-		rows_consume<DBITS, R, HU>(head->w, v0, nvec, xs4, acc);
-		v0 += 32 * HU;
-	}
-	for (; v0 < nvec; v0 += 32 * U) {
-		uint4 w[U][R];
+	if (nvec % (32 * U) == 0) { // whole batches (every production shape): no bounds predicates in the hot loop
+		for (int v0 = lane; v0 < nvec; v0 += 32 * U) {
+			uint4 w[U][R];
 #pragma unroll
-		for (int u = 0; u < U; ++u) {
-			int v = v0 + 32 * u;
+			for (int u = 0; u < U; ++u)
 #pragma unroll
-			for (int r = 0; r < R; ++r) w[u][r] = v < nvec ? ldg_stream(rp[r] + v) : make_uint4(0, 0, 0, 0);
+				for (int r = 0; r < R; ++r) w[u][r] = ldg_stream(rp[r] + v0 + 32 * u);
+			rows_consume<DBITS, R, U, false>(w, v0, nvec, xs4, acc);
 		}
-		rows_consume<DBITS, R, U>(w, v0, nvec, xs4, acc);
+	} else {
+		for (int v0 = lane; v0 < nvec; v0 += 32 * U) {
+			uint4 w[U][R];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				int v = v0 + 32 * u;
+#pragma unroll
+				for (int r = 0; r < R; ++r) w[u][r] = v < nvec ? ldg_stream(rp[r] + v) : make_uint4(0, 0, 0, 0);
+			}
+			rows_consume<DBITS, R, U>(w, v0, nvec, xs4, acc);
+		}
 	}
 #pragma unroll
 	for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
+}
+
+// (batched body of stage_vector below: every thread owns up to SV_MAX 16-byte pieces)
+template <int DBITS, int SV_MAX>
+__device__ __forceinline__ void stage_vector_batched(float* xs, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln,
+                                                     float* xb_out) {
+	const int tid = threadIdx.x, nthr = blockDim.x;
+	const int n4 = n >> 2;
+	const int total4 = xs_floats<DBITS>(n) >> 2;
+	const float4* x4 = reinterpret_cast<const float4*>(x);
+	float4 v[SV_MAX];
+#pragma unroll
+	for (int k = 0; k < SV_MAX; ++k) {
+		int i = tid + k * nthr;
+		v[k] = i < n4 ? __ldcg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	if (normw) {
+		float4 w[SV_MAX];
+#pragma unroll
+		for (int k = 0; k < SV_MAX; ++k) {
+			int i = tid + k * nthr;
+			w[k] = i < n4 ? __ldg(reinterpret_cast<const float4*>(normw) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		float mean = 0.f;
+		if (ln) {
+			float s = 0.f;
+#pragma unroll
+			for (int k = 0; k < SV_MAX; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+			mean = block_sum(s, red) / n;
+		}
+		float ss = 0.f;
+#pragma unroll
+		for (int k = 0; k < SV_MAX; ++k) {
+			if (tid + k * nthr < n4) {
+				float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+				ss = fmaf(dx, dx, ss), ss = fmaf(dy, dy, ss), ss = fmaf(dz, dz, ss), ss = fmaf(dw, dw, ss);
+			}
+		}
+		ss = block_sum(ss, red);
+		const float scale = 1.0f / sqrtf(ss / n + eps);
+#pragma unroll
+		for (int k = 0; k < SV_MAX; ++k) {
+			v[k].x = (v[k].x - mean) * scale * w[k].x, v[k].y = (v[k].y - mean) * scale * w[k].y;
+			v[k].z = (v[k].z - mean) * scale * w[k].z, v[k].w = (v[k].w - mean) * scale * w[k].w;
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < SV_MAX; ++k) {
+		int i = tid + k * nthr;
+		if (i < n4) {
+			if (xb_out) reinterpret_cast<float4*>(xb_out)[i] = v[k];
+			*reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = v[k]; // 4 consecutive elements stay consecutive
+		}
+	}
+	for (int i = n4 + tid; i < total4; i += nthr) *reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = make_float4(0.f, 0.f, 0.f, 0.f);
+	__syncthreads();
 }
 
 // Stage an activation vector into shared memory in the permuted layout of common.cuh, optionally
@@ -100,53 +143,12 @@ __device__ __forceinline__ void stage_vector(float* xs, float* red, const float*
 	const int n4 = n >> 2; // n is a multiple of 32
 	const int total4 = xs_floats<DBITS>(n) >> 2;
 	const float4* x4 = reinterpret_cast<const float4*>(x);
+	if (SV_MAX > 4 && n4 <= nthr * 4) { // the common case (dim 4096, 256 threads): half the registers
+		stage_vector_batched<DBITS, 4>(xs, red, x, n, normw, eps, ln, xb_out);
+		return;
+	}
 	if (n4 <= nthr * SV_MAX) {
-		float4 v[SV_MAX];
-#pragma unroll
-		for (int k = 0; k < SV_MAX; ++k) {
-			int i = tid + k * nthr;
-			v[k] = i < n4 ? __ldcg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-		}
-		if (normw) {
-			float4 w[SV_MAX];
-#pragma unroll
-			for (int k = 0; k < SV_MAX; ++k) {
-				int i = tid + k * nthr;
-				w[k] = i < n4 ? __ldg(reinterpret_cast<const float4*>(normw) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-			}
-			float mean = 0.f;
-			if (ln) {
-				float s = 0.f;
-#pragma unroll
-				for (int k = 0; k < SV_MAX; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-				mean = block_sum(s, red) / n;
-			}
-			float ss = 0.f;
-#pragma unroll
-			for (int k = 0; k < SV_MAX; ++k) {
-				if (tid + k * nthr < n4) {
-					float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
-					ss = fmaf(dx, dx, ss), ss = fmaf(dy, dy, ss), ss = fmaf(dz, dz, ss), ss = fmaf(dw, dw, ss);
-				}
-			}
-			ss = block_sum(ss, red);
-			const float scale = 1.0f / sqrtf(ss / n + eps);
-#pragma unroll
-			for (int k = 0; k < SV_MAX; ++k) {
-				v[k].x = (v[k].x - mean) * scale * w[k].x, v[k].y = (v[k].y - mean) * scale * w[k].y;
-				v[k].z = (v[k].z - mean) * scale * w[k].z, v[k].w = (v[k].w - mean) * scale * w[k].w;
-			}
-		}
-#pragma unroll
-		for (int k = 0; k < SV_MAX; ++k) {
-			int i = tid + k * nthr;
-			if (i < n4) {
-				if (xb_out) reinterpret_cast<float4*>(xb_out)[i] = v[k];
-				*reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = v[k]; // 4 consecutive elements stay consecutive
-			}
-		}
-		for (int i = n4 + tid; i < total4; i += nthr) *reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = make_float4(0.f, 0.f, 0.f, 0.f);
-		__syncthreads();
+		stage_vector_batched<DBITS, SV_MAX>(xs, red, x, n, normw, eps, ln, xb_out);
 		return;
 	}
 	// long vectors: same thing, element by element (two reads of x when normalising)
@@ -252,10 +254,12 @@ struct QkvArgs {
 };
 
 // EARLY: what a warp does about its first row pair BEFORE waiting for the previous kernel and staging the activations
-// (weights are immutable, so this is always legal): 0 nothing, 1 ask the L2 for the rows (no registers), 2 issue the
-// first loads into registers.
+// (weights are immutable, so this is always legal): 0 nothing; 1 ask the L2 for the rows (cp.async.bulk.prefetch.L2,
+// no registers); 2 the same, and k_ffn_up is compiled for 4 CTAs per SM (64 registers) instead of 3.
+// (Issuing the first loads into registers instead was measured 25 % slower: 32 more live registers across the
+// staging cost a CTA per SM or spills.)
 template <int DBITS, typename KVT, int EARLY>
-__global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_qkv(const QkvArgs<KVT> a) {
+__global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	float* red = smem;
@@ -278,14 +282,11 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_qkv(const QkvArgs<K
 	};
 	// weights first: they do not depend on the previous kernel, so their latency hides its tail and the staging of x
 	const int p0 = blockIdx.x * nwarps + warp;
-	RowHead<2, 4> head;
-	if (EARLY != 0 && p0 < npairs) {
+	if (EARLY != 0 && p0 < npairs && lane == 0) {
 		const uint4* rp[2];
 		int j, k;
 		rows_of(p0, rp, j, k);
-		if constexpr (EARLY == 2) rows_request<2, 4>(rp, nvec, head);
-		if constexpr (EARLY == 1)
-			if (lane == 0) l2_prefetch_row(rp[0], nvec * 16), l2_prefetch_row(rp[1], nvec * 16);
+		l2_prefetch_row(rp[0], nvec * 16), l2_prefetch_row(rp[1], nvec * 16);
 	}
 	pdl_wait_prev();
 	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, blockIdx.x == 0 ? a.xb_out : nullptr);
@@ -296,10 +297,7 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_qkv(const QkvArgs<K
 		int j, k;
 		rows_of(p, rp, j, k);
 		float v[2];
-		if (EARLY == 2 && p == p0)
-			warp_dot_rows<DBITS, 2, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v, &head);
-		else
-			warp_dot_rows<DBITS, 2, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
+		warp_dot_rows<DBITS, 2, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
 
 		if (lane == 0) {
 			float v0 = v[0], v1 = v[1];
@@ -778,12 +776,9 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 	// dense models: request the first row pair before waiting for the previous kernel (the expert of a MoE layer is its result)
 	const int p0 = blockIdx.x * nwarps + warp;
 	const bool early = EARLY != 0 && a.sel == nullptr && p0 < a.d / 2;
-	RowHead<2, 4> head4; // (half a batch of the long rows: the other half would spill at 2 CTAs per SM)
-	if (early) {
-		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w) + (size_t)(2 * p0) * nvec, reinterpret_cast<const uint4*>(a.w) + (size_t)(2 * p0 + 1) * nvec};
-		if constexpr (EARLY == 2) rows_request<2, 4>(rp, nvec, head4);
-		if constexpr (EARLY == 1)
-			if (lane == 0) l2_prefetch_row(rp[0], nvec * 16), l2_prefetch_row(rp[1], nvec * 16);
+	if (early && lane == 0) {
+		const uint4* r0 = reinterpret_cast<const uint4*>(a.w) + (size_t)(2 * p0) * nvec;
+		l2_prefetch_row(r0, nvec * 16), l2_prefetch_row(r0 + nvec, nvec * 16);
 	}
 	pdl_wait_prev();
 
@@ -797,19 +792,11 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 		for (int p = blockIdx.x * nwarps + warp; p < a.d / 2; p += gridDim.x * nwarps, ++it) {
 			const uint4* rp[2] = {wb + (size_t)(2 * p) * nvec, wb + (size_t)(2 * p + 1) * nvec};
 			float v[2];
-			const bool pre = EARLY == 2 && early && p == p0;
 			const float4* xs4 = reinterpret_cast<const float4*>(xs);
-			if (long_rows) {
-				if (pre)
-					warp_dot_rows<DBITS, 2, 8, 4>(rp, nvec, xs4, v, &head4);
-				else
-					warp_dot_rows<DBITS, 2, 8>(rp, nvec, xs4, v);
-			} else {
-				if (pre)
-					warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v, &head4);
-				else
-					warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
-			}
+			if (long_rows)
+				warp_dot_rows<DBITS, 2, 8>(rp, nvec, xs4, v);
+			else
+				warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
 			if (lane == 0) {
 				if (a.tpx.world > 1) { // this rank's partial: summed over the ranks below
 					tp_part[it * 16 + warp * 2] = v[0], tp_part[it * 16 + warp * 2 + 1] = v[1];
@@ -848,7 +835,7 @@ struct FfnUpArgs {
 };
 
 template <int DBITS, int EARLY>
-__global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpArgs a) {
+__global__ void __launch_bounds__(256, EARLY == 2 ? 4 : 3) k_ffn_up(const FfnUpArgs a) {
 	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	__shared__ float glog[64];
@@ -861,12 +848,9 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpA
 	// dense models: the first (w1, w3) row pair is requested before the previous kernel has finished and x is staged
 	const int p0 = blockIdx.x * nwarps + warp;
 	const bool early = EARLY != 0 && a.n_experts == 0 && p0 < a.hidden;
-	RowHead<2, 4> head;
-	if (early) {
-		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w1) + (size_t)p0 * nvec, reinterpret_cast<const uint4*>(a.w3) + (size_t)p0 * nvec};
-		if constexpr (EARLY == 2) rows_request<2, 4>(rp, nvec, head);
-		if constexpr (EARLY == 1)
-			if (lane == 0) l2_prefetch_row(rp[0], nvec * 16), l2_prefetch_row(rp[1], nvec * 16);
+	if (early && lane == 0) {
+		l2_prefetch_row(reinterpret_cast<const uint4*>(a.w1) + (size_t)p0 * nvec, nvec * 16);
+		l2_prefetch_row(reinterpret_cast<const uint4*>(a.w3) + (size_t)p0 * nvec, nvec * 16);
 	}
 	pdl_wait_prev();
 	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
@@ -906,10 +890,7 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpA
 		size_t off = (a.n_experts ? (size_t)ssel.expert[e] * esize : 0) + (size_t)i * nvec;
 		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w1) + off, reinterpret_cast<const uint4*>(a.w3) + off};
 		float v[2];
-		if (EARLY == 2 && early && p == p0)
-			warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v, &head);
-		else
-			warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
+		warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
 		if (lane == 0) a.hb[p] = (a.gelu ? act_gelu(v[0]) : act_silu(v[0])) * v[1];
 	}
 }
