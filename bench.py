@@ -374,7 +374,7 @@ def dm_roofline(dm, L, spec, pos, peak, peak_src, ms_per_tok, bytes_per_tok):
     name, (ms, by, nl, *_) = max(((k, v) for k, v in stats.items() if v[1] > 0), key=lambda kv: kv[1][0])
     achieved = by / 1e9 / (ms / 1e3) if ms > 0 else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture in profiles/ (r01: k_ffn_up<8> on this workload)
-    traffic = 117.53e6 + 0.2e6 if (name == "matmul_ffn_up" and spec.name == "llama3-8b-fp8") else None
+    traffic = 117.53e6 + 5.33e6 if (name == "matmul_ffn_up" and spec.name == "llama3-8b-fp8") else None  # profiles/r01_ncu_full_one_layer_staged.csv
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
             "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by / max(nl, 1), "us_per_launch": ms / max(nl, 1) * 1e3, "stages": table}
 

@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	const int nvec = a.n / WFmt<DBITS>::VW;
 	const size_t esize = (size_t)a.d * nvec; // 16-byte vectors per expert
-	const bool long_rows = nvec > 32 * 8 && DBITS != 4; // w2: a warp has one pair and is latency-bound; keep twice the loads in flight
+	const bool long_rows = nvec >= 32 * 8 && DBITS != 4; // a warp has ONE pair and is latency-bound: 8 KB in flight per warp (wo: the whole pair at once)
 	// dense models: request the first row pair before waiting for the previous kernel (the expert of a MoE layer is its result)
 	const int p0 = blockIdx.x * nwarps + warp;
 	const bool early = EARLY != 0 && a.sel == nullptr && p0 < a.d / 2;
