@@ -73,8 +73,8 @@ struct Engine {
 	int* fused_err = nullptr; // pinned + mapped
 	unsigned long long* fused_perf_ns = nullptr; // device [32]
 	bool fused_perf = false;
-	cudaGraphExec_t fgraph[4] = {nullptr, nullptr, nullptr, nullptr};
-	int fgraph_launches[4] = {0, 0, 0, 0};
+	cudaGraphExec_t fgraph[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	int fgraph_launches[5] = {0, 0, 0, 0, 0};
 
 	// tensor parallelism (staged engine): this process owns 1/tp_world of the heads and of the FFN rows
 	int tp_rank = 0, tp_world = 1;
@@ -92,8 +92,15 @@ struct Engine {
 	int persist_nsplit = 1;
 
 	// graphs: 0 = kv only, 1 = logits to host, 2 = logits to device + greedy advance, 3 = logits to host + argmax
-	cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
-	int graph_launches[4] = {0, 0, 0, 0};
+	cudaGraphExec_t graph[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // per call mode: 0 KV only, 1 logits to host, 2 greedy loop, 3 logits + argmax, 4 min-p sampling loop
+	int graph_launches[5] = {0, 0, 0, 0, 0};
+	// device-side min-p sampler (stages.cuh k_sample_*)
+	SampleState* sample_state = nullptr;
+	int sample_chunks = 0;
+	int* sample_count = nullptr;
+	float* sample_csum = nullptr;
+	int* sample_idx = nullptr;
+	float* sample_prob = nullptr;
 	bool use_graph = true;
 	bool use_pdl = true;
 	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + 64-register k_ffn_up
@@ -411,13 +418,20 @@ int run_token(int mode) {
 		StageTimer t(ST_OUTPUT, (double)c.vocab_size * dim * wb / 8);
 		OutputArgs a;
 		a.x = g.x, a.normw = w.rms_final_weight, a.wcls = w.wcls;
-		a.logits = (mode == 2) ? g.logits_dev : g.logits_host;
+		a.logits = (mode == 2 || mode == 4) ? g.logits_dev : g.logits_host;
 		a.cand_val = (mode >= 2) ? g.cand_val : nullptr, a.cand_idx = g.cand_idx;
 		a.dim = dim, a.vocab = c.vocab_size, a.eps = c.norm_eps, a.ln = c.norm_ln;
 		int grid = g.grid_out;
 		launch_pdl(k_output<DBITS>, grid, 256, g.smem_dim, a);
 		++nl;
-		if (mode >= 2) {
+		if (mode == 4) { // min-p sampling on the device (reference sampler.c:44-90), then the bookkeeping of k_advance
+			SampleArgs sa;
+			sa.logits = g.logits_dev, sa.cand_val = g.cand_val, sa.ncand = grid, sa.vocab = c.vocab_size, sa.nchunks = g.sample_chunks;
+			sa.st = g.sample_state, sa.count = g.sample_count, sa.csum = g.sample_csum, sa.sidx = g.sample_idx, sa.sprob = g.sample_prob;
+			launch_pdl(k_sample_scan, g.sample_chunks, 256, 0, sa);
+			launch_pdl(k_sample_pick, 1, 32, 0, sa, g.sample_state, g.tp, g.out_tokens, g.last_token, 1);
+			nl += 2;
+		} else if (mode >= 2) {
 			launch_pdl(k_advance, 1, 256, 0, (const float*)g.cand_val, (const int*)g.cand_idx, grid, g.tp, g.out_tokens, g.last_token, (int)(mode == 2), c.vocab_size);
 			++nl;
 		}
@@ -780,7 +794,7 @@ void launch_token(int mode) {
 	// the persistent kernel serves every token it can; the rest (MoE, fp8 KV, rolled-over cache,
 	// per-stage profiling) goes through the staged engine.  Both are CUDA paths over the same buffers.
 	const bool one_kernel = ((g.engine == 1 && g.fused_ok) || (g.engine == 2 && g.persist_ok)) && (!g.perf || g.fused_perf) && !g.debug_stages &&
-	                        g.cur_pos < g.cfg.seq_len;
+	                        g.cur_pos < g.cfg.seq_len && mode != 4; // the sampler tail lives in the staged token
 	if (one_kernel) {
 		auto run = [&](int m) { return g.engine == 2 ? run_token_persist(m) : run_token_fused(m); };
 		if (!g.use_graph || g.fused_perf) {
@@ -984,6 +998,12 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.cand_idx = (int*)dev_alloc(ncand_cap * sizeof(int));
 	g.out_tokens_cap = 1 << 16;
 	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
+	g.sample_chunks = cdiv(c.vocab_size, SAMPLE_CHUNK);
+	g.sample_state = (SampleState*)dev_alloc(sizeof(SampleState));
+	g.sample_count = (int*)dev_alloc(g.sample_chunks * sizeof(int));
+	g.sample_csum = (float*)dev_alloc(g.sample_chunks * sizeof(float));
+	g.sample_idx = (int*)dev_alloc((size_t)g.sample_chunks * SAMPLE_CHUNK * sizeof(int));
+	g.sample_prob = (float*)dev_alloc((size_t)g.sample_chunks * SAMPLE_CHUNK * sizeof(float));
 
 	if (g.engine == 1) fused_plan();
 	if (g.engine == 2) persist_plan();
@@ -1025,7 +1045,7 @@ extern "C" int calm_b200_tp_mode(void) {
 extern "C" void calm_b200_release(struct Transformer* transformer) {
 	if (!g.ready) return;
 	CUDA_CHECK(cudaDeviceSynchronize());
-	for (int i = 0; i < 4; ++i) {
+	for (int i = 0; i < 5; ++i) {
 		if (g.graph[i]) CUDA_CHECK(cudaGraphExecDestroy(g.graph[i]));
 		if (g.fgraph[i]) CUDA_CHECK(cudaGraphExecDestroy(g.fgraph[i]));
 	}
@@ -1040,6 +1060,7 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 		if (g.tp_peer[p] && g.tp_peer[p] != g.tp_area) cudaIpcCloseMemHandle(g.tp_peer[p]);
 	if (g.tp_area) cudaFree(g.tp_area);
 	if (g.tp_err) cudaFreeHost(g.tp_err);
+	cudaFree(g.sample_state), cudaFree(g.sample_count), cudaFree(g.sample_csum), cudaFree(g.sample_idx), cudaFree(g.sample_prob);
 	if (g.tp_comm) g_nccl.CommDestroy(g.tp_comm);
 	if (g.xpart) cudaFree(g.xpart);
 	for (void* p : g.tp_owned) cudaFree(p);
@@ -1105,6 +1126,40 @@ extern "C" void calm_b200_decode_greedy(struct Transformer* transformer, int tok
 	}
 	sync_stream();
 	CUDA_CHECK(cudaMemcpy(out_tokens, g.out_tokens, n_tokens * sizeof(int), cudaMemcpyDeviceToHost));
+}
+
+// min-p / temperature sampling without a host round trip per token (reference sample(), sampler.c:80-90)
+extern "C" void calm_b200_decode_sample(struct Transformer* transformer, int token0, int pos0, int n_tokens, float temperature, float minp,
+                                        unsigned long long* rng_state, int* out_tokens) {
+	if (temperature == 0.0f || minp >= 1.0f) { // greedy: the reference does not touch the generator either
+		calm_b200_decode_greedy(transformer, token0, pos0, n_tokens, out_tokens);
+		return;
+	}
+	check_call(transformer, token0, pos0);
+	if (n_tokens > g.out_tokens_cap) CALM_FATAL("decode_sample: at most %d tokens per call", g.out_tokens_cap);
+	SampleState st;
+	st.rng = *rng_state, st.temperature = temperature, st.cut_delta = logf(minp) * temperature;
+	CUDA_CHECK(cudaMemcpyAsync(g.sample_state, &st, sizeof(st), cudaMemcpyHostToDevice, g.stream));
+	set_params(token0, pos0, 0);
+	for (int i = 0; i < n_tokens; ++i) {
+		g.cur_pos = pos0 + i;
+		launch_token(4);
+	}
+	sync_stream();
+	CUDA_CHECK(cudaMemcpy(out_tokens, g.out_tokens, n_tokens * sizeof(int), cudaMemcpyDeviceToHost));
+	CUDA_CHECK(cudaMemcpy(&st, g.sample_state, sizeof(st), cudaMemcpyDeviceToHost));
+	*rng_state = st.rng;
+}
+
+extern "C" int calm_b200_forward_sample(struct Transformer* transformer, int token, int pos, float temperature, float minp, unsigned long long* rng_state) {
+	int tok = 0;
+	calm_b200_decode_sample(transformer, token, pos, 1, temperature, minp, rng_state, &tok);
+	return tok;
+}
+
+// the logits of the last device-resident step (decode_greedy / decode_sample keep them in HBM): copy for tests
+extern "C" void calm_b200_read_device_logits(float* out) {
+	CUDA_CHECK(cudaMemcpy(out, g.logits_dev, (size_t)g.cfg.vocab_size * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
 extern "C" void calm_b200_timer_start(void) {

@@ -1015,6 +1015,164 @@ __global__ void k_set_params(TokenParams* tp, int token, int pos, int seq_len, i
 	tp->tp_seq += 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-side min-p sampling (reference sampler.c:44-90): cutoff = max + log(minp) * T; survivors get
+// p_i = exp((l_i - max) / T); r = coin * sum(p); the first index whose running sum exceeds r wins, the last survivor
+// when rounding leaves none.  The reference adds the survivors one by one in index order; k_sample_scan keeps that
+// order (per-chunk lists compacted in index order) and k_sample_pick walks them sequentially with one thread, so the
+// additions are the reference's additions as long as there are at most SAMPLE_EXACT survivors; beyond that (flat
+// distributions) per-chunk sums are added chunk by chunk, which can move a bin edge by an ulp.
+// The coin comes from the reference's xorshift* generator (sampler.c:7-17), advanced on the device.
+
+#define SAMPLE_CHUNK 1024
+#define SAMPLE_EXACT 2048
+
+struct SampleState {
+	unsigned long long rng;
+	float temperature;
+	float cut_delta; // log(minp) * temperature, formed on the host with the host libm like the reference does
+};
+
+struct SampleArgs {
+	const float* logits;
+	const float* cand_val; // per-CTA maxima of k_output
+	int ncand, vocab, nchunks;
+	const SampleState* st;
+	int* count;      // [nchunks]
+	float* csum;     // [nchunks] sequential sum of the chunk's survivors
+	int* sidx;       // [nchunks][SAMPLE_CHUNK]
+	float* sprob;
+};
+
+__global__ void __launch_bounds__(256) k_sample_scan(const SampleArgs a) {
+	pdl_enter();
+	__shared__ float red[8];
+	__shared__ int wcount[8];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	float mx = -FLT_MAX;
+	for (int i = tid; i < a.ncand; i += 256) mx = fmaxf(mx, a.cand_val[i]);
+	for (int m = 16; m > 0; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+	if (lane == 0) red[warp] = mx;
+	__syncthreads();
+	mx = red[0];
+	for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+	const float temp = a.st->temperature, cutoff = mx + a.st->cut_delta;
+
+	// 4 consecutive entries per thread, so that thread order is index order
+	const int base = blockIdx.x * SAMPLE_CHUNK + tid * 4;
+	float p[4];
+	int keep = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		float l = base + k < a.vocab ? a.logits[base + k] : -FLT_MAX;
+		bool s = base + k < a.vocab && l >= cutoff;
+		p[k] = s ? expf((l - mx) / temp) : -1.f;
+		keep += s;
+	}
+	int incl = keep;
+	for (int m = 1; m < 32; m <<= 1) {
+		int o = __shfl_up_sync(0xffffffffu, incl, m);
+		if (lane >= m) incl += o;
+	}
+	if (lane == 31) wcount[warp] = incl;
+	__syncthreads();
+	int off = incl - keep;
+	for (int w = 0; w < warp; ++w) off += wcount[w];
+	int* li = a.sidx + (size_t)blockIdx.x * SAMPLE_CHUNK;
+	float* lp = a.sprob + (size_t)blockIdx.x * SAMPLE_CHUNK;
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+		if (p[k] >= 0.f) li[off] = base + k, lp[off] = p[k], ++off;
+	__syncthreads();
+	if (tid == 0) {
+		int n = 0;
+		for (int w = 0; w < 8; ++w) n += wcount[w];
+		float sum = 0.f;
+		for (int j = 0; j < n; ++j) sum += lp[j];
+		a.count[blockIdx.x] = n, a.csum[blockIdx.x] = sum;
+	}
+}
+
+__device__ __forceinline__ unsigned xorshift_u32(unsigned long long& s) { // reference sampler.c:7-13
+	s ^= s >> 12;
+	s ^= s << 25;
+	s ^= s >> 27;
+	return (unsigned)((s * 0x2545F4914F6CDD1Dull) >> 32);
+}
+
+// one thread: the reference's two sequential passes; then the bookkeeping of k_advance
+__global__ void k_sample_pick(const SampleArgs a, SampleState* st, TokenParams* tp, int* out_tokens, int* last_token, int advance) {
+	pdl_enter();
+	if (threadIdx.x != 0) return;
+	unsigned long long rng = st->rng;
+	const float coin = (float)(xorshift_u32(rng) >> 8) / 16777216.0f; // sampler.c:15-17
+	st->rng = rng;
+	int total = 0;
+	for (int c = 0; c < a.nchunks; ++c) total += a.count[c];
+	int tok = 0, fallback = 0;
+	if (total <= SAMPLE_EXACT) {
+		float cum = 0.f;
+		for (int c = 0; c < a.nchunks; ++c) {
+			const float* lp = a.sprob + (size_t)c * SAMPLE_CHUNK;
+			const int n = a.count[c];
+			for (int j = 0; j < n; ++j) cum += lp[j];
+			if (n) fallback = a.sidx[(size_t)c * SAMPLE_CHUNK + n - 1];
+		}
+		const float r = coin * cum;
+		float cdf = 0.f;
+		tok = -1;
+		for (int c = 0; c < a.nchunks && tok < 0; ++c) {
+			const float* lp = a.sprob + (size_t)c * SAMPLE_CHUNK;
+			const int n = a.count[c];
+			for (int j = 0; j < n; ++j) {
+				cdf += lp[j];
+				if (r < cdf) {
+					tok = a.sidx[(size_t)c * SAMPLE_CHUNK + j];
+					break;
+				}
+			}
+		}
+	} else {
+		float cum = 0.f;
+		for (int c = 0; c < a.nchunks; ++c) {
+			cum += a.csum[c];
+			if (a.count[c]) fallback = a.sidx[(size_t)c * SAMPLE_CHUNK + a.count[c] - 1];
+		}
+		const float r = coin * cum;
+		float cdf = 0.f;
+		tok = -1;
+		for (int c = 0; c < a.nchunks && tok < 0; ++c) {
+			if (r < cdf + a.csum[c]) {
+				const float* lp = a.sprob + (size_t)c * SAMPLE_CHUNK;
+				for (int j = 0; j < a.count[c]; ++j) {
+					cdf += lp[j];
+					if (r < cdf) {
+						tok = a.sidx[(size_t)c * SAMPLE_CHUNK + j];
+						break;
+					}
+				}
+				if (tok < 0) continue; // rounding: the edge belongs to a later chunk
+			} else {
+				cdf += a.csum[c];
+			}
+		}
+	}
+	if (tok < 0) tok = fallback;
+	*last_token = tok;
+	if (advance) {
+		out_tokens[tp->step] = tok;
+		int pos = tp->pos + 1, seq_len = tp->seq_len;
+		int sink = pos >= seq_len ? 2 : 0; // KV_SINKS
+		tp->token = tok;
+		tp->tp_seq += 1;
+		tp->pos = pos;
+		tp->kv_sink = sink;
+		tp->kv_pos = sink + (pos - sink) % (seq_len - sink);
+		tp->kv_len = pos >= seq_len ? seq_len : pos + 1;
+		tp->step += 1;
+	}
+}
+
 // x += p (tensor-parallel: the all-reduced partial of wo / w2 joins the residual stream)
 __global__ void k_addvec(float* x, const float* p, int n) {
 	pdl_enter();

@@ -28,6 +28,7 @@ SYMBOLS = [
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
     "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_engine_in_use", "calm_b200_stage_wait_ms", "calm_b200_barrier_bench", "calm_b200_stage_detail_ms",
     "calm_b200_tp_unique_id", "calm_b200_tp_init", "calm_b200_tp_world", "calm_b200_tp_mode",
+    "calm_b200_decode_sample", "calm_b200_forward_sample", "calm_b200_read_device_logits",
 ]
 
 _lib = None
@@ -72,6 +73,11 @@ def load() -> C.CDLL:
     L.calm_b200_tp_init.argtypes, L.calm_b200_tp_init.restype = [C.c_int, C.c_int, C.c_void_p], None
     L.calm_b200_tp_world.argtypes, L.calm_b200_tp_world.restype = [], C.c_int
     L.calm_b200_tp_mode.argtypes, L.calm_b200_tp_mode.restype = [], C.c_int
+    L.calm_b200_decode_sample.argtypes = [T, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]
+    L.calm_b200_decode_sample.restype = None
+    L.calm_b200_forward_sample.argtypes = [T, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_ulonglong)]
+    L.calm_b200_forward_sample.restype = C.c_int
+    L.calm_b200_read_device_logits.argtypes, L.calm_b200_read_device_logits.restype = [_fptr], None
     _lib = L
     return L
 
@@ -141,6 +147,18 @@ class DeviceModel:
     def decode_greedy(self, token0: int, pos0: int, n: int) -> np.ndarray:
         out = np.zeros(n, np.int32)
         self.lib.calm_b200_decode_greedy(C.byref(self.transformer), token0, pos0, n, out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
+
+    def decode_sample(self, token0: int, pos0: int, n: int, temperature: float, minp: float, rng_state: int):
+        """Device-resident temperature / min-p sampling; returns (tokens, new rng state)."""
+        out = np.zeros(n, np.int32)
+        rng = C.c_ulonglong(rng_state)
+        self.lib.calm_b200_decode_sample(C.byref(self.transformer), token0, pos0, n, temperature, minp, C.byref(rng), out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out, int(rng.value)
+
+    def device_logits(self) -> np.ndarray:
+        out = np.zeros(self.vocab, np.float32)
+        self.lib.calm_b200_read_device_logits(out.ctypes.data_as(_fptr))
         return out
 
     def logits_view(self) -> np.ndarray:

@@ -113,6 +113,17 @@ int calm_b200_forward_argmax(struct Transformer* transformer, int token, int pos
  * This is what bench.py times as the in-HBM throughput. */
 void calm_b200_decode_greedy(struct Transformer* transformer, int token0, int pos0, int n_tokens, int* out_tokens);
 
+/* The reference's sample() (sampler.c:80-90) on the device: temperature / min-p sampling with the reference's
+ * xorshift* generator (sampler.c:7-17), no logits transfer and no host scan of the vocabulary per token.
+ * temperature == 0 or minp >= 1 is greedy and leaves *rng_state alone, as in the reference.  Survivors are added
+ * in index order like the reference does (exactly its additions up to 2048 survivors; chunk by chunk beyond).
+ * decode_sample feeds token0 at pos0 and then n_tokens-1 times its own sample; out_tokens[i] = sample after step i.
+ * The logits stay in HBM (calm_b200_read_device_logits copies the last step's); state.logits is not updated. */
+void calm_b200_decode_sample(struct Transformer* transformer, int token0, int pos0, int n_tokens, float temperature, float minp,
+                             unsigned long long* rng_state, int* out_tokens);
+int calm_b200_forward_sample(struct Transformer* transformer, int token, int pos, float temperature, float minp, unsigned long long* rng_state);
+void calm_b200_read_device_logits(float* out_vocab);
+
 /* Device timer on the library's stream (CUDA events): start, ..., stop -> ms. */
 void calm_b200_timer_start(void);
 float calm_b200_timer_stop(void);

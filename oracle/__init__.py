@@ -125,3 +125,40 @@ def teacher_forced(checker: Checker, model, tokens, pos0: int = 0):
     checker.prepare(model)
     out = [checker.forward(model, tok, pos0 + i, 0) for i, tok in enumerate(tokens)]
     return np.stack(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler (reference src/sampler.c): our restatement and the unmodified reference, same call shape
+
+class _RefSampler(C.Structure):  # struct Sampler, reference sampler.h:3-9
+    _fields_ = [("vocab_size", C.c_int), ("rng_state", C.c_ulonglong), ("temperature", C.c_float), ("minp", C.c_float)]
+
+
+class Sampler:
+    """sample(logits) -> token with an explicit xorshift* state.  kind "port" = oracle_sample (calm_oracle.c),
+    kind "reference" = sample() of the unmodified sampler.c (oracle/_ref/libcalm_ref_sampler.so)."""
+
+    def __init__(self, kind: str, temperature: float, minp: float, rng_state: int):
+        self.kind, self.temperature, self.minp, self.rng_state = kind, float(temperature), float(minp), int(rng_state)
+        path = _PATHS["port"] if kind == "port" else os.path.join(HERE, "_ref", "libcalm_ref_sampler.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        if kind == "port":
+            self.lib.oracle_sample.argtypes = [_fptr, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_ulonglong)]
+            self.lib.oracle_sample.restype = C.c_int
+        else:
+            self.lib.sample.argtypes = [C.POINTER(_RefSampler), _fptr]
+            self.lib.sample.restype = C.c_int
+
+    def sample(self, logits: np.ndarray) -> int:
+        buf = np.array(logits, np.float32, copy=True)  # the reference overwrites its argument with probabilities
+        if self.kind == "port":
+            rng = C.c_ulonglong(self.rng_state)
+            tok = self.lib.oracle_sample(buf.ctypes.data_as(_fptr), len(buf), self.temperature, self.minp, C.byref(rng))
+            self.rng_state = int(rng.value)
+            return tok
+        s = _RefSampler(len(buf), self.rng_state, self.temperature, self.minp)
+        tok = self.lib.sample(C.byref(s), buf.ctypes.data_as(_fptr))
+        self.rng_state = int(s.rng_state)
+        return tok

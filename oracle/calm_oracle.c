@@ -417,3 +417,41 @@ int oracle_argmax(const float* logits, int n) {
 	}
 	return max_i;
 }
+
+/* xorshift* generator of the reference (sampler.c:7-17). */
+static unsigned int oracle_random_u32(unsigned long long* state) {
+	*state ^= *state >> 12;
+	*state ^= *state << 25;
+	*state ^= *state >> 27;
+	return (unsigned int)((*state * 0x2545F4914F6CDD1Dull) >> 32);
+}
+
+float oracle_random_f32(unsigned long long* state) {
+	return (float)(oracle_random_u32(state) >> 8) / 16777216.0f;
+}
+
+/* sample(): greedy when temperature == 0 or minp >= 1, else min-p truncated sampling (reference
+ * sampler.c:44-90).  Survivors (logit >= max + log(minp) * T) get exp((l - max) / T); the running sum is formed in
+ * index order twice: once for the total, once to find the first index whose cumulative sum exceeds coin * total;
+ * the last survivor is the fallback.  Unlike the reference, `logits` is left untouched. */
+int oracle_sample(const float* logits, int n, float temperature, float minp, unsigned long long* rng_state) {
+	if (temperature == 0.0f || minp >= 1.0f) return oracle_argmax(logits, n);
+	float coin = oracle_random_f32(rng_state);
+	float max_logit = -FLT_MAX;
+	for (int i = 0; i < n; ++i) max_logit = logits[i] > max_logit ? logits[i] : max_logit;
+	float cutoff = max_logit + logf(minp) * temperature;
+	float cum = 0.0f;
+	int fallback = 0;
+	for (int i = 0; i < n; ++i)
+		if (logits[i] >= cutoff) {
+			cum += expf((logits[i] - max_logit) / temperature);
+			fallback = i;
+		}
+	float r = coin * cum, cdf = 0.0f;
+	for (int i = 0; i < n; ++i)
+		if (logits[i] >= cutoff) {
+			cdf += expf((logits[i] - max_logit) / temperature);
+			if (r < cdf) return i;
+		}
+	return fallback;
+}
