@@ -103,7 +103,10 @@ struct Engine {
 	float* sample_prob = nullptr;
 	bool use_graph = true;
 	bool use_pdl = true;
-	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + 64-register k_ffn_up
+	bool mma_up = false; // FFN-up on the tensor cores (k_ffn_up_mma)
+	int* tile_ctr = nullptr; // [n_layers] dynamic tile counters of k_ffn_up_mma (zeroed by k_embed every token)
+	int grid_up_mma = 0;
+	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + 288-thread k_ffn_up
 
 	// profiling (perf_cuda)
 	bool perf = false;
@@ -341,6 +344,7 @@ int run_token(int mode) {
 		EmbedArgs<KVT> a;
 		a.x = g.x, a.table = w.token_embedding_table, a.tp = g.tp, a.dim = dim;
 		a.embed_blocks = cdiv(dim, 256);
+		a.tile_ctr = g.tile_ctr, a.n_ctr = c.n_layers;
 		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq;
 		a.n_layers = c.n_layers, a.n_kv_heads = c.n_kv_heads, a.head_dim = hd, a.seq_len = c.seq_len;
 		launch_pdl(k_embed<DBITS, KVT>, a.embed_blocks + 8, 256, 0, a);
@@ -392,7 +396,12 @@ int run_token(int mode) {
 			a.gate = c.n_experts ? w.moegate[l] : nullptr, a.w1 = w.w1[l], a.w3 = w.w3[l], a.hb = g.hb, a.sel = g.moe_sel;
 			a.dim = dim, a.hidden = hidden, a.n_experts = c.n_experts, a.nact = g.nact;
 			a.eps = c.norm_eps, a.ln = c.norm_ln, a.gelu = c.act_gelu;
-			launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, 256, g.smem_dim, a);
+			a.tile_ctr = g.tile_ctr ? g.tile_ctr + l : nullptr;
+			bool done = false;
+			if constexpr (DBITS != 4) {
+				if (g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
+			}
+			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, EARLY == 2 ? 288 : 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -499,7 +508,18 @@ void make_plan() {
 			if (cdiv(c.dim / 2, grid * 8) > TP_MAX_ITERS) CALM_FATAL("tensor parallelism: grid %d outside the exchange tables for dim %d", grid, c.dim);
 	}
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
-	g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
+	{ // EARLY == 2: 9-warp CTAs at 72 registers -- 3996 resident warps instead of 3552, so that 14336 rows take 4 rounds, not 4.04
+		const int threads_up = EARLY == 2 ? 288 : 256;
+		g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, threads_up, g.smem_dim), cdiv(g.nact * c.hidden_dim, threads_up / 32));
+	}
+	g.mma_up = false;
+	if constexpr (DBITS != 4) { // tensor-core FFN-up (stages.cuh k_ffn_up_mma): dense, whole k-blocks per warp
+		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : false;
+		if (want && c.n_experts == 0 && c.dim % (32 * WFmt<DBITS>::VW) == 0 && c.hidden_dim % 8 == 0 && c.dim <= 16384) {
+			g.mma_up = true;
+			g.grid_up_mma = imin(max_ctas(k_ffn_up_mma<DBITS>, 256, g.smem_dim), c.hidden_dim / 8);
+		}
+	}
 	g.grid_out = balanced_grid(cdiv(c.vocab_size, 32), max_ctas(k_output<DBITS>, 256, g.smem_dim));
 	g.ncand = g.grid_out;
 }
@@ -998,6 +1018,10 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.cand_idx = (int*)dev_alloc(ncand_cap * sizeof(int));
 	g.out_tokens_cap = 1 << 16;
 	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
+	if (!(getenv("CALM_B200_MMA_STATIC") && atoi(getenv("CALM_B200_MMA_STATIC")))) {
+		g.tile_ctr = (int*)dev_alloc(MAX_LAYERS * sizeof(int));
+		CUDA_CHECK(cudaMemset(g.tile_ctr, 0, MAX_LAYERS * sizeof(int)));
+	}
 	g.sample_chunks = cdiv(c.vocab_size, SAMPLE_CHUNK);
 	g.sample_state = (SampleState*)dev_alloc(sizeof(SampleState));
 	g.sample_count = (int*)dev_alloc(g.sample_chunks * sizeof(int));
@@ -1060,6 +1084,7 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 		if (g.tp_peer[p] && g.tp_peer[p] != g.tp_area) cudaIpcCloseMemHandle(g.tp_peer[p]);
 	if (g.tp_area) cudaFree(g.tp_area);
 	if (g.tp_err) cudaFreeHost(g.tp_err);
+	if (g.tile_ctr) cudaFree(g.tile_ctr);
 	cudaFree(g.sample_state), cudaFree(g.sample_count), cudaFree(g.sample_csum), cudaFree(g.sample_idx), cudaFree(g.sample_prob);
 	if (g.tp_comm) g_nccl.CommDestroy(g.tp_comm);
 	if (g.xpart) cudaFree(g.xpart);
