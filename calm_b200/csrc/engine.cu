@@ -103,8 +103,6 @@ struct Engine {
 	float* sample_prob = nullptr;
 	bool use_graph = true;
 	bool use_pdl = true;
-	bool stage = false;  // matvec kernels keep extra weight vectors in flight through cp.async into shared memory (warp_dot_rows_staged)
-	size_t stage_dim = 0, stage_hidden = 0; // extra dynamic shared memory of the launches that stage
 	bool mma_up = false; // FFN-up on the tensor cores (k_ffn_up_mma)
 	int* tile_ctr = nullptr; // [n_layers] dynamic tile counters of k_ffn_up_mma (zeroed by k_embed every token)
 	int grid_up_mma = 0;
@@ -363,8 +361,8 @@ int run_token(int mode) {
 			a.q_out = g.q, a.kc = (KVT*)g.kc + l * kv_layer, a.vc = (KVT*)g.vc + l * kv_layer;
 			a.rope_freq = g.rope_freq, a.xb_out = c.norm_par ? g.xb : nullptr, a.tp = g.tp;
 			a.dim = dim, a.q_dim = g.q_dim, a.kv_dim = g.kv_dim, a.head_dim = hd, a.seq_len = c.seq_len;
-			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln, a.stage = g.stage_dim != 0;
-			launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, 256, g.smem_dim + g.stage_dim, a);
+			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln;
+			launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -403,8 +401,7 @@ int run_token(int mode) {
 			if constexpr (DBITS != 4) {
 				if (g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
 			}
-			a.stage = g.stage_dim != 0 && EARLY != 2; // (the 288-thread variant has no room reserved for a ninth warp)
-			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, EARLY == 2 ? 288 : 256, g.smem_dim + g.stage_dim, a);
+			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, EARLY == 2 ? 288 : 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -414,8 +411,7 @@ int run_token(int mode) {
 			a.n = hidden, a.d = dim, a.nact = g.nact, a.accumulate = 1;
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			a.stage = g.stage_hidden != 0;
-			launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden + g.stage_hidden, a);
+			launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
@@ -503,15 +499,10 @@ void make_plan() {
 	g.smem_hidden = xs_bytes<DBITS>(c.hidden_dim);
 	size_t smem_res = g.smem_qdim > g.smem_hidden ? g.smem_qdim : g.smem_hidden;
 	if (smem_res > 227 * 1024 || g.smem_dim > 227 * 1024) CALM_FATAL("activation vector does not fit in shared memory (dim %d, hidden %d)", c.dim, c.hidden_dim);
-	g.stage = DBITS != 4 && getenv("CALM_B200_STAGE") && atoi(getenv("CALM_B200_STAGE")) != 0;
-	g.stage_dim = g.stage ? 8 * 2 * 4 * 512 : 0;    // k_qkv, k_ffn_up: 8 warps x 2 rows x 4 vectors x 512 bytes
-	g.stage_hidden = g.stage ? 8 * 2 * 6 * 512 : 0; // k_matres on the long w2 rows
-	if (g.smem_hidden + g.stage_hidden > 227 * 1024) g.stage_hidden = 0;
-	if (g.smem_hidden + g.stage_hidden > smem_res) smem_res = g.smem_hidden + g.stage_hidden;
-	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT, EARLY>, 256, g.smem_dim + g.stage_dim));
+	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT, EARLY>, 256, g.smem_dim));
 	max_ctas(k_matres<DBITS, EARLY>, 256, smem_res); // opt in to the larger of the two sizes
 	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_qdim));
-	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_hidden + g.stage_hidden));
+	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_hidden));
 	if (g.tp_fused) { // the in-kernel exchange needs co-resident grids (they are: balanced_grid stays under the cap) within its tables
 		for (int grid : {g.grid_wo, g.grid_down})
 			if (cdiv(c.dim / 2, grid * 8) > TP_MAX_ITERS) CALM_FATAL("tensor parallelism: grid %d outside the exchange tables for dim %d", grid, c.dim);
@@ -519,7 +510,7 @@ void make_plan() {
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
 	{ // EARLY == 2: 9-warp CTAs at 72 registers -- 3996 resident warps instead of 3552, so that 14336 rows take 4 rounds, not 4.04
 		const int threads_up = EARLY == 2 ? 288 : 256;
-		g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, threads_up, g.smem_dim + g.stage_dim), cdiv(g.nact * c.hidden_dim, threads_up / 32));
+		g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, threads_up, g.smem_dim), cdiv(g.nact * c.hidden_dim, threads_up / 32));
 	}
 	g.mma_up = false;
 	if constexpr (DBITS != 4) { // tensor-core FFN-up (stages.cuh k_ffn_up_mma): dense, whole k-blocks per warp

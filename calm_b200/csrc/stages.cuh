@@ -74,77 +74,6 @@ __device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int n
 	for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
 }
 
-// The same with SU more vectors per row in flight WITHOUT registers: they land in a warp-private piece of shared memory
-// through cp.async (LDGSTS) while the U register vectors are loaded and consumed, and are read back by the lane that
-// requested them (no barrier: a thread only waits for its own copies).  Bytes in flight per warp go from R*U*512 to
-// R*(U+SU)*512 at the same register count -- the matvec kernels are bound by memory latency, not by bandwidth or issue.
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-
-template <int DBITS, int R, int U, int SU>
-__device__ __forceinline__ void warp_dot_rows_staged(const uint4* const (&rp)[R], int nvec, const float4* __restrict__ xs4, float (&out)[R], uint4* sw) {
-	const int lane = threadIdx.x & 31;
-	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sw + lane);
-
-	float acc[R];
-#pragma unroll
-	for (int r = 0; r < R; ++r) acc[r] = 0.f;
-
-	if (nvec % (32 * (U + SU)) == 0) {
-		for (int v0 = lane; v0 < nvec; v0 += 32 * (U + SU)) {
-#pragma unroll
-			for (int su = 0; su < SU; ++su)
-#pragma unroll
-				for (int r = 0; r < R; ++r) cp_async16(sbase + (su * R + r) * 512, rp[r] + v0 + 32 * (U + su));
-			asm volatile("cp.async.commit_group;" ::: "memory");
-			uint4 w[U][R];
-#pragma unroll
-			for (int u = 0; u < U; ++u)
-#pragma unroll
-				for (int r = 0; r < R; ++r) w[u][r] = ldg_stream(rp[r] + v0 + 32 * u);
-			rows_consume<DBITS, R, U, false>(w, v0, nvec, xs4, acc);
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-			uint4 ws[SU][R];
-#pragma unroll
-			for (int su = 0; su < SU; ++su)
-#pragma unroll
-				for (int r = 0; r < R; ++r) ws[su][r] = sw[(su * R + r) * 32 + lane];
-			rows_consume<DBITS, R, SU, false>(ws, v0 + 32 * U, nvec, xs4, acc);
-		}
-	} else {
-		for (int v0 = lane; v0 < nvec; v0 += 32 * (U + SU)) {
-#pragma unroll
-			for (int su = 0; su < SU; ++su) {
-				int v = v0 + 32 * (U + su);
-#pragma unroll
-				for (int r = 0; r < R; ++r)
-					if (v < nvec) cp_async16(sbase + (su * R + r) * 512, rp[r] + v);
-			}
-			asm volatile("cp.async.commit_group;" ::: "memory");
-			uint4 w[U][R];
-#pragma unroll
-			for (int u = 0; u < U; ++u) {
-				int v = v0 + 32 * u;
-#pragma unroll
-				for (int r = 0; r < R; ++r) w[u][r] = v < nvec ? ldg_stream(rp[r] + v) : make_uint4(0, 0, 0, 0);
-			}
-			rows_consume<DBITS, R, U>(w, v0, nvec, xs4, acc);
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-			uint4 ws[SU][R];
-#pragma unroll
-			for (int su = 0; su < SU; ++su) {
-				int v = v0 + 32 * (U + su);
-#pragma unroll
-				for (int r = 0; r < R; ++r) ws[su][r] = v < nvec ? sw[(su * R + r) * 32 + lane] : make_uint4(0, 0, 0, 0);
-			}
-			rows_consume<DBITS, R, SU>(ws, v0 + 32 * U, nvec, xs4, acc);
-		}
-	}
-#pragma unroll
-	for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
-}
-
 // (batched body of stage_vector below: every thread owns up to SV_MAX 16-byte pieces)
 template <int DBITS, int SV_MAX>
 __device__ __forceinline__ void stage_vector_batched(float* xs, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln,
@@ -326,7 +255,6 @@ struct QkvArgs {
 	int dim, q_dim, kv_dim, head_dim, seq_len;
 	float eps, clip;
 	int ln;
-	int stage; // 1: the launch reserved 8 x 4 KB of shared memory behind the activation vector (warp_dot_rows_staged)
 };
 
 // EARLY: what a warp does about its first row pair BEFORE waiting for the previous kernel and staging the activations
@@ -373,10 +301,7 @@ __global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 		int j, k;
 		rows_of(p, rp, j, k);
 		float v[2];
-		if (DBITS != 4 && a.stage)
-			warp_dot_rows_staged<DBITS, 2, 4, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v, reinterpret_cast<uint4*>(xs + xs_floats<DBITS>(a.dim)) + warp * 256);
-		else
-			warp_dot_rows<DBITS, 2, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
+		warp_dot_rows<DBITS, 2, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
 
 		if (lane == 0) {
 			float v0 = v[0], v1 = v[1];
@@ -838,7 +763,6 @@ struct MatResArgs {
 	const MoeSel* sel; // NULL: one pass with expert 0, weight 1
 	int n, d, nact;
 	int accumulate;   // 1: y += ..., 0: y = ...
-	int stage;        // 1: 8 x 6 KB of shared memory behind the activation vector for the long rows (warp_dot_rows_staged)
 	TpExchange tpx;   // world > 1: the partial is summed over the tensor-parallel ranks inside this kernel
 };
 
@@ -873,9 +797,7 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 			const uint4* rp[2] = {wb + (size_t)(2 * p) * nvec, wb + (size_t)(2 * p + 1) * nvec};
 			float v[2];
 			const float4* xs4 = reinterpret_cast<const float4*>(xs);
-			if (long_rows && a.stage)
-				warp_dot_rows_staged<DBITS, 2, 8, 6>(rp, nvec, xs4, v, reinterpret_cast<uint4*>(xs + xs_floats<DBITS>(a.n)) + warp * 384);
-			else if (long_rows)
+			if (long_rows)
 				warp_dot_rows<DBITS, 2, 8>(rp, nvec, xs4, v);
 			else
 				warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
@@ -914,7 +836,6 @@ struct FfnUpArgs {
 	int dim, hidden, n_experts, nact;
 	float eps;
 	int ln, gelu;
-	int stage;          // 1: 8 x 4 KB of shared memory behind the activation vector (warp_dot_rows_staged)
 	int* tile_ctr;      // k_ffn_up_mma: tiles beyond the first round are handed out through this counter (NULL: static stride)
 };
 
@@ -974,10 +895,7 @@ __global__ void __launch_bounds__(EARLY == 2 ? 288 : 256, 3) k_ffn_up(const FfnU
 		size_t off = (a.n_experts ? (size_t)ssel.expert[e] * esize : 0) + (size_t)i * nvec;
 		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w1) + off, reinterpret_cast<const uint4*>(a.w3) + off};
 		float v[2];
-		if (DBITS != 4 && a.stage)
-			warp_dot_rows_staged<DBITS, 2, 4, 4>(rp, nvec, xs4, v, reinterpret_cast<uint4*>(xs + xs_floats<DBITS>(a.dim)) + warp * 256);
-		else
-			warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
+		warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
 		if (lane == 0) a.hb[p] = (a.gelu ? act_gelu(v[0]) : act_silu(v[0])) * v[1];
 	}
 }
