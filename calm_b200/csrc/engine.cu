@@ -103,6 +103,7 @@ struct Engine {
 	float* sample_prob = nullptr;
 	bool use_graph = true;
 	bool use_pdl = true;
+	int carveout = -1;   // cudaFuncAttributePreferredSharedMemoryCarveout applied to every kernel of the token, or -1
 	bool mma_up = false; // FFN-up on the tensor cores (k_ffn_up_mma)
 	int* tile_ctr = nullptr; // [n_layers] dynamic tile counters of k_ffn_up_mma (zeroed by k_embed every token)
 	int grid_up_mma = 0;
@@ -268,8 +269,21 @@ void tp_fill(TpExchange& t, int idx) {
 
 // Launch on the library's stream with programmatic stream serialization (PDL), so that consecutive kernels
 // of a token overlap their launch latency (the kernels order themselves with griddepcontrol.wait).
+// One L1 / shared-memory split for every kernel of the token (env CALM_B200_CARVEOUT = percent of shared memory, unset:
+// the driver picks per kernel): kernels whose preferred splits differ cannot be co-resident on an SM, which serialises
+// exactly the hand-over that programmatic dependent launch is there to overlap.
+void same_carveout(const void* kernel) {
+	if (g.carveout < 0) return;
+	static std::vector<const void*> done;
+	for (const void* k : done)
+		if (k == kernel) return;
+	done.push_back(kernel);
+	CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, g.carveout));
+}
+
 template <typename... KArgs, typename... Args>
 void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, Args... args) {
+	same_carveout((const void*)kernel);
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = g.stream;
 	cudaLaunchAttribute at[1];
@@ -855,6 +869,7 @@ void launch_token(int mode) {
 void set_params(int token, int pos, int step) {
 	g.cur_kv_len = pos >= g.cfg.seq_len ? g.cfg.seq_len : pos + 1;
 	g.cur_pos = pos;
+	same_carveout((const void*)k_set_params);
 	k_set_params<<<1, 1, 0, g.stream>>>(g.tp, token, pos, g.cfg.seq_len, step);
 	++g_launches;
 }
@@ -936,6 +951,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.use_graph = !(getenv("CALM_B200_GRAPH") && atoi(getenv("CALM_B200_GRAPH")) == 0);
 	g.use_pdl = !(getenv("CALM_B200_PDL") && atoi(getenv("CALM_B200_PDL")) == 0);
 	if (getenv("CALM_B200_EARLY")) g.early = atoi(getenv("CALM_B200_EARLY"));
+	g.carveout = getenv("CALM_B200_CARVEOUT") ? atoi(getenv("CALM_B200_CARVEOUT")) : -1;
 	if (g.early < 0 || g.early > 2) g.early = 0;
 	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
 	if (g.debug) g.use_graph = false, g.debug_stages = true;
