@@ -107,7 +107,7 @@ struct Engine {
 	bool mma_up = false; // FFN-up on the tensor cores (k_ffn_up_mma)
 	int* tile_ctr = nullptr; // [n_layers] dynamic tile counters of k_ffn_up_mma (zeroed by k_embed every token)
 	int grid_up_mma = 0;
-	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + 288-thread k_ffn_up
+	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + k_ffn_up with 8 KB in flight per warp
 
 	// profiling (perf_cuda)
 	bool perf = false;
@@ -415,7 +415,7 @@ int run_token(int mode) {
 			if constexpr (DBITS != 4) {
 				if (g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
 			}
-			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, EARLY == 2 ? 288 : 256, g.smem_dim, a);
+			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -522,10 +522,7 @@ void make_plan() {
 			if (cdiv(c.dim / 2, grid * 8) > TP_MAX_ITERS) CALM_FATAL("tensor parallelism: grid %d outside the exchange tables for dim %d", grid, c.dim);
 	}
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
-	{ // EARLY == 2: 9-warp CTAs at 72 registers -- 3996 resident warps instead of 3552, so that 14336 rows take 4 rounds, not 4.04
-		const int threads_up = EARLY == 2 ? 288 : 256;
-		g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, threads_up, g.smem_dim), cdiv(g.nact * c.hidden_dim, threads_up / 32));
-	}
+	g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
 	g.mma_up = false;
 	if constexpr (DBITS != 4) { // tensor-core FFN-up (stages.cuh k_ffn_up_mma): dense, whole k-blocks per warp
 		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : false;

@@ -259,7 +259,7 @@ struct QkvArgs {
 
 // EARLY: what a warp does about its first row pair BEFORE waiting for the previous kernel and staging the activations
 // (weights are immutable, so this is always legal): 0 nothing; 1 ask the L2 for the rows (cp.async.bulk.prefetch.L2,
-// no registers); 2 the same, and k_ffn_up runs 288-thread CTAs at 72 registers (3 per SM: 27 warps instead of 24).
+// no registers); 2 the same, and k_ffn_up keeps 8 vectors per row in flight at 2 CTAs per SM instead of 4 at 3.
 // (Issuing the first loads into registers instead was measured 25 % slower: 32 more live registers across the
 // staging cost a CTA per SM or spills.)
 template <int DBITS, typename KVT, int EARLY>
@@ -840,7 +840,7 @@ struct FfnUpArgs {
 };
 
 template <int DBITS, int EARLY>
-__global__ void __launch_bounds__(EARLY == 2 ? 288 : 256, 3) k_ffn_up(const FfnUpArgs a) {
+__global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpArgs a) {
 	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	__shared__ float glog[64];
@@ -895,7 +895,10 @@ __global__ void __launch_bounds__(EARLY == 2 ? 288 : 256, 3) k_ffn_up(const FfnU
 		size_t off = (a.n_experts ? (size_t)ssel.expert[e] * esize : 0) + (size_t)i * nvec;
 		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w1) + off, reinterpret_cast<const uint4*>(a.w3) + off};
 		float v[2];
-		warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
+		if constexpr (EARLY == 2 && DBITS != 4) // the whole row pair in one round trip: 8 KB per warp, 2 CTAs per SM
+			warp_dot_rows<DBITS, 2, 8>(rp, nvec, xs4, v);
+		else
+			warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
 		if (lane == 0) a.hb[p] = (a.gelu ? act_gelu(v[0]) : act_silu(v[0])) * v[1];
 	}
 }
