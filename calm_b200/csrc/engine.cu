@@ -525,7 +525,8 @@ void make_plan() {
 	g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
 	g.mma_up = false;
 	if constexpr (DBITS != 4) { // tensor-core FFN-up (stages.cuh k_ffn_up_mma): dense, whole k-blocks per warp
-		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : false;
+		// measured (profiles/README.md): +2.6 % tokens/s with fp16 weights, -1 % with fp8, so it is on by default for fp16 only
+		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : DBITS == 16;
 		if (want && c.n_experts == 0 && c.dim % (32 * WFmt<DBITS>::VW) == 0 && c.hidden_dim % 8 == 0 && c.dim <= 16384) {
 			g.mma_up = true;
 			g.grid_up_mma = imin(max_ctas(k_ffn_up_mma<DBITS>, 256, g.smem_dim), c.hidden_dim / 8);
