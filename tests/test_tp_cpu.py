@@ -73,3 +73,33 @@ def test_id_file_handoff(tmp_path):
     assert tp.wait_id(path, 1.0) == ident
     with pytest.raises(TimeoutError):
         tp.wait_id(str(tmp_path / "missing"), 0.2)
+
+
+@pytest.mark.parametrize("d,grid", [(4096, 256), (8192, 256), (8192, 296), (512, 32), (256, 16), (4096, 148), (5120, 160), (896, 56)])
+def test_exchange_row_map_covers_every_row_once(d, grid):
+    """Index arithmetic of the in-kernel all-reduce (stages.cuh tp_exchange_add / k_matres): CTA b handles row pairs
+    p = b*8 + w + it*grid*8 (w = warp 0..7); the exchange addresses its partial as cell it*16 + k <-> row
+    2*((it*grid + b)*8) + k, with niter = ceil((d/2 - b*8) / (grid*8)) iterations.  Every row below d must be pushed and
+    summed exactly once, and both formulas must agree on which rows a CTA owns."""
+    per = grid * 8
+    seen = np.zeros(d, np.int32)
+    for b in range(grid):
+        niter = max(0, -(-(d // 2 - b * 8) // per))
+        # rows the matvec loop of this CTA produces (lane 0 of warp w stores v[0], v[1] at part[it*16 + w*2 + {0,1}])
+        produced = {}
+        for w in range(8):
+            it, p = 0, b * 8 + w
+            while p < d // 2:
+                produced[it * 16 + w * 2] = 2 * p
+                produced[it * 16 + w * 2 + 1] = 2 * p + 1
+                p += per
+                it += 1
+        # rows the exchange believes those cells are
+        for j in range(niter * 16):
+            row = 2 * (((j >> 4) * grid + b) * 8) + (j & 15)
+            if row < d:
+                assert produced.get(j) == row, (b, j)
+                seen[row] += 1
+        assert all((j >> 4) < niter for j in produced), "a produced cell lies beyond the iterations the exchange walks"
+    assert np.all(seen == 1)
+    assert -(-(d // 2) // per) <= 16  # TP_MAX_ITERS
