@@ -43,7 +43,7 @@ for binary in ("run_ref", "run_b200"):
         env.pop("CALM_CPU", None)
         if poso:
             env["CALM_POSO"] = poso
-        for engine in ((None,) if binary == "run_ref" else ("0", "2")):
+        for engine in ((None,) if binary == "run_ref" else tuple(os.environ.get("REF_BENCH_ENGINES", "0,2").split(","))):
             if engine is not None:
                 env["CALM_B200_ENGINE"] = engine
             r = subprocess.run([exe, path, "-n", str(n), "-t", "0", "-i", "<|t5|>"], capture_output=True, text=True, env=env, timeout=600)
