@@ -80,3 +80,65 @@ def test_device_sampler_follows_the_restatement(oracle_pkg, temperature, minp):
         assert rg == 77 and list(g) == list(dm.decode_greedy(5, 0, 8))
     finally:
         dm.close()
+
+
+def _device_algorithm(logits, temperature, minp, rng_state, chunk=1024, exact=2048):
+    """Python mirror of k_sample_scan + k_sample_pick (stages.cuh): chunked compaction in index order, then the exact walk
+    (<= `exact` survivors) or the chunk-sum walk.  float32 arithmetic step by step, like the one device thread."""
+    f = np.float32
+    s = rng_state
+    s ^= s >> 12
+    s ^= (s << 25) & 0xFFFFFFFFFFFFFFFF
+    s ^= s >> 27
+    coin = f(((s * 0x2545F4914F6CDD1D & 0xFFFFFFFFFFFFFFFF) >> 32) >> 8) / f(16777216.0)
+    mx = f(logits.max())
+    cutoff = f(mx + f(f(np.log(f(minp))) * f(temperature)))
+    chunks = []
+    for c0 in range(0, len(logits), chunk):
+        l = logits[c0:c0 + chunk]
+        keep = np.nonzero(l >= cutoff)[0]
+        probs = np.exp(((l[keep] - mx) / f(temperature)).astype(f)).astype(f)
+        csum = f(0)
+        for p in probs:
+            csum = f(csum + p)
+        chunks.append((keep + c0, probs, csum))
+    total = sum(len(k) for k, _, _ in chunks)
+    fallback = max((int(k[-1]) for k, _, _ in chunks if len(k)), default=0)
+    cum = f(0)
+    if total <= exact:
+        for _, probs, _ in chunks:
+            for p in probs:
+                cum = f(cum + p)
+    else:
+        for _, _, cs in chunks:
+            cum = f(cum + cs)
+    r = f(coin * cum)
+    cdf = f(0)
+    for idx, probs, cs in chunks:
+        if total > exact and not (r < f(cdf + cs)):
+            cdf = f(cdf + cs)
+            continue
+        for i, p in zip(idx, probs):
+            cdf = f(cdf + p)
+            if r < cdf:
+                return int(i), s
+    return fallback, s
+
+
+@pytest.mark.parametrize("vocab,scale", [(1000, 0.3), (4128, 0.3), (4128, 4.0), (9000, 0.2)])
+def test_device_sampling_algorithm_agrees_with_the_restatement(oracle_pkg, vocab, scale):
+    """The chunked algorithm the device kernels implement (several chunks, a ragged last chunk, the chunk-sum path beyond
+    2048 survivors) against oracle_sample on the same logits: identical draws up to a stray bin edge."""
+    rng = np.random.default_rng(vocab)
+    agree = n = 0
+    for t, m in [(1.0, 0.1), (0.7, 0.02)]:
+        ref = oracle_pkg.Sampler("port", t, m, 42)
+        state = 42
+        for _ in range(40):
+            logits = (rng.standard_normal(vocab) * scale).astype(np.float32)
+            tok, state = _device_algorithm(logits, t, m, state)
+            want = ref.sample(logits)
+            assert state == ref.rng_state
+            agree += int(tok == want)
+            n += 1
+    assert agree >= n - 1, (agree, n)
