@@ -19,8 +19,10 @@ Printed JSON (one line, rank 0):
   cpu_baseline  the reference's CPU implementation (oracle/_ref, or the oracle port) on this box's cores,
              bounded sample of the same workload.  Reported, not a target.
 With --impl reference the same metric is measured on the reference's CPU path only (no product code).
-For N > 1 every rank decodes its own sequence on its own GPU (replicas: the 8B model fits one GPU and the
-path has no exchange step at this size); value is the aggregate, "scaling": "weak".
+For N > 1 the N GPUs serve ONE token stream, tensor-parallel (--parallel tp, the default): every rank holds 1/N of the
+heads and FFN rows, the two partial projections per layer are summed inside k_matres over NVLink peer memory, the
+classifier is split by vocabulary; "scaling": "strong".  --parallel replicas runs N independent copies instead
+("scaling": "weak", no data-path collective).
 """
 from __future__ import annotations
 
@@ -62,7 +64,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -76,12 +78,12 @@ class ClockSampler:
     def stop(self, t0: float, t1: float):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         for ts, line in self.lines:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 8 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+            if len(f) < 8 or not (t0 <= ts <= t1 + 0.03):  # a line is printed up to one period after its sample
                 continue
             try:
                 sm.append(float(f[1]))
@@ -146,17 +148,44 @@ def host_model(spec, seed):
     return mg.HostModel(spec, tensors=t, seq_len=4096 if spec.max_seq_len >= 4096 else None)
 
 
-def cpu_tokens_per_s(spec, seed, n_tokens, warmup, pos0, budget_s=None, model=None):
-    """Time the reference CPU forward() (oracle/_ref when it travelled, else the oracle port) on all host
-    threads.  Returns (tok/s, kind, threads, n_timed)."""
+def numa_spread(model, threads):
+    """Re-home the big weight tensors so that each OpenMP thread first-touches the rows it will later read (the
+    reference's matmul splits rows statically over threads, infer.c:209-221): without this every page sits on the
+    NUMA node of the thread that generated the model and a 2-socket host swings 9x between runs."""
+    import ctypes as C
+
+    import oracle
+    import torch
+
+    lib = C.CDLL(oracle._PATHS["port"])
+    if not hasattr(lib, "oracle_parallel_copy"):
+        return
+    lib.oracle_parallel_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    for name, t in list(model.tensors.items()):
+        if t.dim() < 2 or t.numel() * t.element_size() < (1 << 22):
+            continue
+        rows = int(np.prod(t.shape[:-1]))
+        dst = torch.empty_like(t)  # untouched pages
+        lib.oracle_parallel_copy(dst.data_ptr(), t.data_ptr(), rows, t.shape[-1] * t.element_size())
+        model.tensors[name] = dst
+    model.rebind()
+
+
+def cpu_tokens_per_s(spec, seed, n_tokens, warmup, pos0, budget_s=None, model=None, threads=None):
+    """Time the reference CPU forward() (oracle/_ref when it travelled, else the oracle port).
+    Returns (tok/s, kind, threads, n_timed).  OMP_NUM_THREADS is ASSIGNED (torchrun exports 1 to its children)."""
     import oracle
 
     kind = "reference" if oracle.available("reference") else "port"
     if kind == "port" and not oracle.available("port"):
         oracle.build(ref=False)
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))  # reference default is nproc/2 (infer.c:171-176); use all
+    threads = threads or (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.setdefault("OMP_PROC_BIND", "true")
     model = model or host_model(spec, seed)
+    if not getattr(model, "_spread", False):
+        numa_spread(model, threads)
+        model._spread = True
     ck = oracle.Checker(kind)
     ck.prepare(model)
     tok = 17
@@ -171,7 +200,7 @@ def cpu_tokens_per_s(spec, seed, n_tokens, warmup, pos0, budget_s=None, model=No
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return done / dt, kind, int(os.environ["OMP_NUM_THREADS"]), done
+    return done / dt, kind, threads, done
 
 
 def run_reference_arm(args, spec):
@@ -195,9 +224,13 @@ def run_reference_arm(args, spec):
 
 
 def workload_config(spec, pos0, args):
+    from calm_b200 import modelgen as mg
+
+    per_gpu = mg.algorithmic_bytes(spec) / (args.gpus if (args.gpus > 1 and args.parallel == "tp") else 1)
     return {"workload": f"{spec.name}: {spec.n_layers} layers, dim {spec.dim}, hidden {spec.hidden_dim}, heads {spec.n_heads}/{spec.n_kv_heads}x{spec.head_dim}, "
                         f"vocab {spec.vocab_size}, {spec.dtype} weights, fp16 KV cache, context 4096, batch 1",
-            "positions": f"{pos0}..{pos0 + args.steps + args.warmup - 1} (KV cache pre-filled to pos0)", "l2": "inputs (7.5 GB of weights per step) exceed the 126 MB L2; no flush",
+            "positions": f"{pos0}..{pos0 + args.steps + args.warmup - 1} (KV cache pre-filled to pos0)",
+            "l2": f"inputs ({per_gpu / 1e9:.2f} GB of weights per step and GPU) exceed the 126 MB L2; no flush",
             "parallelism": "single GPU" if args.gpus <= 1 else (f"tp{args.gpus}" if args.parallel == "tp" else "replicas")}
 
 
@@ -210,13 +243,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="llama3-8b-fp8")
-    ap.add_argument("--engine", type=int, default=None)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
-    ap.add_argument("--parallel", default="replicas", choices=["replicas", "tp"],
-                    help="N>1: independent replicas (weak scaling, no data-path collective; default) or ONE token stream "
-                         "tensor-parallel over the N GPUs (strong scaling; two NCCL all-reduces per layer)")
+    ap.add_argument("--parallel", default="tp", choices=["replicas", "tp"],
+                    help="N>1: ONE token stream tensor-parallel over the N GPUs (strong scaling; the two all-reduces per layer run "
+                         "inside k_matres over NVLink peer memory; default) or independent replicas (weak scaling, no data-path collective)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference infer.cu (oracle/_ref/libcalm_ref_cuda.so) on this GPU")
     ap.add_argument("--layers", type=int, default=None, help="(debug) override the layer count")
     ap.add_argument("--pos0", type=int, default=None, help="(debug) first timed position instead of the end of the context")
     args = ap.parse_args()
@@ -268,7 +301,7 @@ def main():
     is_tp = tp is not None
     tensors = mg.generate(spec, args.seed + (0 if is_tp else rank), device="cuda")  # TP ranks hold the SAME model
     torch.cuda.synchronize()
-    dm = lib.DeviceModel(spec, tensors, seq_len=seq_len, device=local, engine=args.engine, tp=tp)
+    dm = lib.DeviceModel(spec, tensors, seq_len=seq_len, device=local, tp=tp)
     K, W = args.steps, args.warmup
     pos0 = max(0, seq_len - (K + W)) if args.pos0 is None else args.pos0
     dm.fill_kv(min(pos0, seq_len), seed=1 + rank)
@@ -290,7 +323,6 @@ def main():
     barrier()
     t_wall1 = time.time()
     launches = int(L.calm_b200_launch_count() - l0)
-    clocks = sampler.stop(t_wall0, t_wall1)
     ms = max_over_ranks(ms)
     value = K / (ms / 1e3) if is_tp else agg.whole_job_rate(K, ms)  # TP: the N GPUs serve ONE token stream
 
@@ -307,24 +339,14 @@ def main():
         tok = int(np.argmax(np.ctypeslib.as_array(p, shape=(spec.vocab_size,))))
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop(t_wall0, time.time())  # both timed regions (device loop, then host-stepped loop)
     barrier()
     e2e = K / e2e_s if is_tp else agg.whole_job_rate(K, e2e_s * 1e3)
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel (per GPU: under tensor parallelism a rank streams 1/N of the layers and of the classifier)
     peak, peak_src = measured_peak()
-    if is_tp:
-        # per GPU: 1/N of every layer's weights and KV entries, the whole (replicated) classifier; the unit is the token
-        cls_b = spec.vocab_size * spec.dim * spec.dbits / 8
-        per_gpu = (bytes_per_tok - cls_b) / world + cls_b
-        roof = {"bound": "hbm", "kernel": f"whole token on one of {world} tensor-parallel GPUs (staged kernels + 2 all-reduces per layer)",
-                "achieved": per_gpu / 1e9 / (ms / K / 1e3), "peak": peak, "unit": "GB/s", "frac": per_gpu / 1e9 / (ms / K / 1e3) / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu}
-        try:  # per-stage event timing of this rank's shard (eager launches; wo / w2 include the exchange wait)
-            roof["stages"] = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src, ms / K, bytes_per_tok)["stages"]
-        except Exception as e:
-            roof["stages"] = f"unavailable: {e}"
-    else:
-        roof = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src, ms / K, bytes_per_tok)
+    per_gpu = bytes_per_tok / (world if is_tp else 1)
+    roof = dm_roofline(dm, L, spec, seq_len - 16, peak, peak_src, ms / K, per_gpu)
 
     out = {
         "metric": "tok/s single-batch decode", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -332,18 +354,44 @@ def main():
         "data": "synthetic", "config": workload_config(spec, pos0, args),
         "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": spec.vocab_size * 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-        "algorithmic_gb_per_token": bytes_per_tok / 1e9, "hbm_gbs_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3),
-        "frac_of_peak_whole_token": bytes_per_tok / 1e9 / (ms / K / 1e3) / peak, "engine": "fused" if dm.uses_fused() else "staged", "tp_mode": {0: None, 1: "ncclAllReduce between kernels", 2: "all-reduce inside k_matres over peer memory"}[L.calm_b200_tp_mode()],
+        "algorithmic_gb_per_token": bytes_per_tok / 1e9, "algorithmic_gb_per_token_per_gpu": per_gpu / 1e9, "hbm_gbs_whole_token_per_gpu": per_gpu / 1e9 / (ms / K / 1e3),
+        "frac_of_peak_whole_token": per_gpu / 1e9 / (ms / K / 1e3) / peak, "tp_mode": {0: None, 1: "ncclAllReduce between kernels", 2: "all-reduce inside k_matres over peer memory"}[L.calm_b200_tp_mode()],
     }
     dm.close()
 
+    if rank == 0 and world == 1 and not args.no_ref_cuda and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcalm_ref_cuda.so")):
+        # the kernel to beat: the UNMODIFIED reference infer.cu on this GPU, same model, same positions, same
+        # host-stepped protocol as the e2e leg; its own process (global statics, abort() on error), after ours released the device
+        try:
+            del tensors
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_cuda_worker.py"), "--spec", args.workload, "--seq-len", str(seq_len), "--seed", str(args.seed),
+                                "--bench", f"{pos0},{W},{K}"] + (["--layers", str(args.layers)] if args.layers else []), capture_output=True, text=True, timeout=600, cwd=ROOT)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode == 0 and line:
+                rc = json.loads(line[-1])
+                out["ref_cuda"] = {"e2e_tok_s": rc["tok_s"], "ms_per_step": rc["ms_per_step"], "ours_e2e_over_ref": e2e / rc["tok_s"],
+                                   "what": "unmodified reference src/infer.cu (sm_100a build, oracle/_ref/libcalm_ref_cuda.so): forward_cuda per token, host argmax, same model and positions as e2e"}
+            else:
+                out["ref_cuda"] = {"unavailable": (r.stderr or r.stdout)[-300:]}
+            tensors = None
+        except Exception as e:
+            out["ref_cuda"] = {"unavailable": str(e)}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
+            if tensors is None:
+                tensors = mg.generate(spec, args.seed, device="cuda")
             hm = mg.HostModel(spec, tensors=tensors, seq_len=seq_len)
             del tensors
-            tps, kind, threads, done = cpu_tokens_per_s(spec, args.seed, 10 ** 6, 1, seq_len - 64, budget_s=args.cpu_budget, model=hm)
+            ncpu = os.cpu_count() or 1
+            tps, kind, threads, done = cpu_tokens_per_s(spec, args.seed, 10 ** 6, 1, seq_len - 64, budget_s=args.cpu_budget / 2, model=hm, threads=ncpu)
+            tps2, _, threads2, done2 = cpu_tokens_per_s(spec, args.seed, 10 ** 6, 1, seq_len - 64, budget_s=args.cpu_budget / 2, model=hm, threads=max(1, ncpu // 2))
+            if tps2 > tps:
+                tps, threads, done, tps2, threads2, done2 = tps2, threads2, done2, tps, threads, done
             out["cpu_baseline"] = {"value": tps, "unit": "tok/s", "cores": threads, "kind": kind,
-                                   "sample": f"{done} tokens at pos {seq_len - 63}.. of the same model ({args.cpu_budget:.0f} s budget), {threads} threads"}
+                                   "sample": f"{done} tokens at pos {seq_len - 63}.. of the same model ({args.cpu_budget / 2:.0f} s budget), {threads} threads, rows first-touched by "
+                                             f"the thread that reads them; the other setting ({threads2} threads; reference default is nproc/2, infer.c:171-176): {tps2:.2f} tok/s"}
         except Exception as e:  # the baseline is reported, never required
             out["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
@@ -353,32 +401,21 @@ def main():
 
 
 def dm_roofline(dm, L, spec, pos, peak, peak_src, ms_per_tok, bytes_per_tok):
-    """Roofline of the dominant kernel.
-
-    Fused engine: ONE kernel (k_fused) runs the whole token, so the dominant kernel is that launch:
-    achieved = algorithmic bytes per launch (n_bandwidth + KV bytes, reference run.c:161-165, 523-532) /
-    mean launch duration, measured live with CUDA events over the timed region of leg 1.  The per-stage
-    table comes from %globaltimer stamps inside the kernel (8 extra tokens after the timed legs).
-    Staged engine: the dominant kernel is the stage with the largest share of the token's time, timed with
-    CUDA events around every launch (8 eager tokens)."""
-    fused = dm.uses_fused()
-    stats = dm.profile(23, pos, 8, mode=2 if fused else 1)
+    """Roofline of the dominant kernel: the stage with the largest share of the token's time.  Launch durations come from
+    %globaltimer stamps INSIDE the kernels of the production CUDA graph (first CTA past its dependency wait -> last CTA
+    done; 8 extra tokens after the timed legs), so they describe the graph + PDL path that produced `value`."""
+    stats, span_ms = dm.profile(23, pos, 8)
     total_ms = sum(v[0] for v in stats.values()) or 1.0
     table = {k: {"share": v[0] / total_ms, "us_per_launch": v[0] / max(v[2], 1) * 1e3, "gbs": (v[1] / 1e9 / (v[0] / 1e3)) if v[0] > 0 else None,
-                 "barrier_wait_us": v[3] / max(v[2], 1) * 1e3, "load_x_us": v[4] / max(v[2], 1) * 1e3, "tile_wait_us": v[5] / max(v[2], 1) * 1e3}
-             for k, v in stats.items()}
-    if fused:
-        achieved = bytes_per_tok / 1e9 / (ms_per_tok / 1e3)
-        return {"bound": "hbm", "kernel": "k_fused (persistent: all layers + classifier of one token)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_tok, "us_per_launch": ms_per_tok * 1e3,
-                "stages": table}
-    # the dominant kernel is chosen among the matvec stages by share of the token's time
-    name, (ms, by, nl, *_) = max(((k, v) for k, v in stats.items() if v[1] > 0), key=lambda kv: kv[1][0])
+                 "frac": (v[1] / 1e9 / (v[0] / 1e3) / peak) if v[0] > 0 else None}
+             for k, v in stats.items() if v[2] > 0}
+    name, (ms, by, nl) = max(((k, v) for k, v in stats.items() if v[1] > 0), key=lambda kv: kv[1][0])
     achieved = by / 1e9 / (ms / 1e3) if ms > 0 else None
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture in profiles/ (r01: k_ffn_up<8> on this workload)
-    traffic = 117.53e6 + 5.33e6 if (name == "matmul_ffn_up" and spec.name == "llama3-8b-fp8") else None  # profiles/r01_ncu_full_one_layer_staged.csv
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch: not measurable in-run; the figure of the committed ncu capture is quoted with its source
+    traffic, traffic_src = (117.53e6 + 5.33e6, "profiles/r01_ncu_full_one_layer_staged.csv (k_ffn_up<8>, Llama-3-8B fp8)") if (name == "matmul_ffn_up" and spec.name == "llama3-8b-fp8") else (None, None)
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by / max(nl, 1), "us_per_launch": ms / max(nl, 1) * 1e3, "stages": table}
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": by / max(nl, 1), "us_per_launch": ms / max(nl, 1) * 1e3,
+            "timing": "in-kernel %globaltimer stamps, production graph", "token_span_us_profiled": span_ms * 1e3, "stages": table}
 
 
 if __name__ == "__main__":

@@ -14,12 +14,11 @@
 
 #include <vector>
 
-#include "fused.cuh"
-#include "persist.cuh"
 #include "stages.cuh"
 
 namespace {
 
+#define MAX_STAMPS (2 + 5 * MAX_LAYERS)
 enum Stage { ST_EMBED, ST_QKV, ST_ATTN, ST_WO, ST_FFN_UP, ST_FFN_DOWN, ST_OUTPUT, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"embed", "matmul_qkv", "attention", "matmul_attn", "matmul_ffn_up", "matmul_ffn_down", "output"};
 
@@ -58,23 +57,16 @@ struct Engine {
 	size_t smem_dim = 0, smem_qdim = 0, smem_hidden = 0;
 	int cur_kv_len = 0; // host copy, for the perf table only
 	int cur_pos = 0;
-	int engine = 1;
-	bool debug_stages = false;
 	int attn_nsplit_cap = 1 << 30;
 
-	// fused engine (engine kind 1)
-	bool fused_ok = false;   // model/configuration is served by the persistent kernel
-	bool fused_attr_set = false;
-	int fused_xr = 64;
-	int fused_slot_bytes = 0, fused_nslots = 0, fused_scratch = 0, fused_xbuf = 0, fused_nwbuf = 0;
-	size_t fused_smem = 0;
-	int fused_nsplit = 1;
-	unsigned* fused_bar = nullptr;
-	int* fused_err = nullptr; // pinned + mapped
-	unsigned long long* fused_perf_ns = nullptr; // device [32]
-	bool fused_perf = false;
-	cudaGraphExec_t fgraph[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-	int fgraph_launches[5] = {0, 0, 0, 0, 0};
+	// L2 prefetch schedule (common.cuh Prefetch): what each stage requests for the stages after it.  Bytes, or flags.
+	bool pf_kv = true;            // k_qkv / w2 request the KV prefix the next attention kernel reads
+	bool pf_attn_wo = true;       // k_attn requests wo
+	size_t pf_attn_up = 40 << 20; // ... and this much of w1 + w3
+	size_t pf_wo_up = 0;          // wo requests this much more of w1 + w3
+	size_t pf_up_down = 0;        // k_ffn_up requests this much of w2
+	bool pf_down_qkv = true;      // w2 requests the next layer's wq / wk / wv
+
 
 	// tensor parallelism (staged engine): this process owns 1/tp_world of the heads and of the FFN rows
 	int tp_rank = 0, tp_world = 1;
@@ -86,14 +78,11 @@ struct Engine {
 	int* tp_err = nullptr;           // mapped host word for the exchange watchdog
 	std::vector<void*> tp_owned;     // shard copies made by prepare_cuda (wo / w2 column slices, packed biases)
 
-	// persistent engine (engine kind 2)
-	bool persist_ok = false;
-	size_t persist_smem = 0;
-	int persist_nsplit = 1;
 
-	// graphs: 0 = kv only, 1 = logits to host, 2 = logits to device + greedy advance, 3 = logits to host + argmax
-	cudaGraphExec_t graph[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // per call mode: 0 KV only, 1 logits to host, 2 greedy loop, 3 logits + argmax, 4 min-p sampling loop
-	int graph_launches[5] = {0, 0, 0, 0, 0};
+	// one graph per call mode: 0 KV only, 1 logits to host, 2 greedy loop, 3 logits + argmax, 4 min-p sampling loop;
+	// [1][mode] = the same token with stage stamps (perf_cuda)
+	cudaGraphExec_t graph[2][5] = {};
+	int graph_launches[2][5] = {};
 	// device-side min-p sampler (stages.cuh k_sample_*)
 	SampleState* sample_state = nullptr;
 	int sample_chunks = 0;
@@ -109,22 +98,24 @@ struct Engine {
 	int grid_up_mma = 0;
 	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + k_ffn_up with 8 KB in flight per warp
 
-	// profiling (perf_cuda)
+	// profiling (perf_cuda): in-kernel %globaltimer stamps per launch of the production graph (stages.cuh stamp_begin/end)
 	bool perf = false;
 	bool debug = false;
+	unsigned long long* stamps = nullptr;    // device [MAX_STAMPS][2]: {min start, max end} of each launch of the current token
+	unsigned long long* stamp_acc = nullptr; // device [MAX_STAMPS + 2]: summed durations; [MAX_STAMPS] token span, [MAX_STAMPS + 1] tokens
+	int n_stamps = 0;                        // launches with a slot in the current token
+	int stamp_stage[MAX_STAMPS] = {};        // launch -> Stage
+	double stamp_bytes[MAX_STAMPS] = {};     // algorithmic bytes of that launch (KV bytes use the host copy of kv_len)
 	double stage_ms[ST_COUNT] = {};
 	double stage_bytes[ST_COUNT] = {};
 	long stage_launches[ST_COUNT] = {};
-	double stage_wait_ms[ST_COUNT] = {}; // fused engine: part of stage_ms spent waiting in the grid barrier
-	double stage_loadx_ms[ST_COUNT] = {}, stage_tilewait_ms[ST_COUNT] = {}; // ... loading the activation slice / waiting for tiles
+	double token_span_ms = 0;
 	int perf_runs = 0;
-	cudaEvent_t ev[2] = {nullptr, nullptr};
 	cudaEvent_t timer[2] = {nullptr, nullptr};
 };
 
 Engine g;
 int g_device_override = -1;
-int g_engine_kind = -1;
 uint64_t g_launches = 0;
 
 void select_device() {
@@ -148,9 +139,15 @@ void* dev_alloc(size_t bytes) {
 	return p;
 }
 
+// opt in to more than 48 KB of dynamic shared memory (once per kernel, with the LARGEST size any launch will use, outside stream capture)
+template <typename F>
+void smem_optin(F kernel, size_t smem) {
+	if (smem > 227 * 1024) CALM_FATAL("kernel needs %zu bytes of shared memory per CTA (limit 227 KB)", smem);
+	if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
 template <typename F>
 int max_ctas(F kernel, int block, size_t smem) {
-	if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
 	if (per_sm < 1) CALM_FATAL("kernel does not fit on an SM (block %d, %zu bytes of shared memory)", block, smem);
@@ -296,36 +293,62 @@ void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, Args
 // ---------------------------------------------------------------------------------------------
 // one token = this sequence of launches
 
-struct StageTimer {
-	bool on;
+// A stage launch: hands out the stamp slot when the profiling graph is being built (NULL in the production graph) and,
+// under CALM_B200_DEBUG=1, synchronises after the launch to name the stage that faults or hangs.
+struct StageScope {
 	Stage st;
-	StageTimer(Stage s, double bytes) : on(g.perf), st(s) {
-		if (on) {
-			CUDA_CHECK(cudaEventRecord(g.ev[0], g.stream));
-			g.stage_bytes[st] += bytes;
+	unsigned long long* slot = nullptr;
+	StageScope(Stage s, double bytes) : st(s) {
+		if (g.perf && g.n_stamps < MAX_STAMPS) {
+			g.stamp_stage[g.n_stamps] = s, g.stamp_bytes[g.n_stamps] = bytes;
+			slot = g.stamps + 2 * (size_t)g.n_stamps++;
 		}
 	}
-	~StageTimer() {
-		if (g.debug) { // CALM_B200_DEBUG=1: find the stage that faults or hangs
+	~StageScope() {
+		if (g.debug) {
 			cudaError_t e = cudaStreamSynchronize(g.stream);
 			fprintf(stderr, "calm_b200: stage %s -> %s\n", kStageNames[st], cudaGetErrorName(e));
-		}
-		if (on) {
-			CUDA_CHECK(cudaEventRecord(g.ev[1], g.stream));
-			CUDA_CHECK(cudaEventSynchronize(g.ev[1]));
-			float ms = 0;
-			CUDA_CHECK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
-			g.stage_ms[st] += ms;
-			g.stage_launches[st] += 1;
 		}
 	}
 };
 
+// end of a profiled token: fold the launch stamps into the running sums (one thread per slot)
+__global__ void k_stamp_accum(const unsigned long long* stamps, unsigned long long* acc, int n) {
+	pdl_enter();
+	__shared__ unsigned long long lo[256], hi[256];
+	unsigned long long mn = ~0ull, mx = 0;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		const unsigned long long b = stamps[2 * i], e = stamps[2 * i + 1];
+		if (b != ~0ull && e > b) {
+			acc[i] += e - b;
+			mn = b < mn ? b : mn, mx = e > mx ? e : mx;
+		}
+	}
+	lo[threadIdx.x] = mn, hi[threadIdx.x] = mx;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int i = 1; i < (int)blockDim.x; ++i) mn = lo[i] < mn ? lo[i] : mn, mx = hi[i] > mx ? hi[i] : mx;
+		if (mx > mn) acc[MAX_STAMPS] += mx - mn;
+		acc[MAX_STAMPS + 1] += 1;
+	}
+}
+
+// shared memory of k_attn<., HG>: the per-warp records of the in-CTA merge, or the coefficient tables of the slice merge
+size_t attn_smem(int hg, int head_dim, int nsplit) {
+	size_t smem = (size_t)(ATTN_THREADS / 32) * hg * (head_dim + 2) * sizeof(float);
+	size_t smem2 = (size_t)(2 * nsplit + 1) * hg * sizeof(float);
+	return smem2 > smem ? smem2 : smem;
+}
+
+// nl == NULL: only opt in to the shared-memory size (prepare time, outside stream capture; head_dim 256 with 8 query heads
+// per kv head needs 66 KB)
 template <typename KVT, int HG>
 void launch_attn(const AttnArgs& a, int nunits, int* nl) {
-	size_t smem = (size_t)(ATTN_THREADS / 32) * HG * (a.head_dim + 2) * sizeof(float);
-	size_t smem2 = (size_t)(2 * a.nsplit + 1) * HG * sizeof(float);
-	if (smem2 > smem) smem = smem2;
+	const size_t smem = attn_smem(HG, a.head_dim, a.nsplit);
+	if (!nl) {
+		smem_optin(k_attn<KVT, HG>, smem);
+		return;
+	}
 	launch_pdl(k_attn<KVT, HG>, nunits * a.nsplit, ATTN_THREADS, smem, a);
 	++*nl;
 }
@@ -344,7 +367,16 @@ void dispatch_attn(const AttnArgs& a, int nunits, int* nl) {
 	}
 }
 
-// mode: 0 kv only, 1 logits -> host, 2 logits -> device + advance (greedy loop), 3 logits -> host + argmax
+// first `budget` bytes of the (w1, w3) row interleave that k_ffn_up walks: half from each matrix (row prefixes)
+static void pf_up_prefix(Prefetch& pf, int slot, const void* w1, const void* w3, size_t skip, size_t budget, size_t matrix_bytes) {
+	size_t off = (skip / 2) & ~(size_t)15, len = (budget / 2) & ~(size_t)15;
+	if (off >= matrix_bytes) return;
+	if (off + len > matrix_bytes) len = matrix_bytes - off;
+	pf.p[slot] = (const char*)w1 + off, pf.bytes[slot] = len;
+	pf.p[slot + 1] = (const char*)w3 + off, pf.bytes[slot + 1] = len;
+}
+
+// mode: 0 kv only, 1 logits -> host, 2 logits -> device + advance (greedy loop), 3 logits -> host + argmax, 4 logits -> device + min-p sample + advance
 template <int DBITS, typename KVT, int EARLY>
 int run_token(int mode) {
 	const Config& c = g.cfg;
@@ -352,47 +384,66 @@ int run_token(int mode) {
 	const int dim = c.dim, hidden = c.hidden_dim, hd = c.head_dim;
 	const size_t wb = (size_t)DBITS; // bits per weight
 	int nl = 0;
+	g.n_stamps = 0;
+	const size_t kv_layer = (size_t)c.n_kv_heads * c.seq_len * hd; // elements per layer
+	const size_t qkv_bytes[3] = {(size_t)g.q_dim * dim * wb / 8, (size_t)g.kv_dim * dim * wb / 8, (size_t)g.kv_dim * dim * wb / 8};
+	const size_t wo_bytes = (size_t)dim * g.q_dim * wb / 8, up_bytes = (size_t)hidden * dim * wb / 8 /* per matrix (and expert) */, down_bytes = up_bytes;
+	const bool dense = c.n_experts == 0;
+	auto kv_prefix = [&](Prefetch& pf, int l) {
+		pf.kc = (KVT*)g.kc + l * kv_layer, pf.vc = (KVT*)g.vc + l * kv_layer;
+		pf.kv_rowbytes = hd * (int)sizeof(KVT), pf.kv_heads = c.n_kv_heads, pf.kv_head_stride = (unsigned long long)c.seq_len * hd * sizeof(KVT);
+	};
+	auto qkv_weights = [&](Prefetch& pf, int l) {
+		pf.p[0] = w.wq[l], pf.bytes[0] = qkv_bytes[0], pf.p[1] = w.wk[l], pf.bytes[1] = qkv_bytes[1], pf.p[2] = w.wv[l], pf.bytes[2] = qkv_bytes[2];
+	};
 
 	{
-		StageTimer t(ST_EMBED, 0);
-		EmbedArgs<KVT> a;
+		StageScope t(ST_EMBED, 0);
+		EmbedArgs<KVT> a = {};
 		a.x = g.x, a.table = w.token_embedding_table, a.tp = g.tp, a.dim = dim;
 		a.embed_blocks = cdiv(dim, 256);
 		a.tile_ctr = g.tile_ctr, a.n_ctr = c.n_layers;
 		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq;
 		a.n_layers = c.n_layers, a.n_kv_heads = c.n_kv_heads, a.head_dim = hd, a.seq_len = c.seq_len;
+		a.stamp = nullptr, a.stamp_reset = g.perf ? g.stamps : nullptr, a.n_stamps = MAX_STAMPS;
+		if (g.pf_down_qkv) qkv_weights(a.pf, 0);
 		launch_pdl(k_embed<DBITS, KVT>, a.embed_blocks + 8, 256, 0, a);
 		++nl;
 	}
 
-	const size_t kv_layer = (size_t)c.n_kv_heads * c.seq_len * hd; // elements per layer
-
 	for (int l = 0; l < c.n_layers; ++l) {
 		{
-			StageTimer t(ST_QKV, (double)(g.q_dim + 2 * g.kv_dim) * dim * wb / 8);
-			QkvArgs<KVT> a;
+			StageScope t(ST_QKV, (double)(g.q_dim + 2 * g.kv_dim) * dim * wb / 8);
+			QkvArgs<KVT> a = {};
 			a.x = g.x, a.normw = w.rms_att_weight[l], a.wq = w.wq[l], a.wk = w.wk[l], a.wv = w.wv[l], a.bias = w.bqkv[l];
 			a.q_out = g.q, a.kc = (KVT*)g.kc + l * kv_layer, a.vc = (KVT*)g.vc + l * kv_layer;
 			a.rope_freq = g.rope_freq, a.xb_out = c.norm_par ? g.xb : nullptr, a.tp = g.tp;
 			a.dim = dim, a.q_dim = g.q_dim, a.kv_dim = g.kv_dim, a.head_dim = hd, a.seq_len = c.seq_len;
 			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln;
+			a.stamp = t.slot;
+			if (g.pf_kv && (l == 0 || !g.pf_down_qkv)) kv_prefix(a.pf, l); // later layers: requested by the previous w2 kernel
 			launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, 256, g.smem_dim, a);
 			++nl;
 		}
 		{
-			StageTimer t(ST_ATTN, 2.0 * g.kv_dim * g.cur_kv_len * (g.kvbits / 8));
-			AttnArgs a;
+			StageScope t(ST_ATTN, -1.0); // bytes depend on the position: accounted per token in launch_token()
+			AttnArgs a = {};
 			a.q = g.q, a.kc = (KVT*)g.kc + l * kv_layer, a.vc = (KVT*)g.vc + l * kv_layer;
 			a.partial = g.attn_partial, a.counter = g.attn_counter, a.out = g.att, a.tp = g.tp;
 			a.head_dim = hd, a.seq_len = c.seq_len, a.nsplit = g.attn_nsplit, a.lpp = g.attn_lpp;
 			a.kv_mul = g.kv_mul, a.qgroups = g.attn_qgroups;
 			a.inv_sqrt_hd = 1.0f / sqrtf((float)hd);
+			a.stamp = t.slot;
+			if (g.pf_attn_wo) a.pf.p[0] = w.wo[l], a.pf.bytes[0] = wo_bytes;
+			if (dense && g.pf_attn_up) pf_up_prefix(a.pf, 1, w.w1[l], w.w3[l], 0, g.pf_attn_up, up_bytes);
 			dispatch_attn<KVT>(a, c.n_kv_heads * g.attn_qgroups, &nl);
 		}
 		{
-			StageTimer t(ST_WO, (double)dim * g.q_dim * wb / 8);
+			StageScope t(ST_WO, (double)dim * g.q_dim * wb / 8);
 			MatResArgs a = {};
-			a.xin = g.att, a.w = w.wo[l], a.y = g.x, a.sel = nullptr, a.n = g.q_dim, a.d = dim, a.nact = 1, a.accumulate = 1;
+			a.xin = g.att, a.w = w.wo[l], a.y = g.x, a.sel = nullptr, a.n = g.q_dim, a.d = dim, a.nact = 1, a.accumulate = 1, a.tp = g.tp;
+			a.stamp = t.slot;
+			if (dense && g.pf_wo_up) pf_up_prefix(a.pf, 0, w.w1[l], w.w3[l], g.pf_attn_up, g.pf_wo_up, up_bytes);
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l); // partial over this rank's heads, summed over the ranks in the kernel
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
 			launch_pdl(k_matres<DBITS, EARLY>, g.grid_wo, 256, g.smem_qdim, a);
@@ -404,13 +455,15 @@ int run_token(int mode) {
 			}
 		}
 		{
-			StageTimer t(ST_FFN_UP, (double)2 * g.nact * hidden * dim * wb / 8);
-			FfnUpArgs a;
+			StageScope t(ST_FFN_UP, (double)2 * g.nact * hidden * dim * wb / 8);
+			FfnUpArgs a = {};
 			a.x = (c.norm_par ? g.xb : g.x), a.normw = c.norm_par ? nullptr : w.rms_ffn_weight[l];
 			a.gate = c.n_experts ? w.moegate[l] : nullptr, a.w1 = w.w1[l], a.w3 = w.w3[l], a.hb = g.hb, a.sel = g.moe_sel;
 			a.dim = dim, a.hidden = hidden, a.n_experts = c.n_experts, a.nact = g.nact;
 			a.eps = c.norm_eps, a.ln = c.norm_ln, a.gelu = c.act_gelu;
 			a.tile_ctr = g.tile_ctr ? g.tile_ctr + l : nullptr;
+			a.stamp = t.slot;
+			if (dense && g.pf_up_down) a.pf.p[0] = w.w2[l], a.pf.bytes[0] = (g.pf_up_down < down_bytes ? g.pf_up_down : down_bytes) & ~(size_t)15;
 			bool done = false;
 			if constexpr (DBITS != 4) {
 				if (g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
@@ -419,10 +472,15 @@ int run_token(int mode) {
 			++nl;
 		}
 		{
-			StageTimer t(ST_FFN_DOWN, (double)g.nact * hidden * dim * wb / 8);
+			StageScope t(ST_FFN_DOWN, (double)g.nact * hidden * dim * wb / 8);
 			MatResArgs a = {};
 			a.xin = g.hb, a.w = w.w2[l], a.y = g.x, a.sel = c.n_experts ? g.moe_sel : nullptr;
-			a.n = hidden, a.d = dim, a.nact = g.nact, a.accumulate = 1;
+			a.n = hidden, a.d = dim, a.nact = g.nact, a.accumulate = 1, a.tp = g.tp;
+			a.stamp = t.slot;
+			if (l + 1 < c.n_layers && g.pf_down_qkv) {
+				qkv_weights(a.pf, l + 1);
+				if (g.pf_kv) kv_prefix(a.pf, l + 1);
+			}
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
 			launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
@@ -435,15 +493,14 @@ int run_token(int mode) {
 		}
 	}
 
-	if (mode == 0) return nl;
-
-	{
-		StageTimer t(ST_OUTPUT, (double)c.vocab_size * dim * wb / 8);
-		OutputArgs a;
+	if (mode != 0) {
+		StageScope t(ST_OUTPUT, (double)c.vocab_size * dim * wb / 8);
+		OutputArgs a = {};
 		a.x = g.x, a.normw = w.rms_final_weight, a.wcls = w.wcls;
 		a.logits = (mode == 2 || mode == 4) ? g.logits_dev : g.logits_host;
 		a.cand_val = (mode >= 2) ? g.cand_val : nullptr, a.cand_idx = g.cand_idx;
 		a.dim = dim, a.vocab = c.vocab_size, a.eps = c.norm_eps, a.ln = c.norm_ln;
+		a.stamp = t.slot;
 		int grid = g.grid_out;
 		launch_pdl(k_output<DBITS>, grid, 256, g.smem_dim, a);
 		++nl;
@@ -458,6 +515,10 @@ int run_token(int mode) {
 			launch_pdl(k_advance, 1, 256, 0, (const float*)g.cand_val, (const int*)g.cand_idx, grid, g.tp, g.out_tokens, g.last_token, (int)(mode == 2), c.vocab_size);
 			++nl;
 		}
+	}
+	if (g.perf) {
+		launch_pdl(k_stamp_accum, 1, 256, 0, (const unsigned long long*)g.stamps, g.stamp_acc, g.n_stamps);
+		++nl;
 	}
 	return nl;
 }
@@ -513,8 +574,14 @@ void make_plan() {
 	g.smem_hidden = xs_bytes<DBITS>(c.hidden_dim);
 	size_t smem_res = g.smem_qdim > g.smem_hidden ? g.smem_qdim : g.smem_hidden;
 	if (smem_res > 227 * 1024 || g.smem_dim > 227 * 1024) CALM_FATAL("activation vector does not fit in shared memory (dim %d, hidden %d)", c.dim, c.hidden_dim);
+	smem_optin(k_qkv<DBITS, KVT, EARLY>, g.smem_dim), smem_optin(k_ffn_up<DBITS, EARLY>, g.smem_dim), smem_optin(k_output<DBITS>, g.smem_dim);
+	smem_optin(k_matres<DBITS, EARLY>, smem_res); // ONE attribute per kernel: the larger of its two launch shapes (wo, w2)
+	{
+		AttnArgs aa = {};
+		aa.head_dim = c.head_dim, aa.nsplit = g.attn_nsplit_cap;
+		dispatch_attn<KVT>(aa, 0, nullptr);
+	}
 	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT, EARLY>, 256, g.smem_dim));
-	max_ctas(k_matres<DBITS, EARLY>, 256, smem_res); // opt in to the larger of the two sizes
 	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_qdim));
 	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_hidden));
 	if (g.tp_fused) { // the in-kernel exchange needs co-resident grids (they are: balanced_grid stays under the cap) within its tables
@@ -529,6 +596,7 @@ void make_plan() {
 		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : DBITS == 16;
 		if (want && c.n_experts == 0 && c.dim % (32 * WFmt<DBITS>::VW) == 0 && c.hidden_dim % 8 == 0 && c.dim <= 16384) {
 			g.mma_up = true;
+			smem_optin(k_ffn_up_mma<DBITS>, g.smem_dim);
 			g.grid_up_mma = imin(max_ctas(k_ffn_up_mma<DBITS>, 256, g.smem_dim), c.hidden_dim / 8);
 		}
 	}
@@ -563,305 +631,32 @@ int run_token_any(int mode) {
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// fused engine: plan + launch
-
-template <int DBITS, int XR>
-void fused_launch_t(const FusedArgs& fa) {
-	if (!g.fused_attr_set) { // per model (the ring size depends on the shapes); first call comes from fused_plan()
-		CUDA_CHECK(cudaFuncSetAttribute(k_fused<DBITS, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.fused_smem));
-		g.fused_attr_set = true;
-		if (fa.dim == 0) return; // attribute-only call
-	}
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(g.sms), cfg.blockDim = dim3(FUSED_THREADS), cfg.dynamicSmemBytes = g.fused_smem, cfg.stream = g.stream;
-	cudaLaunchAttribute at[1];
-	at[0].id = cudaLaunchAttributeCooperative;
-	at[0].val.cooperative = 1;
-	cfg.attrs = at, cfg.numAttrs = 1;
-	CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_fused<DBITS, XR>, fa));
-}
-
-void fused_launch(const FusedArgs& fa) {
-	const int key = g.w.dbits * 1000 + g.fused_xr;
-	switch (key) {
-	case 8032: fused_launch_t<8, 32>(fa); break;
-	case 8064: fused_launch_t<8, 64>(fa); break;
-	case 16032: fused_launch_t<16, 32>(fa); break;
-	case 16064: fused_launch_t<16, 64>(fa); break;
-	case 4032: fused_launch_t<4, 32>(fa); break;
-	case 4064: fused_launch_t<4, 64>(fa); break;
-	default: CALM_FATAL("fused engine: no kernel for dbits %d / xr %d", g.w.dbits, g.fused_xr);
-	}
-}
-
-// Decide whether the persistent kernel can serve this model and size its ring.
-void fused_plan() {
-	const Config& c = g.cfg;
-	g.fused_ok = false;
-	if (c.n_experts || g.kvbits != 16) return; // MoE and fp8 KV: staged engine
-	const int vw = g.w.dbits == 16 ? 8 : (g.w.dbits == 8 ? 16 : 32);
-	int nvmax = (c.hidden_dim > g.q_dim ? c.hidden_dim : g.q_dim);
-	if (c.dim > nvmax) nvmax = c.dim;
-	nvmax /= vw;
-	int need_it = cdiv(nvmax, FUSED_NCW * 32);
-	if (need_it <= 32 / vw)
-		g.fused_xr = 32;
-	else if (need_it <= 64 / vw)
-		g.fused_xr = 64;
-	else
-		return;
-	// slot: must hold the smallest legal tile of every stage; prefer 32 KB
-	size_t rb_dim = (size_t)c.dim * g.w.dbits / 8, rb_q = (size_t)g.q_dim * g.w.dbits / 8, rb_hid = (size_t)c.hidden_dim * g.w.dbits / 8;
-	size_t need = 2 * rb_dim;
-	if (rb_q > need) need = rb_q;
-	if (rb_hid > need) need = rb_hid;
-	if ((size_t)4 * c.head_dim > need) need = (size_t)4 * c.head_dim;
-	size_t slot = 32 * 1024;
-	if (need > slot) slot = (need + 1023) & ~(size_t)1023;
-	g.fused_scratch = (int)(((size_t)FUSED_AW * g.attn_hg * (c.head_dim + 2) * sizeof(float) + 127) & ~(size_t)127);
-	{ // the last CTA of an attention unit also keeps 2 * nsplit * hg floats there
-		size_t need2 = (size_t)2 * g.sms * g.attn_hg * sizeof(float);
-		if (need2 > (size_t)g.fused_scratch) g.fused_scratch = (int)((need2 + 127) & ~(size_t)127);
-	}
-	// shared staging of the activation vector for stages whose rows are shared by fewer than all warps
-	auto staged_floats = [&](int n) {
-		int nvec = n / vw, itmax = g.fused_xr / vw, wg = 1;
-		while ((nvec + wg * 32 - 1) / (wg * 32) > itmax && wg < FUSED_NCW) wg *= 2;
-		return wg < FUSED_NCW ? n : 0;
-	};
-	int xf = staged_floats(c.dim);
-	if (staged_floats(g.q_dim) > xf) xf = staged_floats(g.q_dim);
-	if (staged_floats(c.hidden_dim) > xf) xf = staged_floats(c.hidden_dim);
-	g.fused_xbuf = (int)(((size_t)xf * sizeof(float) + 127) & ~(size_t)127);
-	g.fused_nwbuf = (int)(((size_t)c.dim * sizeof(float) + 127) & ~(size_t)127);
-	size_t fixed = ((sizeof(FusedShared) + 127) & ~(size_t)127) + g.fused_scratch + g.fused_xbuf + g.fused_nwbuf;
-	size_t avail = 227 * 1024 - fixed;
-	int nslots = (int)(avail / slot);
-	if (nslots > FUSED_MAX_SLOTS) nslots = FUSED_MAX_SLOTS;
-	if (getenv("CALM_B200_FUSED_SLOTS") && atoi(getenv("CALM_B200_FUSED_SLOTS")) >= 2 && atoi(getenv("CALM_B200_FUSED_SLOTS")) < nslots) nslots = atoi(getenv("CALM_B200_FUSED_SLOTS"));
-	if (nslots < 2) return;
-	g.fused_slot_bytes = (int)slot, g.fused_nslots = nslots;
-	g.fused_smem = fixed + (size_t)nslots * slot;
-	int units = c.n_kv_heads * g.attn_qgroups;
-	g.fused_nsplit = g.sms / units;
-	if (g.fused_nsplit < 1) return; // more (kv head, query group) units than SMs: staged engine
-	int maxsplit = cdiv(c.seq_len, 16);
-	if (g.fused_nsplit > maxsplit) g.fused_nsplit = maxsplit;
-	if (g.fused_nsplit > g.attn_nsplit_cap) g.fused_nsplit = g.attn_nsplit_cap;
-
-	FusedLayer layers[MAX_LAYERS] = {};
-	for (int l = 0; l < c.n_layers; ++l) {
-		layers[l].wq = g.w.wq[l], layers[l].wk = g.w.wk[l], layers[l].wv = g.w.wv[l], layers[l].wo = g.w.wo[l];
-		layers[l].w1 = g.w.w1[l], layers[l].w2 = g.w.w2[l], layers[l].w3 = g.w.w3[l];
-		layers[l].rms_att = g.w.rms_att_weight[l], layers[l].rms_ffn = g.w.rms_ffn_weight[l], layers[l].bqkv = g.w.bqkv[l];
-	}
-	CUDA_CHECK(cudaMemcpyToSymbol(c_fused_layers, layers, sizeof(layers)));
-	g.fused_bar = (unsigned*)dev_alloc(sizeof(unsigned));
-	CUDA_CHECK(cudaMemset(g.fused_bar, 0, sizeof(unsigned)));
-	CUDA_CHECK(cudaHostAlloc((void**)&g.fused_err, sizeof(int), cudaHostAllocMapped));
-	*g.fused_err = 0;
-	g.fused_perf_ns = (unsigned long long*)dev_alloc(32 * sizeof(unsigned long long));
-	CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 32 * sizeof(unsigned long long)));
-	g.fused_attr_set = false;
-	FusedArgs none = {};
-	fused_launch(none); // sets the shared-memory opt-in outside of any stream capture
-	g.fused_ok = true;
-}
-
-int run_token_fused(int mode) {
-	const Config& c = g.cfg;
-	FusedArgs fa = {};
-	fa.dim = c.dim, fa.hidden = c.hidden_dim, fa.q_dim = g.q_dim, fa.kv_dim = g.kv_dim, fa.head_dim = c.head_dim;
-	fa.n_heads = c.n_heads, fa.n_kv_heads = c.n_kv_heads, fa.n_layers = c.n_layers, fa.vocab = c.vocab_size, fa.seq_len = c.seq_len, fa.kv_mul = g.kv_mul;
-	fa.eps = c.norm_eps, fa.clip = c.qkv_clip, fa.ln = c.norm_ln, fa.norm_par = c.norm_par, fa.gelu = c.act_gelu;
-	fa.x = g.x, fa.xb = g.xb, fa.q = g.q, fa.att = g.att, fa.hb = g.hb;
-	fa.logits = (mode == 2) ? g.logits_dev : g.logits_host;
-	fa.attn_partial = g.attn_partial, fa.attn_counter = g.attn_counter;
-	fa.kc = (__half*)g.kc, fa.vc = (__half*)g.vc, fa.rope_freq = g.rope_freq;
-	fa.embed = g.w.token_embedding_table, fa.wcls = g.w.wcls, fa.rms_final = g.w.rms_final_weight;
-	fa.tp = g.tp, fa.bar = g.fused_bar, fa.err = g.fused_err;
-	fa.perf = g.fused_perf ? g.fused_perf_ns : nullptr;
-	fa.cand_val = (mode >= 2) ? g.cand_val : nullptr, fa.cand_idx = g.cand_idx;
-	fa.mode = mode;
-	fa.dbg = getenv("CALM_B200_FUSED_DBG") ? atoi(getenv("CALM_B200_FUSED_DBG")) : 0;
-	fa.slot_bytes = g.fused_slot_bytes, fa.nslots = g.fused_nslots;
-	fa.window = getenv("CALM_B200_FUSED_WINDOW") ? atoi(getenv("CALM_B200_FUSED_WINDOW")) : 3;
-	if (fa.window < 1) fa.window = 1;
-	if (fa.window > fa.nslots) fa.window = fa.nslots;
-	fa.attn_nsplit = g.fused_nsplit, fa.attn_hg = g.attn_hg, fa.attn_qgroups = g.attn_qgroups, fa.attn_lpp = g.attn_lpp;
-	fa.attn_scratch_bytes = g.fused_scratch;
-	fa.xbuf_bytes = g.fused_xbuf, fa.nwbuf_bytes = g.fused_nwbuf;
-	fa.inv_sqrt_hd = 1.0f / sqrtf((float)c.head_dim);
-	fused_launch(fa);
-	int nl = 1;
-	if (mode >= 2) {
-		k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, g.sms, g.tp, g.out_tokens, g.last_token, mode == 2, c.vocab_size);
-		++nl;
-	}
-	return nl;
-}
-
-// ---------------------------------------------------------------------------------------------
-// persistent engine: plan + launch
-
-template <int DBITS, int HH>
-void persist_launch_t(const PersistArgs& pa, bool attr_only) {
-	auto kern = k_persist<DBITS, __half, HH>;
-	if (attr_only) {
-		CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.persist_smem));
-		int per_sm = 0;
-		CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PERSIST_THREADS, g.persist_smem));
-		if (per_sm < 1) g.persist_ok = false;
-		return;
-	}
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(g.sms), cfg.blockDim = dim3(PERSIST_THREADS), cfg.dynamicSmemBytes = g.persist_smem, cfg.stream = g.stream;
-	cudaLaunchAttribute at[1];
-	at[0].id = cudaLaunchAttributeCooperative;
-	at[0].val.cooperative = 1;
-	cfg.attrs = at, cfg.numAttrs = 1;
-	CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, pa));
-}
-
-template <int DBITS>
-void persist_launch_hh(const PersistArgs& pa, bool attr_only) {
-	switch ((g.attn_hg + 1) / 2) {
-	case 1: persist_launch_t<DBITS, 1>(pa, attr_only); break;
-	case 2: persist_launch_t<DBITS, 2>(pa, attr_only); break;
-	case 3: persist_launch_t<DBITS, 3>(pa, attr_only); break;
-	default: persist_launch_t<DBITS, 4>(pa, attr_only); break;
-	}
-}
-
-void persist_launch(const PersistArgs& pa, bool attr_only) {
-	switch (g.w.dbits) {
-	case 16: persist_launch_hh<16>(pa, attr_only); break;
-	case 8: persist_launch_hh<8>(pa, attr_only); break;
-	default: persist_launch_hh<4>(pa, attr_only); break;
-	}
-}
-
-void persist_plan() {
-	const Config& c = g.cfg;
-	g.persist_ok = false;
-	if (c.n_experts || g.kvbits != 16) return; // MoE and fp8 KV: staged engine
-	int units = c.n_kv_heads * g.attn_qgroups;
-	g.persist_nsplit = g.sms / units;
-	if (g.persist_nsplit < 1) return;
-	int maxsplit = cdiv(c.seq_len, 32);
-	if (g.persist_nsplit > maxsplit) g.persist_nsplit = maxsplit;
-	if (g.persist_nsplit > g.attn_nsplit_cap) g.persist_nsplit = g.attn_nsplit_cap;
-	size_t need = g.smem_dim > g.smem_hidden ? g.smem_dim : g.smem_hidden;
-	if (g.smem_qdim > need) need = g.smem_qdim;
-	size_t attn = (size_t)(PERSIST_WARPS / 2) * g.attn_hg * (c.head_dim + 2) * sizeof(float);
-	size_t attn2 = (size_t)(2 * g.persist_nsplit + 1) * g.attn_hg * sizeof(float);
-	if (attn > need) need = attn;
-	if (attn2 > need) need = attn2;
-	if (need > 220 * 1024) return;
-	g.persist_smem = need;
-	PersistLayer layers[MAX_LAYERS] = {};
-	for (int l = 0; l < c.n_layers; ++l) {
-		layers[l].wq = g.w.wq[l], layers[l].wk = g.w.wk[l], layers[l].wv = g.w.wv[l], layers[l].wo = g.w.wo[l];
-		layers[l].w1 = g.w.w1[l], layers[l].w2 = g.w.w2[l], layers[l].w3 = g.w.w3[l];
-		layers[l].rms_att = g.w.rms_att_weight[l], layers[l].rms_ffn = g.w.rms_ffn_weight[l], layers[l].bqkv = g.w.bqkv[l];
-	}
-	CUDA_CHECK(cudaMemcpyToSymbol(c_persist_layers, layers, sizeof(layers)));
-	if (!g.fused_bar) {
-		g.fused_bar = (unsigned*)dev_alloc(sizeof(unsigned));
-		CUDA_CHECK(cudaMemset(g.fused_bar, 0, sizeof(unsigned)));
-		CUDA_CHECK(cudaHostAlloc((void**)&g.fused_err, sizeof(int), cudaHostAllocMapped));
-		*g.fused_err = 0;
-		g.fused_perf_ns = (unsigned long long*)dev_alloc(32 * sizeof(unsigned long long));
-		CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 32 * sizeof(unsigned long long)));
-	}
-	g.persist_ok = true;
-	PersistArgs none = {};
-	persist_launch(none, true); // shared-memory opt-in + occupancy check, outside of any stream capture
-}
-
-int run_token_persist(int mode) {
-	const Config& c = g.cfg;
-	PersistArgs pa = {};
-	pa.dim = c.dim, pa.hidden = c.hidden_dim, pa.q_dim = g.q_dim, pa.kv_dim = g.kv_dim, pa.head_dim = c.head_dim;
-	pa.n_heads = c.n_heads, pa.n_kv_heads = c.n_kv_heads, pa.n_layers = c.n_layers, pa.vocab = c.vocab_size, pa.seq_len = c.seq_len, pa.kv_mul = g.kv_mul;
-	pa.eps = c.norm_eps, pa.clip = c.qkv_clip, pa.ln = c.norm_ln, pa.norm_par = c.norm_par, pa.gelu = c.act_gelu;
-	pa.x = g.x, pa.xb = g.xb, pa.q = g.q, pa.att = g.att, pa.hb = g.hb;
-	pa.logits = (mode == 2) ? g.logits_dev : g.logits_host;
-	pa.attn_partial = g.attn_partial, pa.attn_counter = g.attn_counter;
-	pa.kc = g.kc, pa.vc = g.vc, pa.rope_freq = g.rope_freq;
-	pa.embed = g.w.token_embedding_table, pa.wcls = g.w.wcls, pa.rms_final = g.w.rms_final_weight;
-	pa.tp = g.tp, pa.bar = g.fused_bar, pa.err = g.fused_err;
-	pa.perf = g.fused_perf ? g.fused_perf_ns : nullptr;
-	pa.cand_val = (mode >= 2) ? g.cand_val : nullptr, pa.cand_idx = g.cand_idx;
-	pa.mode = mode;
-	pa.attn_nsplit = g.persist_nsplit, pa.attn_hg = g.attn_hg, pa.attn_qgroups = g.attn_qgroups, pa.attn_lpp = g.attn_lpp;
-	pa.inv_sqrt_hd = 1.0f / sqrtf((float)c.head_dim);
-	pa.pf_pairs = getenv("CALM_B200_PF_PAIRS") ? atoi(getenv("CALM_B200_PF_PAIRS")) : 1;
-	pa.pf_bytes = getenv("CALM_B200_PF_BYTES") ? atoi(getenv("CALM_B200_PF_BYTES")) : 6144;
-	persist_launch(pa, false);
-	int nl = 1;
-	if (mode >= 2) {
-		k_advance<<<1, 256, 0, g.stream>>>(g.cand_val, g.cand_idx, g.sms, g.tp, g.out_tokens, g.last_token, mode == 2, c.vocab_size);
-		++nl;
-	}
-	return nl;
-}
-
-// per-stage algorithmic bytes of one token (the reference's accounting, infer.cu:683-699)
-void account_fused_bytes(int mode) {
-	const Config& c = g.cfg;
-	const double wb = g.w.dbits / 8.0, L = c.n_layers;
-	g.stage_bytes[ST_QKV] += L * (g.q_dim + 2.0 * g.kv_dim) * c.dim * wb;
-	g.stage_bytes[ST_ATTN] += L * 2.0 * g.kv_dim * g.cur_kv_len * (g.kvbits / 8);
-	g.stage_bytes[ST_WO] += L * (double)c.dim * g.q_dim * wb;
-	g.stage_bytes[ST_FFN_UP] += L * 2.0 * g.nact * c.hidden_dim * c.dim * wb;
-	g.stage_bytes[ST_FFN_DOWN] += L * 1.0 * g.nact * c.hidden_dim * c.dim * wb;
-	g.stage_launches[ST_QKV] += c.n_layers, g.stage_launches[ST_ATTN] += c.n_layers, g.stage_launches[ST_WO] += c.n_layers;
-	g.stage_launches[ST_FFN_UP] += c.n_layers, g.stage_launches[ST_FFN_DOWN] += c.n_layers;
-	if (mode != 0) g.stage_bytes[ST_OUTPUT] += (double)c.vocab_size * c.dim * wb, g.stage_launches[ST_OUTPUT] += 1;
-}
-
 void launch_token(int mode) {
-	// the persistent kernel serves every token it can; the rest (MoE, fp8 KV, rolled-over cache,
-	// per-stage profiling) goes through the staged engine.  Both are CUDA paths over the same buffers.
-	const bool one_kernel = ((g.engine == 1 && g.fused_ok) || (g.engine == 2 && g.persist_ok)) && (!g.perf || g.fused_perf) && !g.debug_stages &&
-	                        g.cur_pos < g.cfg.seq_len && mode != 4; // the sampler tail lives in the staged token
-	if (one_kernel) {
-		auto run = [&](int m) { return g.engine == 2 ? run_token_persist(m) : run_token_fused(m); };
-		if (!g.use_graph || g.fused_perf) {
-			if (g.fused_perf) account_fused_bytes(mode);
-			g_launches += run(mode);
-			CUDA_CHECK(cudaGetLastError());
-			return;
-		}
-		if (!g.fgraph[mode]) {
-			cudaGraph_t graph;
-			CUDA_CHECK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
-			g.fgraph_launches[mode] = run(mode);
-			CUDA_CHECK(cudaStreamEndCapture(g.stream, &graph));
-			CUDA_CHECK(cudaGraphInstantiate(&g.fgraph[mode], graph, 0));
-			CUDA_CHECK(cudaGraphDestroy(graph));
-		}
-		CUDA_CHECK(cudaGraphLaunch(g.fgraph[mode], g.stream));
-		g_launches += g.fgraph_launches[mode];
-		return;
-	}
-	if (!g.use_graph || g.perf) {
+	const int pv = g.perf ? 1 : 0; // the profiling variant is the same graph with stamp slots
+	if (!g.use_graph) {
 		g_launches += run_token_any(mode);
 		CUDA_CHECK(cudaGetLastError());
-		return;
+	} else {
+		if (!g.graph[pv][mode]) {
+			cudaGraph_t graph;
+			CUDA_CHECK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+			g.graph_launches[pv][mode] = run_token_any(mode);
+			CUDA_CHECK(cudaStreamEndCapture(g.stream, &graph));
+			CUDA_CHECK(cudaGraphInstantiate(&g.graph[pv][mode], graph, 0));
+			CUDA_CHECK(cudaGraphDestroy(graph));
+		}
+		CUDA_CHECK(cudaGraphLaunch(g.graph[pv][mode], g.stream));
+		g_launches += g.graph_launches[pv][mode];
 	}
-	if (!g.graph[mode]) {
-		cudaGraph_t graph;
-		CUDA_CHECK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
-		g.graph_launches[mode] = run_token_any(mode);
-		CUDA_CHECK(cudaStreamEndCapture(g.stream, &graph));
-		CUDA_CHECK(cudaGraphInstantiate(&g.graph[mode], graph, 0));
-		CUDA_CHECK(cudaGraphDestroy(graph));
+	if (g.perf) { // algorithmic bytes of this token per stage (the reference's accounting, infer.cu:683-699)
+		const int n = g.cfg.n_layers * 5 + (mode != 0 ? 1 : 0) + 1;
+		for (int i = 0; i < n && i < MAX_STAMPS; ++i) {
+			const int st = g.stamp_stage[i];
+			g.stage_bytes[st] += g.stamp_bytes[i] >= 0 ? g.stamp_bytes[i] : 2.0 * g.kv_dim * g.cur_kv_len * (g.kvbits / 8);
+			g.stage_launches[st] += 1;
+		}
+		++g.perf_runs;
 	}
-	CUDA_CHECK(cudaGraphLaunch(g.graph[mode], g.stream));
-	g_launches += g.graph_launches[mode];
 }
 
 void set_params(int token, int pos, int step) {
@@ -883,14 +678,6 @@ extern "C" int calm_b200_abi_version(void) {
 
 extern "C" void calm_b200_set_device(int device) {
 	g_device_override = device;
-}
-
-extern "C" int calm_b200_engine_in_use(void) {
-	return g.ready && ((g.engine == 1 && g.fused_ok) || (g.engine == 2 && g.persist_ok)) ? g.engine : 0;
-}
-
-extern "C" void calm_b200_set_engine(int engine) {
-	g_engine_kind = engine;
 }
 
 extern "C" void* upload_cuda(void* host, size_t size) {
@@ -952,15 +739,20 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.carveout = getenv("CALM_B200_CARVEOUT") ? atoi(getenv("CALM_B200_CARVEOUT")) : -1;
 	if (g.early < 0 || g.early > 2) g.early = 0;
 	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
-	if (g.debug) g.use_graph = false, g.debug_stages = true;
+	if (g.debug) g.use_graph = false;
 	g.perf = (getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF"))) || getenv("CUDA_INJECTION64_PATH");
-	const bool want_fused_perf = getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF")) == 2;
+	if (const char* e = getenv("CALM_B200_PF")) { // kv,attn_wo,attn_up_MB,wo_up_MB,up_down_MB,down_qkv  (experiments; defaults in struct Engine)
+		int kv = 1, awo = 1, aup = 40, wup = 0, ud = 0, dq = 1;
+		sscanf(e, "%d,%d,%d,%d,%d,%d", &kv, &awo, &aup, &wup, &ud, &dq);
+		g.pf_kv = kv != 0, g.pf_attn_wo = awo != 0, g.pf_attn_up = (size_t)aup << 20, g.pf_wo_up = (size_t)wup << 20, g.pf_up_down = (size_t)ud << 20, g.pf_down_qkv = dq != 0;
+	}
 
 	CUDA_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-	for (int i = 0; i < 2; ++i) {
-		CUDA_CHECK(cudaEventCreate(&g.ev[i]));
-		CUDA_CHECK(cudaEventCreate(&g.timer[i]));
-	}
+	for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventCreate(&g.timer[i]));
+	g.stamps = (unsigned long long*)dev_alloc((size_t)MAX_STAMPS * 2 * sizeof(unsigned long long));
+	g.stamp_acc = (unsigned long long*)dev_alloc((size_t)(MAX_STAMPS + 2) * sizeof(unsigned long long));
+	CUDA_CHECK(cudaMemset(g.stamps, 0, (size_t)MAX_STAMPS * 2 * sizeof(unsigned long long)));
+	CUDA_CHECK(cudaMemset(g.stamp_acc, 0, (size_t)(MAX_STAMPS + 2) * sizeof(unsigned long long)));
 	if (g.tp_world > 1) { // first collective outside any graph capture: NCCL sets up its channels and buffers here
 		CUDA_CHECK(cudaMemsetAsync(g.xpart, 0, c.dim * sizeof(float), g.stream));
 		tp_allreduce(g.xpart, c.dim);
@@ -1020,16 +812,13 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.tp = (TokenParams*)dev_alloc(sizeof(TokenParams));
 	CUDA_CHECK(cudaMemset(g.tp, 0, sizeof(TokenParams)));
 
-	g.engine = g_engine_kind >= 0 ? g_engine_kind : (getenv("CALM_B200_ENGINE") ? atoi(getenv("CALM_B200_ENGINE")) : 0);
-	if (g.tp_world > 1) g.engine = 0; // the all-reduce is a stream-ordered NCCL call between staged kernels
 	switch (w.dbits) {
 	case 16: make_plan_kv<16>(); break;
 	case 8: make_plan_kv<8>(); break;
 	default: make_plan_kv<4>(); break;
 	}
-	const int ncand_cap = g.ncand > g.sms ? g.ncand : g.sms; // the fused engine publishes one candidate per SM
-	g.cand_val = (float*)dev_alloc(ncand_cap * sizeof(float));
-	g.cand_idx = (int*)dev_alloc(ncand_cap * sizeof(int));
+	g.cand_val = (float*)dev_alloc(g.ncand * sizeof(float));
+	g.cand_idx = (int*)dev_alloc(g.ncand * sizeof(int));
 	g.out_tokens_cap = 1 << 16;
 	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
 	if (!(getenv("CALM_B200_MMA_STATIC") && atoi(getenv("CALM_B200_MMA_STATIC")))) {
@@ -1042,10 +831,6 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.sample_csum = (float*)dev_alloc(g.sample_chunks * sizeof(float));
 	g.sample_idx = (int*)dev_alloc((size_t)g.sample_chunks * SAMPLE_CHUNK * sizeof(int));
 	g.sample_prob = (float*)dev_alloc((size_t)g.sample_chunks * SAMPLE_CHUNK * sizeof(float));
-
-	if (g.engine == 1) fused_plan();
-	if (g.engine == 2) persist_plan();
-	g.fused_perf = want_fused_perf && (g.fused_ok || g.persist_ok);
 
 	// what the reference backend publishes in RunState (infer.cu:99-112)
 	s->x = g.x, s->hb = g.hb, s->he = g.hb, s->q = g.q, s->att = g.att;
@@ -1083,13 +868,10 @@ extern "C" int calm_b200_tp_mode(void) {
 extern "C" void calm_b200_release(struct Transformer* transformer) {
 	if (!g.ready) return;
 	CUDA_CHECK(cudaDeviceSynchronize());
-	for (int i = 0; i < 5; ++i) {
-		if (g.graph[i]) CUDA_CHECK(cudaGraphExecDestroy(g.graph[i]));
-		if (g.fgraph[i]) CUDA_CHECK(cudaGraphExecDestroy(g.fgraph[i]));
-	}
-	if (g.fused_bar) cudaFree(g.fused_bar);
-	if (g.fused_perf_ns) cudaFree(g.fused_perf_ns);
-	if (g.fused_err) cudaFreeHost(g.fused_err);
+	for (int v = 0; v < 2; ++v)
+		for (int i = 0; i < 5; ++i)
+			if (g.graph[v][i]) CUDA_CHECK(cudaGraphExecDestroy(g.graph[v][i]));
+	cudaFree(g.stamps), cudaFree(g.stamp_acc);
 	cudaFree(g.x), cudaFree(g.xb), cudaFree(g.q), cudaFree(g.att), cudaFree(g.hb), cudaFree(g.logits_dev);
 	cudaFreeHost(g.logits_host), cudaFreeHost(g.last_token);
 	cudaFree(g.kc), cudaFree(g.vc), cudaFree(g.rope_freq), cudaFree(g.attn_partial), cudaFree(g.attn_counter);
@@ -1104,7 +886,7 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 	if (g.xpart) cudaFree(g.xpart);
 	for (void* p : g.tp_owned) cudaFree(p);
 	g_tp_world = 1, g_tp_rank = 0; // a new communicator needs a new calm_b200_tp_init
-	for (int i = 0; i < 2; ++i) cudaEventDestroy(g.ev[i]), cudaEventDestroy(g.timer[i]);
+	for (int i = 0; i < 2; ++i) cudaEventDestroy(g.timer[i]);
 	cudaStreamDestroy(g.stream);
 	int dev = g.device;
 	g = Engine();
@@ -1119,9 +901,8 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 static void sync_stream() {
 	cudaError_t e = cudaStreamSynchronize(g.stream);
 	if (e != cudaSuccess) {
-		int code = g.fused_err ? *(volatile int*)g.fused_err : 0;
-		if (g.tp_err && *(volatile int*)g.tp_err) code = *(volatile int*)g.tp_err; // 9000 + rank never heard from
-		fprintf(stderr, "calm_b200: device failure: %s (%s); fused-engine watchdog code %d\n", cudaGetErrorString(e), cudaGetErrorName(e), code);
+		const int code = g.tp_err ? *(volatile int*)g.tp_err : 0; // 9000 + the rank never heard from
+		fprintf(stderr, "calm_b200: device failure: %s (%s); tensor-parallel watchdog code %d\n", cudaGetErrorString(e), cudaGetErrorName(e), code);
 		abort();
 	}
 }
@@ -1143,7 +924,6 @@ extern "C" float* forward_cuda(struct Transformer* transformer, int token, int p
 	launch_token(1);
 	sync_stream();
 	CUDA_CHECK(cudaGetLastError());
-	if (g.perf) ++g.perf_runs;
 	return g.logits_host;
 }
 
@@ -1160,7 +940,7 @@ extern "C" void calm_b200_decode_greedy(struct Transformer* transformer, int tok
 	if (n_tokens > g.out_tokens_cap) CALM_FATAL("decode_greedy: at most %d tokens per call", g.out_tokens_cap);
 	set_params(token0, pos0, 0);
 	for (int i = 0; i < n_tokens; ++i) {
-		g.cur_pos = pos0 + i;
+		g.cur_pos = pos0 + i, g.cur_kv_len = g.cur_pos >= g.cfg.seq_len ? g.cfg.seq_len : g.cur_pos + 1;
 		launch_token(2);
 	}
 	sync_stream();
@@ -1181,7 +961,7 @@ extern "C" void calm_b200_decode_sample(struct Transformer* transformer, int tok
 	CUDA_CHECK(cudaMemcpyAsync(g.sample_state, &st, sizeof(st), cudaMemcpyHostToDevice, g.stream));
 	set_params(token0, pos0, 0);
 	for (int i = 0; i < n_tokens; ++i) {
-		g.cur_pos = pos0 + i;
+		g.cur_pos = pos0 + i, g.cur_kv_len = g.cur_pos >= g.cfg.seq_len ? g.cfg.seq_len : g.cur_pos + 1;
 		launch_token(4);
 	}
 	sync_stream();
@@ -1271,6 +1051,7 @@ static float matvec_impl(const void* w_device, const float* x_host, float* y_hos
 	CUDA_CHECK(cudaGetDeviceProperties(&prop, g.device));
 	g.sms = prop.multiProcessorCount;
 	size_t smem = xs_bytes<DBITS>(n);
+	smem_optin(k_matvec<DBITS>, smem);
 	int cap = max_ctas(k_matvec<DBITS>, 256, smem);
 	int grid = imin(cap, cdiv((d + 1) / 2, 8));
 	MatvecArgs a{x, w_device, y, n, d};
@@ -1303,26 +1084,26 @@ extern "C" float calm_b200_matvec(int dbits, const void* w_device, const float* 
 	return 0.f;
 }
 
-// Pull the in-kernel stage timers of the fused engine into the host-side tables.
-static void fused_perf_collect() {
-	if (!g.fused_perf || !g.fused_perf_ns) return;
+// Pull the in-kernel launch stamps (summed on the device by k_stamp_accum) into the per-stage tables.
+static void perf_collect() {
+	if (!g.stamp_acc) return;
 	CUDA_CHECK(cudaStreamSynchronize(g.stream));
-	unsigned long long ns[32];
-	CUDA_CHECK(cudaMemcpy(ns, g.fused_perf_ns, sizeof(ns), cudaMemcpyDeviceToHost));
-	for (int i = 0; i < ST_COUNT; ++i) {
-		g.stage_ms[i] = (double)(ns[i] + ns[8 + i]) / 1e6, g.stage_wait_ms[i] = (double)ns[8 + i] / 1e6;
-		g.stage_loadx_ms[i] = (double)ns[16 + i] / 1e6, g.stage_tilewait_ms[i] = (double)ns[24 + i] / 1e6;
-	}
+	std::vector<unsigned long long> acc(MAX_STAMPS + 2);
+	CUDA_CHECK(cudaMemcpy(acc.data(), g.stamp_acc, acc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < ST_COUNT; ++i) g.stage_ms[i] = 0;
+	for (int i = 0; i < MAX_STAMPS; ++i) g.stage_ms[g.stamp_stage[i]] += (double)acc[i] / 1e6;
+	g.token_span_ms = (double)acc[MAX_STAMPS] / 1e6;
 }
 
 extern "C" void calm_b200_set_perf(int on) {
-	if (!on) fused_perf_collect();
+	if (!g.ready) return;
+	if (!on) perf_collect();
 	g.perf = on != 0;
-	g.fused_perf = on == 2 && (g.fused_ok || g.persist_ok);
-	if (g.fused_perf_ns) CUDA_CHECK(cudaMemset(g.fused_perf_ns, 0, 32 * sizeof(unsigned long long)));
 	if (!on) return;
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	CUDA_CHECK(cudaMemset(g.stamp_acc, 0, (size_t)(MAX_STAMPS + 2) * sizeof(unsigned long long)));
 	for (int i = 0; i < ST_COUNT; ++i) g.stage_ms[i] = 0, g.stage_bytes[i] = 0, g.stage_launches[i] = 0;
-	g.perf_runs = 0;
+	g.perf_runs = 0, g.token_span_ms = 0;
 }
 
 extern "C" int calm_b200_stage_stats(int stage, char* name, int name_cap, double* ms_total, double* bytes_total, long* launches) {
@@ -1331,58 +1112,29 @@ extern "C" int calm_b200_stage_stats(int stage, char* name, int name_cap, double
 		strncpy(name, kStageNames[stage], name_cap - 1);
 		name[name_cap - 1] = 0;
 	}
-	if (g.fused_perf) fused_perf_collect();
+	if (g.perf) perf_collect();
 	*ms_total = g.stage_ms[stage], *bytes_total = g.stage_bytes[stage], *launches = g.stage_launches[stage];
 	return 1;
 }
 
-extern "C" double calm_b200_stage_wait_ms(int stage) {
-	if (stage < 0 || stage >= ST_COUNT) return 0;
-	if (g.fused_perf) fused_perf_collect();
-	return g.stage_wait_ms[stage];
-}
-
-extern "C" void calm_b200_stage_detail_ms(int stage, double* load_x_ms, double* tile_wait_ms) {
-	*load_x_ms = *tile_wait_ms = 0;
-	if (stage < 0 || stage >= ST_COUNT) return;
-	if (g.fused_perf) fused_perf_collect();
-	*load_x_ms = g.stage_loadx_ms[stage], *tile_wait_ms = g.stage_tilewait_ms[stage];
-}
-
-extern "C" float calm_b200_barrier_bench(int rounds) {
-	select_device();
-	cudaDeviceProp prop;
-	CUDA_CHECK(cudaGetDeviceProperties(&prop, g.device));
-	unsigned* bar;
-	int* err;
-	unsigned long long* ns;
-	CUDA_CHECK(cudaMalloc(&bar, sizeof(unsigned)));
-	CUDA_CHECK(cudaMalloc(&err, sizeof(int)));
-	CUDA_CHECK(cudaMalloc(&ns, sizeof(unsigned long long)));
-	CUDA_CHECK(cudaMemset(bar, 0, sizeof(unsigned)));
-	CUDA_CHECK(cudaMemset(err, 0, sizeof(int)));
-	void* args[] = {&bar, &err, &rounds, &ns};
-	CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_barrier_bench, dim3(prop.multiProcessorCount), dim3(FUSED_THREADS), args, 0, 0));
-	CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_barrier_bench, dim3(prop.multiProcessorCount), dim3(FUSED_THREADS), args, 0, 0));
-	CUDA_CHECK(cudaDeviceSynchronize());
-	unsigned long long h = 0;
-	CUDA_CHECK(cudaMemcpy(&h, ns, sizeof(h), cudaMemcpyDeviceToHost));
-	cudaFree(bar), cudaFree(err), cudaFree(ns);
-	g_launches += 2;
-	return (float)((double)h / 1e3 / rounds); // microseconds per barrier
+extern "C" double calm_b200_perf_token_ms(void) {
+	if (g.perf) perf_collect();
+	return g.perf_runs ? g.token_span_ms / g.perf_runs : 0.0;
 }
 
 extern "C" void perf_cuda(void) {
 	if (!g.ready || !g.perf || g.perf_runs == 0) return;
-	fused_perf_collect();
+	perf_collect();
 	double total = 0;
 	for (int i = 0; i < ST_COUNT; ++i) total += g.stage_ms[i];
-	printf("\nforward breakdown (over %d runs, avg %.1f usec/run):\n", g.perf_runs, total / g.perf_runs * 1e3);
+	if (total <= 0) return;
+	// same shape as the reference's table (infer.cu:761-801); times are first-CTA-start to last-CTA-end of every launch of
+	// the production CUDA graph, read from %globaltimer inside the kernels
+	printf("\nforward breakdown (over %d runs, avg %.1f usec/run; token span %.1f usec):\n", g.perf_runs, total / g.perf_runs * 1e3, g.token_span_ms / g.perf_runs * 1e3);
 	for (int i = 0; i < ST_COUNT; ++i) {
 		if (g.stage_ms[i] == 0) continue;
-		printf("\t[%d] %16s: %4.1f%%; %8.1f usec/run, %6.1f GB/s", i, kStageNames[i], g.stage_ms[i] / total * 100, g.stage_ms[i] / g.perf_runs * 1e3,
+		printf("\t[%d] %16s: %4.1f%%; %8.1f usec/run, %6.1f GB/s\n", i, kStageNames[i], g.stage_ms[i] / total * 100, g.stage_ms[i] / g.perf_runs * 1e3,
 		       g.stage_bytes[i] / 1e9 / (g.stage_ms[i] / 1e3));
-		if (g.fused_perf) printf(" (grid-barrier wait %.1f usec/run)", g.stage_wait_ms[i] / g.perf_runs * 1e3);
-		printf("\n");
 	}
+	fflush(stdout);
 }

@@ -75,9 +75,13 @@ __device__ __forceinline__ void warp_dot_rows(const uint4* const (&rp)[R], int n
 }
 
 // (batched body of stage_vector below: every thread owns up to SV_MAX 16-byte pieces)
+// RMSNorm is applied the way the reference CUDA backend applies it (infer.cu:296-330, 453): x * weight goes to shared
+// memory at once and the matvec RESULT is multiplied by 1/sqrt(mean(x^2) + eps), so the only thing between the loads of
+// x and the first weight load is ONE barrier (which also publishes the per-warp sums of squares).  LayerNorm needs
+// the mean first and keeps the two-pass form of the CPU reference (infer.c:183-207).  Returns that output factor.
 template <int DBITS, int SV_MAX>
-__device__ __forceinline__ void stage_vector_batched(float* xs, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln,
-                                                     float* xb_out) {
+__device__ __forceinline__ float stage_vector_batched(float* xs, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln,
+                                                      float* xb_out) {
 	const int tid = threadIdx.x, nthr = blockDim.x;
 	const int n4 = n >> 2;
 	const int total4 = xs_floats<DBITS>(n) >> 2;
@@ -88,6 +92,8 @@ __device__ __forceinline__ void stage_vector_batched(float* xs, float* red, cons
 		int i = tid + k * nthr;
 		v[k] = i < n4 ? __ldcg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 	}
+	float post = 1.f;
+	bool rms = false;
 	if (normw) {
 		float4 w[SV_MAX];
 #pragma unroll
@@ -95,62 +101,77 @@ __device__ __forceinline__ void stage_vector_batched(float* xs, float* red, cons
 			int i = tid + k * nthr;
 			w[k] = i < n4 ? __ldg(reinterpret_cast<const float4*>(normw) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 		}
-		float mean = 0.f;
 		if (ln) {
 			float s = 0.f;
 #pragma unroll
 			for (int k = 0; k < SV_MAX; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-			mean = block_sum(s, red) / n;
-		}
-		float ss = 0.f;
+			const float mean = block_sum(s, red) / n;
+			float ss = 0.f;
 #pragma unroll
-		for (int k = 0; k < SV_MAX; ++k) {
-			if (tid + k * nthr < n4) {
-				float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
-				ss = fmaf(dx, dx, ss), ss = fmaf(dy, dy, ss), ss = fmaf(dz, dz, ss), ss = fmaf(dw, dw, ss);
+			for (int k = 0; k < SV_MAX; ++k) {
+				if (tid + k * nthr < n4) {
+					float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+					ss = fmaf(dx, dx, ss), ss = fmaf(dy, dy, ss), ss = fmaf(dz, dz, ss), ss = fmaf(dw, dw, ss);
+				}
 			}
-		}
-		ss = block_sum(ss, red);
-		const float scale = 1.0f / sqrtf(ss / n + eps);
+			ss = block_sum(ss, red);
+			const float scale = 1.0f / sqrtf(ss / n + eps);
 #pragma unroll
-		for (int k = 0; k < SV_MAX; ++k) {
-			v[k].x = (v[k].x - mean) * scale * w[k].x, v[k].y = (v[k].y - mean) * scale * w[k].y;
-			v[k].z = (v[k].z - mean) * scale * w[k].z, v[k].w = (v[k].w - mean) * scale * w[k].w;
+			for (int k = 0; k < SV_MAX; ++k) {
+				v[k].x = (v[k].x - mean) * scale * w[k].x, v[k].y = (v[k].y - mean) * scale * w[k].y;
+				v[k].z = (v[k].z - mean) * scale * w[k].z, v[k].w = (v[k].w - mean) * scale * w[k].w;
+			}
+		} else {
+			rms = true;
+			float ss = 0.f;
+#pragma unroll
+			for (int k = 0; k < SV_MAX; ++k) {
+				ss = fmaf(v[k].x, v[k].x, ss), ss = fmaf(v[k].y, v[k].y, ss), ss = fmaf(v[k].z, v[k].z, ss), ss = fmaf(v[k].w, v[k].w, ss);
+				v[k].x *= w[k].x, v[k].y *= w[k].y, v[k].z *= w[k].z, v[k].w *= w[k].w;
+			}
+			ss = warp_sum(ss);
+			if ((tid & 31) == 0) red[tid >> 5] = ss;
 		}
 	}
 #pragma unroll
 	for (int k = 0; k < SV_MAX; ++k) {
 		int i = tid + k * nthr;
 		if (i < n4) {
-			if (xb_out) reinterpret_cast<float4*>(xb_out)[i] = v[k];
+			if (xb_out && !rms) reinterpret_cast<float4*>(xb_out)[i] = v[k];
 			*reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = v[k]; // 4 consecutive elements stay consecutive
 		}
 	}
 	for (int i = n4 + tid; i < total4; i += nthr) *reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = make_float4(0.f, 0.f, 0.f, 0.f);
 	__syncthreads();
+	if (rms) {
+		const int lane = tid & 31, nwarps = (nthr + 31) >> 5;
+		const float ss = warp_sum(lane < nwarps ? red[lane] : 0.f);
+		post = 1.0f / sqrtf(ss / n + eps);
+		if (xb_out) { // the normalised vector itself (norm_par: the FFN reuses it)
+#pragma unroll
+			for (int k = 0; k < SV_MAX; ++k) {
+				int i = tid + k * nthr;
+				if (i < n4) reinterpret_cast<float4*>(xb_out)[i] = make_float4(v[k].x * post, v[k].y * post, v[k].z * post, v[k].w * post);
+			}
+		}
+	}
+	return post;
 }
 
 // Stage an activation vector into shared memory in the permuted layout of common.cuh, optionally
-// applying RMSNorm / LayerNorm-without-bias first (reference infer.c:183-207: mean only when ln,
-// variance around the mean, eps inside the sqrt, then * weight).  Ends with a __syncthreads().
+// applying RMSNorm / LayerNorm-without-bias (reference infer.c:183-207: mean only when ln, variance around the
+// mean, eps inside the sqrt, then * weight).  Ends with a __syncthreads().  Returns the factor the caller must
+// multiply its dot products by (1 unless the RMS scale was left for the epilogue, see stage_vector_batched).
 // Every thread requests all of its elements (16-byte loads, up to SV_MAX per thread) before it touches the
-// first one, so staging costs one L2 round trip instead of one per element; the vector is read through L2
-// (inside the persistent kernel other SMs wrote it during the same launch).
+// first one, so staging costs one L2 round trip instead of one per element.
 template <int DBITS, int SV_MAX = 8>
-__device__ __forceinline__ void stage_vector(float* xs, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln,
-                                             float* xb_out) {
+__device__ __forceinline__ float stage_vector(float* xs, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln,
+                                              float* xb_out) {
 	const int tid = threadIdx.x, nthr = blockDim.x;
 	const int n4 = n >> 2; // n is a multiple of 32
-	const int total4 = xs_floats<DBITS>(n) >> 2;
-	const float4* x4 = reinterpret_cast<const float4*>(x);
-	if (SV_MAX > 4 && n4 <= nthr * 4) { // the common case (dim 4096, 256 threads): half the registers
-		stage_vector_batched<DBITS, 4>(xs, red, x, n, normw, eps, ln, xb_out);
-		return;
-	}
-	if (n4 <= nthr * SV_MAX) {
-		stage_vector_batched<DBITS, SV_MAX>(xs, red, x, n, normw, eps, ln, xb_out);
-		return;
-	}
+	if (SV_MAX > 4 && n4 <= nthr * 4) // the common case (dim 4096, 256 threads): half the registers
+		return stage_vector_batched<DBITS, 4>(xs, red, x, n, normw, eps, ln, xb_out);
+	if (n4 <= nthr * SV_MAX) return stage_vector_batched<DBITS, SV_MAX>(xs, red, x, n, normw, eps, ln, xb_out);
 	// long vectors: same thing, element by element (two reads of x when normalising)
 	float mean = 0.f, scale = 1.f;
 	if (normw) {
@@ -178,6 +199,7 @@ __device__ __forceinline__ void stage_vector(float* xs, float* red, const float*
 		xs[xs_index<DBITS>(j)] = v;
 	}
 	__syncthreads();
+	return 1.f;
 }
 
 __device__ __forceinline__ float act_silu(float x) { // reference infer.c:273-275
@@ -201,6 +223,10 @@ struct EmbedArgs {
 	int embed_blocks;
 	int* tile_ctr; // per-layer work counters of k_ffn_up_mma, zeroed here once per token
 	int n_ctr;
+	unsigned long long* stamp; // perf_cuda: {min start, max end} of this launch, or NULL
+	unsigned long long* stamp_reset; // perf_cuda: all slots of the token, re-armed here
+	int n_stamps;
+	Prefetch pf;
 	// sinks
 	KVT* key_cache;
 	const float* rope_freq;
@@ -209,7 +235,12 @@ struct EmbedArgs {
 
 template <int DBITS, typename KVT>
 __global__ void k_embed(const EmbedArgs<KVT> a) {
-	pdl_enter();
+	pdl_launch_next();
+	prefetch_ranges(a.pf); // layer 0's first weights: nothing else is streaming yet
+	pdl_wait_prev();
+	if (a.stamp_reset) { // grid-stride: (start, end) = (max, 0); every later kernel of the token waits for this grid
+		for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_stamps; j += gridDim.x * blockDim.x) a.stamp_reset[2 * j] = ~0ull, a.stamp_reset[2 * j + 1] = 0ull;
+	}
 	if ((int)blockIdx.x < a.embed_blocks) {
 		int i = blockIdx.x * blockDim.x + threadIdx.x;
 		if (i < a.dim) a.x[i] = weight_at<DBITS>(a.table, (size_t)a.tp->token * a.dim + i);
@@ -255,6 +286,8 @@ struct QkvArgs {
 	int dim, q_dim, kv_dim, head_dim, seq_len;
 	float eps, clip;
 	int ln;
+	unsigned long long* stamp;
+	Prefetch pf;
 };
 
 // EARLY: what a warp does about its first row pair BEFORE waiting for the previous kernel and staging the activations
@@ -292,9 +325,12 @@ __global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 		rows_of(p0, rp, j, k);
 		l2_prefetch_row(rp[0], nvec * 16), l2_prefetch_row(rp[1], nvec * 16);
 	}
+	prefetch_ranges(a.pf);
 	pdl_wait_prev();
-	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, blockIdx.x == 0 ? a.xb_out : nullptr);
+	stamp_begin(a.stamp);
+	const float post = stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, blockIdx.x == 0 ? a.xb_out : nullptr);
 	const int pos = a.tp->pos, kv_pos = a.tp->kv_pos;
+	prefetch_kv(a.pf, a.tp->kv_len); // this layer's cache prefix, for the attention kernel that follows
 
 	for (int p = p0; p < npairs; p += gridDim.x * nwarps) {
 		const uint4* rp[2];
@@ -304,7 +340,7 @@ __global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 		warp_dot_rows<DBITS, 2, 4>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
 
 		if (lane == 0) {
-			float v0 = v[0], v1 = v[1];
+			float v0 = v[0] * post, v1 = v[1] * post;
 			if (a.bias) v0 += a.bias[j], v1 += a.bias[j + 1];
 			v0 = fminf(fmaxf(v0, -a.clip), a.clip);
 			v1 = fminf(fmaxf(v1, -a.clip), a.clip);
@@ -325,6 +361,7 @@ __global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 			}
 		}
 	}
+	stamp_end(a.stamp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -348,6 +385,8 @@ struct AttnArgs {
 	int head_dim, seq_len, nsplit, lpp; // lpp: lanes per position (power of two >= head_dim/8)
 	int kv_mul, qgroups;                // query heads per kv head; qgroups = kv_mul / HG
 	float inv_sqrt_hd;
+	unsigned long long* stamp;
+	Prefetch pf;
 };
 
 template <typename KVT>
@@ -662,22 +701,26 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int HG, int hsets, 
 #define ATTN_THREADS 256
 template <typename KVT, int HG>
 __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnArgs a) {
-	pdl_enter();
+	pdl_launch_next();
+	prefetch_ranges(a.pf); // wo and the head of w1 / w3: HBM is nearly idle while this kernel runs
+	pdl_wait_prev();
+	stamp_begin(a.stamp);
 	extern __shared__ __align__(16) float smem[];
 	__shared__ int flag;
 	const int unit = blockIdx.x / a.nsplit, split = blockIdx.x % a.nsplit, kv_len = a.tp->kv_len;
 	// transposing score path when the lanes of a position are a small multiple of the heads (head_dim 128 / 64)
+	bool done = false;
 	if constexpr (HG == 2 || HG == 4 || HG == 8) {
 		if (a.lpp == 16 && HG >= 4) {
 			attn_item<KVT, HG, 16 / HG, true, 16>(a, HG, 1, unit, split, kv_len, smem, &flag);
-			return;
-		}
-		if (a.lpp == 8) {
+			done = true;
+		} else if (a.lpp == 8) {
 			attn_item<KVT, HG, 8 / HG, true, 8>(a, HG, 1, unit, split, kv_len, smem, &flag);
-			return;
+			done = true;
 		}
 	}
-	attn_item<KVT, HG, (HG > 4 ? 2 : 4), true>(a, HG, 1, unit, split, kv_len, smem, &flag);
+	if (!done) attn_item<KVT, HG, (HG > 4 ? 2 : 4), true>(a, HG, 1, unit, split, kv_len, smem, &flag);
+	stamp_end(a.stamp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -716,7 +759,9 @@ __device__ __forceinline__ void tp_exchange_add(const TpExchange& t, const float
 		const int row = 2 * (((j >> 4) * gridDim.x + blockIdx.x) * 8) + (j & 15);
 		if (row < d) {
 			uint2* dst = t.cell[peer] + ((size_t)slot * W + t.rank) * d + row;
-			asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(part[j])), "r"(epoch) : "memory");
+			// ONE 64-bit store: a reader that sees the epoch word sees the value word (a .v2 access is two scalar accesses to the memory model)
+			const unsigned long long cell = ((unsigned long long)epoch << 32) | __float_as_uint(part[j]);
+			asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(cell) : "memory");
 		}
 	}
 	for (int j = threadIdx.x; j < cells; j += blockDim.x) {
@@ -729,11 +774,13 @@ __device__ __forceinline__ void tp_exchange_add(const TpExchange& t, const float
 				sum += part[j];
 				continue;
 			}
-			unsigned vx, vy, spins = 0;
+			unsigned vx, spins = 0;
 			unsigned long long t0 = 0;
 			for (;;) {
-				asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "l"(base + (size_t)p * d) : "memory");
-				if (vy == epoch) break;
+				unsigned long long cell;
+				asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(cell) : "l"(base + (size_t)p * d) : "memory");
+				vx = (unsigned)cell;
+				if ((unsigned)(cell >> 32) == epoch) break;
 				if ((++spins & 1023) == 0) {
 					unsigned long long now;
 					asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
@@ -764,6 +811,9 @@ struct MatResArgs {
 	int n, d, nact;
 	int accumulate;   // 1: y += ..., 0: y = ...
 	TpExchange tpx;   // world > 1: the partial is summed over the tensor-parallel ranks inside this kernel
+	const TokenParams* tp;
+	unsigned long long* stamp;
+	Prefetch pf;
 };
 
 template <int DBITS, int EARLY>
@@ -784,7 +834,10 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 		const uint4* r0 = reinterpret_cast<const uint4*>(a.w) + (size_t)(2 * p0) * nvec;
 		l2_prefetch_row(r0, nvec * 16), l2_prefetch_row(r0 + nvec, nvec * 16);
 	}
+	prefetch_ranges(a.pf);
 	pdl_wait_prev();
+	stamp_begin(a.stamp);
+	prefetch_kv(a.pf, a.tp->kv_len); // w2: the NEXT layer's cache prefix (same token: same length)
 
 	for (int e = 0; e < a.nact; ++e) {
 		if (e > 0) __syncthreads();
@@ -818,6 +871,7 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 		const int per = gridDim.x * 8;
 		tp_exchange_add(a.tpx, tp_part, (a.d / 2 - blockIdx.x * 8 + per - 1) / per, a.y, a.d);
 	}
+	stamp_end(a.stamp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -826,6 +880,8 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 // with strict '>' so the lowest index wins ties, weights = softmax over the selected; infer.c:277-305).
 
 struct FfnUpArgs {
+	unsigned long long* stamp;
+	Prefetch pf;
 	const float* x;
 	const float* normw; // NULL: stage `x` as is (norm_par: x = saved attention-norm output)
 	const void* gate;   // router (n_experts, dim) or NULL
@@ -858,14 +914,16 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpA
 		l2_prefetch_row(reinterpret_cast<const uint4*>(a.w3) + (size_t)p0 * nvec, nvec * 16);
 	}
 	pdl_wait_prev();
-	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
+	stamp_begin(a.stamp);
+	const float post = stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
+	prefetch_ranges(a.pf); // w2 (dense models): behind this kernel's own first requests
 
 	if (a.n_experts) {
 		for (int e = warp; e < a.n_experts; e += nwarps) {
 			const uint4* rp[1] = {reinterpret_cast<const uint4*>(a.gate) + (size_t)e * nvec};
 			float v[1];
 			warp_dot_rows<DBITS, 1>(rp, nvec, xs4, v);
-			if (lane == 0) glog[e] = v[0];
+			if (lane == 0) glog[e] = v[0] * post;
 		}
 		__syncthreads();
 		if (threadIdx.x == 0) {
@@ -899,8 +957,12 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpA
 			warp_dot_rows<DBITS, 2, 8>(rp, nvec, xs4, v);
 		else
 			warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
-		if (lane == 0) a.hb[p] = (a.gelu ? act_gelu(v[0]) : act_silu(v[0])) * v[1];
+		if (lane == 0) {
+			const float u1 = v[0] * post, u3 = v[1] * post;
+			a.hb[p] = (a.gelu ? act_gelu(u1) : act_silu(u1)) * u3;
+		}
 	}
+	stamp_end(a.stamp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1058,6 +1120,8 @@ __global__ void __launch_bounds__(256, 3) k_ffn_up_mma(const FfnUpArgs a) {
 		l2_prefetch(w1 + off, kpw * 64), l2_prefetch(w3 + off, kpw * 64);
 	}
 	pdl_wait_prev();
+	stamp_begin(a.stamp);
+	prefetch_ranges(a.pf);
 	float out_scale;
 	if (a.dim / 4 <= (int)blockDim.x * 4)
 		out_scale = stage_vector_h<4>(H, Lo, red, a.x, a.dim, a.normw, a.eps, a.ln != 0);
@@ -1100,6 +1164,7 @@ __global__ void __launch_bounds__(256, 3) k_ffn_up_mma(const FfnUpArgs a) {
 		}
 		ti = next_tile[buf]; // written before this iteration's barrier
 	}
+	stamp_end(a.stamp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1117,11 +1182,13 @@ struct OutputArgs {
 	int dim, vocab;
 	float eps;
 	int ln;
+	unsigned long long* stamp;
 };
 
 template <int DBITS>
 __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
 	pdl_enter();
+	stamp_begin(a.stamp);
 	constexpr int R = 4;
 	extern __shared__ __align__(16) float smem[];
 	__shared__ float outbuf[32]; // nwarps * R
@@ -1129,7 +1196,7 @@ __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
 	__shared__ int bidx[8];
 	float* red = smem;
 	float* xs = smem + 32;
-	stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
+	const float post = stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5; // nwarps == 8
 	const int nvec = a.dim / WFmt<DBITS>::VW;
@@ -1147,6 +1214,7 @@ __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
 		if (lane == 0) {
 #pragma unroll
 			for (int r = 0; r < R; ++r) {
+				v[r] *= post;
 				outbuf[warp * R + r] = v[r];
 				if (r0 + r < a.vocab && v[r] > best) best = v[r], besti = r0 + r;
 			}
@@ -1166,6 +1234,7 @@ __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
 			a.cand_idx[blockIdx.x] = besti;
 		}
 	}
+	stamp_end(a.stamp);
 }
 
 // Fold the per-CTA candidates, publish the greedy token, and advance the token parameters so the

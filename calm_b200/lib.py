@@ -23,10 +23,10 @@ _fptr = C.POINTER(C.c_float)
 # every symbol include/calm_b200.h declares
 SYMBOLS = [
     "upload_cuda", "prepare_cuda", "forward_cuda", "perf_cuda",
-    "calm_b200_abi_version", "calm_b200_set_device", "calm_b200_free", "calm_b200_release", "calm_b200_set_engine",
+    "calm_b200_abi_version", "calm_b200_set_device", "calm_b200_free", "calm_b200_release",
     "calm_b200_forward_argmax", "calm_b200_decode_greedy", "calm_b200_timer_start", "calm_b200_timer_stop",
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
-    "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_engine_in_use", "calm_b200_stage_wait_ms", "calm_b200_barrier_bench", "calm_b200_stage_detail_ms",
+    "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_perf_token_ms",
     "calm_b200_tp_unique_id", "calm_b200_tp_init", "calm_b200_tp_world", "calm_b200_tp_mode",
     "calm_b200_decode_sample", "calm_b200_forward_sample", "calm_b200_read_device_logits",
 ]
@@ -51,7 +51,6 @@ def load() -> C.CDLL:
     L.calm_b200_set_device.argtypes, L.calm_b200_set_device.restype = [C.c_int], None
     L.calm_b200_free.argtypes, L.calm_b200_free.restype = [C.c_void_p], None
     L.calm_b200_release.argtypes, L.calm_b200_release.restype = [T], None
-    L.calm_b200_set_engine.argtypes, L.calm_b200_set_engine.restype = [C.c_int], None
     L.calm_b200_forward_argmax.argtypes, L.calm_b200_forward_argmax.restype = [T, C.c_int, C.c_int], C.c_int
     L.calm_b200_decode_greedy.argtypes, L.calm_b200_decode_greedy.restype = [T, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)], None
     L.calm_b200_timer_start.argtypes, L.calm_b200_timer_start.restype = [], None
@@ -65,10 +64,7 @@ def load() -> C.CDLL:
     L.calm_b200_set_perf.argtypes, L.calm_b200_set_perf.restype = [C.c_int], None
     L.calm_b200_stage_stats.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]
     L.calm_b200_stage_stats.restype = C.c_int
-    L.calm_b200_engine_in_use.argtypes, L.calm_b200_engine_in_use.restype = [], C.c_int
-    L.calm_b200_stage_wait_ms.argtypes, L.calm_b200_stage_wait_ms.restype = [C.c_int], C.c_double
-    L.calm_b200_barrier_bench.argtypes, L.calm_b200_barrier_bench.restype = [C.c_int], C.c_float
-    L.calm_b200_stage_detail_ms.argtypes, L.calm_b200_stage_detail_ms.restype = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)], None
+    L.calm_b200_perf_token_ms.argtypes, L.calm_b200_perf_token_ms.restype = [], C.c_double
     L.calm_b200_tp_unique_id.argtypes, L.calm_b200_tp_unique_id.restype = [C.c_void_p], None
     L.calm_b200_tp_init.argtypes, L.calm_b200_tp_init.restype = [C.c_int, C.c_int, C.c_void_p], None
     L.calm_b200_tp_world.argtypes, L.calm_b200_tp_world.restype = [], C.c_int
@@ -101,7 +97,7 @@ class DeviceModel:
     """
 
     def __init__(self, spec: mg.ModelSpec, tensors: Dict[str, "object"], seq_len: Optional[int] = None, kvbits: int = 16,
-                 device: Optional[int] = None, engine: Optional[int] = None, tp=None):
+                 device: Optional[int] = None, tp=None):
         """tp = (rank, world, id128) turns on tensor parallelism (include/calm_b200.h); tensors stay the FULL model."""
         self.lib = load()
         self.spec = spec
@@ -109,8 +105,6 @@ class DeviceModel:
             self.lib.calm_b200_set_device(device)
         if tp is not None:
             self.lib.calm_b200_tp_init(int(tp[0]), int(tp[1]), C.c_char_p(tp[2]) if tp[2] else None)
-        if engine is not None:
-            self.lib.calm_b200_set_engine(engine)
         self._uploaded = []
         self._keep = tensors
         ptrs = {}
@@ -173,10 +167,10 @@ class DeviceModel:
     def fill_kv(self, n_pos: int, seed: int = 1) -> None:
         self.lib.calm_b200_fill_kv(C.byref(self.transformer), n_pos, seed)
 
-    def profile(self, token: int, pos0: int, n: int, mode: int = 1):
-        """Run n tokens with per-stage timing; returns {stage: (ms_total, bytes_total, launches)}.
-        mode 1: staged engine, CUDA events around every launch; mode 2: fused engine, in-kernel timers."""
-        self.lib.calm_b200_set_perf(mode)
+    def profile(self, token: int, pos0: int, n: int):
+        """Run n greedy tokens of the production graph with in-kernel stage stamps; returns
+        ({stage: (ms_total, bytes_total, launches)}, mean token span in ms)."""
+        self.lib.calm_b200_set_perf(1)
         tok = token
         for i in range(n):
             tok = self.forward_argmax(tok, pos0 + i)
@@ -185,16 +179,11 @@ class DeviceModel:
         name = C.create_string_buffer(64)
         ms, by, nl = C.c_double(), C.c_double(), C.c_long()
         while self.lib.calm_b200_stage_stats(i, name, 64, C.byref(ms), C.byref(by), C.byref(nl)):
-            lx, tw = C.c_double(), C.c_double()
-            self.lib.calm_b200_stage_detail_ms(i, C.byref(lx), C.byref(tw))
-            out[name.value.decode()] = (ms.value, by.value, nl.value, self.lib.calm_b200_stage_wait_ms(i) if mode == 2 else 0.0, lx.value, tw.value)
+            out[name.value.decode()] = (ms.value, by.value, nl.value)
             i += 1
+        span = self.lib.calm_b200_perf_token_ms()
         self.lib.calm_b200_set_perf(0)
-        return out
-
-    def uses_fused(self) -> bool:
-        """True when the persistent fused kernel serves this model (else the staged engine does)."""
-        return bool(self.lib.calm_b200_engine_in_use())
+        return out, span
 
     def close(self) -> None:
         if self.transformer is not None:

@@ -105,6 +105,13 @@ SPECS.update({
     "tiny-mha": replace(_T, name="tiny-mha", n_heads=8, n_kv_heads=8),
     # QKV bias + tied classifier on a shape two tensor-parallel ranks can split (tiny-qwen has a single kv head)
     "tiny-bias2": replace(_T, name="tiny-bias2", dtype="fp16", n_heads=4, n_kv_heads=2, head_dim=64, qkv_bias=True, tied=True),
+    # Gemma-style multi-query attention: 8 query heads on ONE kv head of 256 dims (the attention kernel's merge
+    # records exceed the default 48 KB of dynamic shared memory)
+    # (hidden >= dim >= q_dim: the reference CPU backend reuses xb2[dim] and hb[hidden] as scratch, infer.c:152-153, 404, 409)
+    "tiny-hd256": replace(_T, name="tiny-hd256", dim=2048, n_layers=2, n_heads=8, n_kv_heads=1, head_dim=256, hidden_dim=2048),
+    # Llama-3-8B's attention geometry (32 query / 8 kv heads of 128, so 8 units x 18 slices on 148 SMs) at the full
+    # 4096-token context, on widths the CPU oracle finishes in milliseconds per token
+    "attn-l8": ModelSpec("attn-l8", 256, 512, 2, 32, 8, 128, 512, "fp8", rope_theta=5e5, max_seq_len=4096),
 })
 
 
@@ -355,16 +362,21 @@ class HostModel:
     """A generated model held in host memory + the struct Transformer pointing at it
     (what the CPU reference / oracle consume)."""
 
-    def __init__(self, spec: ModelSpec, seed: int = 0, seq_len: Optional[int] = None, tensors=None):
+    def __init__(self, spec: ModelSpec, seed: int = 0, seq_len: Optional[int] = None, tensors=None, kvbits: int = 16):
         self.spec = spec
         self.tensors = tensors if tensors is not None else generate(spec, seed)
         self.tensors = {k: v.contiguous().cpu() for k, v in self.tensors.items()}
+        self._seq_len, self._kvbits = seq_len, kvbits
+        self.rebind()
+
+    def rebind(self) -> None:
+        """(Re)build struct Transformer over self.tensors (call after replacing tensors with copies elsewhere in memory)."""
 
         def ptr_of(name):
             v = self.tensors.get(name)
             return v.data_ptr() if v is not None else 0
 
-        self.transformer = fill_transformer(spec, ptr_of, seq_len)
+        self.transformer = fill_transformer(self.spec, ptr_of, self._seq_len, self._kvbits)
 
     @property
     def seq_len(self) -> int:
@@ -374,3 +386,19 @@ class HostModel:
 def teacher_tokens(vocab_size: int, n: int, start: int = 0) -> list:
     """Fixed token list for teacher-forced parity runs: tok_i = (7919 i + 13) mod vocab."""
     return [((7919 * (i + start)) + 13) % vocab_size for i in range(n)]
+
+
+def kv_fill_pattern(n_layers_heads: int, n_pos: int, head_dim: int, seed: int):
+    """The deterministic pseudo-random cache fill of calm_b200_fill_kv (csrc/stages.cuh k_fill_kv), restated in numpy
+    so a CPU checker can be given the SAME cache: returns (k, v) float32 [n_layers_heads, n_pos, head_dim] BEFORE the
+    rounding to the cache element type (fp16 RN, or e5m2 RN)."""
+    i = np.arange(n_layers_heads * n_pos * head_dim, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (i + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    a = ((z & np.uint64(0xFFFFFF)).astype(np.float64) / 16777216.0 - 0.5) * 2.0
+    b = (((z >> np.uint64(24)) & np.uint64(0xFFFFFF)).astype(np.float64) / 16777216.0 - 0.5) * 2.0
+    shape = (n_layers_heads, n_pos, head_dim)
+    return a.astype(np.float32).reshape(shape), b.astype(np.float32).reshape(shape)

@@ -75,12 +75,6 @@ void calm_b200_free(void* device_ptr);
  * never frees, run.c:636) so another model can be prepared in this process. */
 void calm_b200_release(struct Transformer* transformer);
 
-/* Which engine forward_cuda() uses: 0 = one kernel per stage (CUDA graph), 1 = persistent kernel fed by a
- * TMA ring (fused.cuh), 2 = persistent kernel with streaming loads and cross-barrier prefetch (persist.cuh).
- * Default from env CALM_B200_ENGINE, else 0 (the fastest measured).  Must be called before
- * prepare_cuda(). */
-void calm_b200_set_engine(int engine);
-
 /* Tensor parallelism for models that do not fit (or should not sit on) one GPU -- the 70B shape of
  * BASELINE.json configs[4]; the reference has no counterpart (single device, infer.cu:79).  One process per GPU.
  * Rank 0 obtains a 128-byte NCCL id with calm_b200_tp_unique_id() and hands it to the other ranks by any means
@@ -89,7 +83,7 @@ void calm_b200_set_engine(int engine);
  * prepare, forward the same (token, pos) on every rank.  prepare_cuda() keeps this rank's 1/world of the query /
  * kv heads and of the FFN rows (row ranges of wq/wk/wv/w1/w3 in place, packed column ranges of wo/w2); each
  * forward sums the two partial projections per layer over NVLink (inside the CUDA graph) and every rank returns the full, identical logits.  Requires world | n_heads, n_kv_heads and 32*world |
- * hidden_dim; dense models; staged engine.  libnccl.so.2 is bound with dlopen on first use.
+ * hidden_dim; dense models.  libnccl.so.2 is bound with dlopen on first use.
  * calm_b200_tp_mode(): 0 = not tensor-parallel, 2 = the wo / w2 kernels sum their partials themselves through
  * CUDA-IPC-mapped peer memory (one-shot push all-reduce inside k_matres; default), 1 = ncclAllReduce between
  * kernels (peer mapping unavailable, or env CALM_B200_TP_FUSED=0). */
@@ -98,9 +92,6 @@ void calm_b200_tp_init(int rank, int world, const void* id128);
 int calm_b200_tp_world(void);
 int calm_b200_tp_mode(void);
 
-/* The engine that serves the prepared model: 1 or 2 (one persistent kernel per token), or 0 when the staged
- * engine does (MoE, fp8 KV cache, unsupported shapes, or engine 0 requested). */
-int calm_b200_engine_in_use(void);
 
 /* forward + device-side greedy sample.  Returns argmax(logits) with the
  * reference's tie rule (lowest index, sampler.c:34-42).  The logits are still
@@ -143,22 +134,17 @@ void calm_b200_read_kv(struct Transformer* transformer, int layer, int kv_pos, f
  * whole prefix). */
 void calm_b200_fill_kv(struct Transformer* transformer, int n_pos, uint64_t seed);
 
-/* Per-stage profiling at run time (what CALM_B200_PERF=1 enables from the start): while on, every
- * stage is launched eagerly and bracketed by CUDA events on the library's stream.  set_perf(1) also
- * clears the counters.  stage_stats() returns 0 past the last stage; totals are over all launches of
- * that stage since set_perf(1): milliseconds, algorithmic bytes (the reference's per-stage accounting,
- * infer.cu:683-699) and launch count.  set_perf(2) keeps the fused engine and times its stages INSIDE the
- * persistent kernel with %globaltimer (what the reference's coopstage does, infer.cu:390-402). */
+/* Per-stage profiling at run time (what CALM_B200_PERF=1 enables from the start).  While on, every token runs the
+ * PRODUCTION CUDA graph (same kernels, programmatic dependent launch) with one extra argument per launch: a stamp slot
+ * into which the kernel folds min(start) / max(end) of its CTAs, read from %globaltimer -- the reference's coopstage
+ * scheme (infer.cu:390-402), so perf_cuda() describes the path that produces the tokens, not an eager variant.
+ * set_perf(1) clears the counters.  stage_stats() returns 0 past the last stage; totals are over all launches of that
+ * stage since set_perf(1): milliseconds (first CTA past its dependency wait -> last CTA done), algorithmic bytes (the
+ * reference's per-stage accounting, infer.cu:683-699) and launch count.  perf_token_ms(): mean span of a token, first
+ * stamp to last (consecutive kernels overlap under PDL, so the stage sums can exceed it). */
 void calm_b200_set_perf(int on);
 int calm_b200_stage_stats(int stage, char* name, int name_cap, double* ms_total, double* bytes_total, long* launches);
-
-/* Fused engine only: the part of stage_stats()'s ms_total that CTA 0 spent waiting in the grid barrier. */
-double calm_b200_stage_wait_ms(int stage);
-/* ... and the parts spent loading the stage's activation slice and waiting for weight tiles to land. */
-void calm_b200_stage_detail_ms(int stage, double* load_x_ms, double* tile_wait_ms);
-
-/* Micro-benchmark: microseconds per grid barrier of the fused engine (all SMs, no work in between). */
-float calm_b200_barrier_bench(int rounds);
+double calm_b200_perf_token_ms(void);
 
 /* Stand-alone run of the production matvec kernel: y[d] = W[d,n] . x[n] with W
  * in the `dbits` format at device pointer `w_device`; x and y are HOST arrays.

@@ -17,7 +17,7 @@
  * How it is pinned: the reference has no golden vectors or unit tests
  * (SURVEY.md section 4), so parity is pinned by EXECUTING the reference:
  * oracle/Makefile compiles the unmodified reference sources from
- * /root/reference/src into oracle/_ref/, tests/test_oracle_vs_ref.py runs
+ * /root/reference/src into oracle/_ref/, tests/test_oracle.py runs
  * both on the same seeded synthetic models, and tools/make_golden.py stores
  * reference outputs as fixtures under tests/golden/ for boxes that do not
  * have /root/reference.
@@ -66,6 +66,24 @@ float oracle_fp8_to_float(uint8_t v) {
 	} cvt;
 	cvt.u = (uint16_t)(v << 8);
 	return (float)cvt.h;
+}
+
+/* float -> e5m2 -> float: what the reference CUDA backend's fp8 KV cache does to an entry (KVT = __nv_fp8_e5m2 when
+ * kvbits == 8, run.c:537-539; stores infer.cu:476-481 through the __nv_fp8_e5m2(float) constructor = round to nearest
+ * even, saturate to the largest finite value 57344; loads are exact).  e5m2: 2 mantissa bits, normal exponents
+ * 2^-14..2^15, subnormal quantum 2^-16.  Every e5m2 value is a half, so the cache keeps half_t storage. */
+float oracle_round_e5m2(float v) {
+	if (v != v) return v;
+	float a = fabsf(v);
+	if (a >= 57344.f) return copysignf(57344.f, v); /* includes +-inf: SATFINITE */
+	int e;
+	frexpf(a, &e);  /* a = m * 2^e, m in [0.5, 1) -> leading bit at 2^(e-1) */
+	int qe = e - 1 - 2; /* quantum: two bits below the leading one */
+	if (qe < -16) qe = -16;
+	float q = ldexpf(1.f, qe);
+	float r = nearbyintf(a / q) * q; /* exact scaling by a power of two; default rounding mode = nearest even */
+	if (r > 57344.f) r = 57344.f;
+	return copysignf(r, v);
 }
 
 /* gf4 word -> weight k (0..7): (q_k - 4) * (s / -4) with s the e5m2 scale in
@@ -245,7 +263,8 @@ static float clipf(float x, float v) { /* reference infer.c:307-309 */
 /* ---- state ---------------------------------------------------------------- */
 
 /* Allocate activations and an fp16 KV cache laid out [layer][pos][kv_dim]
- * (reference infer.c:142-181; kvbits must be 16 on the CPU path, :160). */
+ * (reference infer.c:142-181).  The reference CPU path insists on kvbits == 16 (:160); kvbits == 8 here restates
+ * the reference CUDA path's e5m2 cache (see oracle_round_e5m2) so the device's fp8 cache has a CPU checker too. */
 void oracle_prepare(struct Transformer* t) {
 	struct Config* p = &t->config;
 	struct RunState* s = &t->state;
@@ -264,7 +283,7 @@ void oracle_prepare(struct Transformer* t) {
 	s->att = calloc((size_t)p->n_heads * p->seq_len, sizeof(float));
 	s->exp = calloc(p->n_experts + nact * 2, sizeof(float));
 	s->logits = calloc(p->vocab_size, sizeof(float));
-	assert(s->kvbits == 16);
+	assert(s->kvbits == 16 || s->kvbits == 8);
 	s->key_cache = calloc((size_t)p->n_layers * p->seq_len * kv_dim, sizeof(half_t));
 	s->value_cache = calloc((size_t)p->n_layers * p->seq_len * kv_dim, sizeof(half_t));
 	if (!s->x || !s->xb || !s->xb2 || !s->hb || !s->hb2 || !s->q || !s->k || !s->v || !s->att || !s->exp || !s->logits || !s->key_cache || !s->value_cache) {
@@ -335,15 +354,16 @@ float* oracle_forward_taps(struct Transformer* t, int token, int pos, unsigned f
 		oracle_rope(s->k, kv_dim, p->head_dim, pos, p->rope_theta, p->rotary_dim);
 		if (tap_q) memcpy(tap_q + (size_t)l * q_dim, s->q, q_dim * sizeof(float));
 
+		const int kv8 = s->kvbits == 8;
 		for (int i = 0; i < kv_dim; ++i) {
-			kb[(size_t)kv_pos * kv_dim + i] = (half_t)s->k[i];
-			vb[(size_t)kv_pos * kv_dim + i] = (half_t)s->v[i];
+			kb[(size_t)kv_pos * kv_dim + i] = (half_t)(kv8 ? oracle_round_e5m2(s->k[i]) : s->k[i]);
+			vb[(size_t)kv_pos * kv_dim + i] = (half_t)(kv8 ? oracle_round_e5m2(s->v[i]) : s->v[i]);
 		}
 
 		for (int r = 0; r < kv_sink; ++r) {
 			for (int i = 0; i < kv_dim; ++i) s->k[i] = (float)kb[(size_t)r * kv_dim + i];
 			oracle_rope(s->k, kv_dim, p->head_dim, 1, p->rope_theta, p->rotary_dim);
-			for (int i = 0; i < kv_dim; ++i) kb[(size_t)r * kv_dim + i] = (half_t)s->k[i];
+			for (int i = 0; i < kv_dim; ++i) kb[(size_t)r * kv_dim + i] = (half_t)(kv8 ? oracle_round_e5m2(s->k[i]) : s->k[i]);
 		}
 
 #pragma omp parallel for schedule(static)
@@ -454,4 +474,11 @@ int oracle_sample(const float* logits, int n, float temperature, float minp, uns
 			if (r < cdf) return i;
 		}
 	return fallback;
+}
+
+/* bench.py's CPU arm: copy a row-major matrix so that the OpenMP thread which will later READ a row (static row split,
+ * as the reference's matmul does, infer.c:209-221) is the one that first touches its destination pages. */
+void oracle_parallel_copy(void* dst, const void* src, size_t rows, size_t row_bytes) {
+#pragma omp parallel for schedule(static)
+	for (long long r = 0; r < (long long)rows; ++r) memcpy((char*)dst + (size_t)r * row_bytes, (const char*)src + (size_t)r * row_bytes, row_bytes);
 }

@@ -23,19 +23,17 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 from make_golden import GOLDEN_SPECS, model_digest  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-ENGINES = [2, 0]  # 2 = persistent kernel (default), 0 = one kernel per stage; engine 1 (TMA ring) is covered by test_engines_agree
 
 
-def run_device(spec, seed, tokens, pos0=0, seq_len=None, engine=0, kvbits=16):
+def run_device(spec, seed, tokens, pos0=0, seq_len=None, kvbits=16):
     host = mg.HostModel(spec, seed=seed, seq_len=seq_len)
-    with lib.DeviceModel(spec, host.tensors, seq_len=seq_len, engine=engine, kvbits=kvbits) as dm:
+    with lib.DeviceModel(spec, host.tensors, seq_len=seq_len, kvbits=kvbits) as dm:
         logits = np.stack([dm.forward(t, pos0 + i) for i, t in enumerate(tokens)])
     return logits
 
 
-@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", GOLDEN_SPECS)
-def test_logits_match_golden_and_oracle(oracle_pkg, name, engine):
+def test_logits_match_golden_and_oracle(oracle_pkg, name):
     g = golden(name)
     spec = mg.SPECS[name]
     host = mg.HostModel(spec, seed=0)
@@ -43,7 +41,7 @@ def test_logits_match_golden_and_oracle(oracle_pkg, name, engine):
     toks = [int(t) for t in g["tokens"]]
     ck = oracle_pkg.Checker("port")
     ref = oracle_pkg.teacher_forced(ck, host, toks)
-    with lib.DeviceModel(spec, host.tensors, engine=engine) as dm:
+    with lib.DeviceModel(spec, host.tensors) as dm:
         got = np.stack([dm.forward(t, i) for i, t in enumerate(toks)])
         sigma = float(ref.std())
         tol = TOL_SIGMA * sigma
@@ -63,8 +61,7 @@ def test_logits_match_golden_and_oracle(oracle_pkg, name, engine):
     ck.release(host)
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-def test_against_live_reference(oracle_pkg, engine):
+def test_against_live_reference(oracle_pkg):
     """The unmodified reference CPU backend, executed on this box, different seed / positions."""
     if not oracle_pkg.available("reference"):
         pytest.skip("oracle/_ref/libcalm_ref_cpu.so did not travel")
@@ -73,71 +70,55 @@ def test_against_live_reference(oracle_pkg, engine):
         toks = mg.teacher_tokens(spec.vocab_size, 20, start=50)
         host = mg.HostModel(spec, seed=5)
         ref = oracle_pkg.teacher_forced(oracle_pkg.Checker("reference"), host, toks)
-        got = run_device(spec, 5, toks, engine=engine)
+        got = run_device(spec, 5, toks)
         tol = TOL_SIGMA * ref.std()
         assert np.abs(got - ref).max() <= tol, name
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-def test_kv_only_flag_and_prompt_pipeline(oracle_pkg, engine):
+def test_kv_only_flag_and_prompt_pipeline(oracle_pkg):
     """FF_UPDATE_KV_ONLY returns NULL, still advances the cache (reference infer.cu:724-727), and a
     prompt fed that way gives the same final logits as feeding it with logits requested."""
     spec = mg.SPECS["tiny-fp8"]
     toks = mg.teacher_tokens(spec.vocab_size, 16)
     host = mg.HostModel(spec, seed=2)
-    full = run_device(spec, 2, toks, engine=engine)
-    with lib.DeviceModel(spec, host.tensors, engine=engine) as dm:
+    full = run_device(spec, 2, toks)
+    with lib.DeviceModel(spec, host.tensors) as dm:
         for i, t in enumerate(toks[:-1]):
             assert dm.forward(t, i, FF_UPDATE_KV_ONLY) is None
         last = dm.forward(toks[-1], len(toks) - 1)
     np.testing.assert_array_equal(last, full[-1])  # same kernels, same order: bit-identical
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-def test_rolling_cache_with_sinks(oracle_pkg, engine):
+def test_rolling_cache_with_sinks(oracle_pkg):
     """pos >= seq_len: ring buffer with 2 pinned, re-rotated sinks (reference infer.c:330-332, 384-394)."""
     spec = mg.SPECS["tiny-fp8"]
     toks = mg.teacher_tokens(spec.vocab_size, 40)
     host = mg.HostModel(spec, seed=1, seq_len=16)
     ref = oracle_pkg.teacher_forced(oracle_pkg.Checker("port"), host, toks)
-    got = run_device(spec, 1, toks, seq_len=16, engine=engine)
+    got = run_device(spec, 1, toks, seq_len=16)
     # the sinks are re-rounded to fp16 every step, which compounds; allow 4x the base tolerance
     assert np.abs(got - ref).max() <= 4 * TOL_SIGMA * ref.std()
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-def test_device_argmax_and_greedy_loop(oracle_pkg, engine):
+def test_device_argmax_and_greedy_loop(oracle_pkg):
     """Device-side greedy pick == host argmax with the reference tie rule (sampler.c:34-42), and the
     device-resident decode loop reproduces the host-stepped loop token for token."""
     spec = mg.SPECS["tiny-llama"]
     host = mg.HostModel(spec, seed=4)
-    with lib.DeviceModel(spec, host.tensors, engine=engine) as dm:
+    with lib.DeviceModel(spec, host.tensors) as dm:
         tok, seq = 5, []
         for pos in range(20):
             logits = dm.forward(tok, pos)
             tok = int(np.argmax(logits))  # numpy argmax: first maximum
             seq.append(tok)
-    with lib.DeviceModel(spec, host.tensors, engine=engine) as dm:
+    with lib.DeviceModel(spec, host.tensors) as dm:
         tok, seq2 = 5, []
         for pos in range(20):
             tok = dm.forward_argmax(tok, pos)
             seq2.append(tok)
-    with lib.DeviceModel(spec, host.tensors, engine=engine) as dm:
+    with lib.DeviceModel(spec, host.tensors) as dm:
         seq3 = list(dm.decode_greedy(5, 0, 20))
     assert seq == seq2 == seq3
-
-
-def test_engines_agree():
-    """The three CUDA engines compute the same function with different summation trees: logits agree to a
-    few fp32 ulps of the accumulations, greedy tokens are identical."""
-    for name in ("tiny-llama", "tiny-qwen", "tiny-gf4"):
-        spec = mg.SPECS[name]
-        toks = mg.teacher_tokens(spec.vocab_size, 24)
-        a = run_device(spec, 9, toks, engine=0)
-        for eng in (1, 2):
-            b = run_device(spec, 9, toks, engine=eng)
-            assert np.abs(a - b).max() <= 1e-3 * a.std(), (name, eng)
-            assert (a.argmax(1) == b.argmax(1)).all()
 
 
 @pytest.mark.parametrize("dbits,n,d", [(8, 4096, 512), (16, 896, 130), (4, 4096, 96), (8, 14336, 64), (16, 4096, 33), (4, 1792, 40), (8, 32, 8)])
@@ -180,8 +161,7 @@ def test_full_size_matvec_properties(oracle_pkg):
     assert np.abs(y1[rows] - ref).max() <= 1e-4 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-def test_full_size_layer_count_independent_shapes(oracle_pkg, engine):
+def test_full_size_layer_count_independent_shapes(oracle_pkg):
     """Llama-3-8B widths (dim 4096, hidden 14336, 32/8 heads of 128, vocab 128256) with 2 layers: the
     real row lengths / head shapes at a depth the oracle finishes in seconds."""
     spec = mg.SPECS["llama3-8b-fp8"]
@@ -191,7 +171,7 @@ def test_full_size_layer_count_independent_shapes(oracle_pkg, engine):
     toks = mg.teacher_tokens(spec.vocab_size, 6)
     host = mg.HostModel(spec, seed=0)
     ref = oracle_pkg.teacher_forced(oracle_pkg.Checker("port"), host, toks)
-    with lib.DeviceModel(spec, host.tensors, engine=engine) as dm:
+    with lib.DeviceModel(spec, host.tensors) as dm:
         got = np.stack([dm.forward(t, i) for i, t in enumerate(toks)])
     tol = TOL_SIGMA * ref.std()
     print(f"llama3-8b widths, 2 layers: |cuda-oracle| {np.abs(got - ref).max():.2e} tol {tol:.2e}")
@@ -201,15 +181,15 @@ def test_full_size_layer_count_independent_shapes(oracle_pkg, engine):
     assert (got.argmax(1)[safe] == ref.argmax(1)[safe]).all()
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-def test_long_context_attention_property(engine):
-    """Attention over a long, synthetic cache: with all keys of a head identical the softmax is uniform,
-    so the output equals the mean of the values, whatever the split over CTAs."""
+def test_long_context_is_idempotent():
+    """Attention over a long, synthetic cache: the same token at the same position twice gives bit-identical logits
+    (the cache slot is rewritten identically and the split over CTAs is deterministic).  The VALUES at long context are
+    checked against the oracle in tests/test_scale_gpu.py."""
     spec = mg.SPECS["tiny-llama"]
     host = mg.HostModel(spec, seed=7, seq_len=2048)
-    with lib.DeviceModel(spec, host.tensors, seq_len=2048, engine=engine) as dm:
+    with lib.DeviceModel(spec, host.tensors, seq_len=2048) as dm:
         dm.fill_kv(2000, seed=3)
         a = dm.forward(3, 2000)
-        b = dm.forward(3, 2000)  # same token at the same position: idempotent (cache slot rewritten identically)
+        b = dm.forward(3, 2000)
         np.testing.assert_array_equal(a, b)
         assert np.isfinite(a).all()

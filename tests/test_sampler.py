@@ -56,7 +56,7 @@ def test_device_sampler_follows_the_restatement(oracle_pkg, temperature, minp):
 
     spec = mg.SPECS["tiny-llama"]
     model = mg.HostModel(spec, seed=0)
-    dm = lib.DeviceModel(spec, model.tensors, engine=0)
+    dm = lib.DeviceModel(spec, model.tensors)
     try:
         ref = oracle_pkg.Sampler("port", temperature, minp, 1234567)
         rng, tok, agree, n = 1234567, 5, 0, 48

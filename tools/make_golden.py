@@ -27,7 +27,7 @@ import oracle  # noqa: E402
 from calm_b200 import modelgen as mg  # noqa: E402
 
 GOLDEN_SPECS = ["tiny-fp8", "tiny-fp16", "tiny-gf4", "tiny-qwen", "tiny-llama", "tiny-moe", "tiny-moe-gf4",
-                "tiny-gelu-clip", "tiny-ln", "tiny-lnpar", "tiny-mha", "tiny-bias2"]
+                "tiny-gelu-clip", "tiny-ln", "tiny-lnpar", "tiny-mha", "tiny-bias2", "tiny-hd256"]
 N_TOKENS = 24
 STEPS = [0, 1, 7, 15, 23]
 KVPOS = [0, 5, 23]
@@ -47,7 +47,10 @@ def main():
     ck = oracle.Checker("reference")
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    only = sys.argv[1:]  # optional: regenerate just these fixtures
     for name in GOLDEN_SPECS:
+        if only and name not in only:
+            continue
         spec = mg.SPECS[name]
         model = mg.HostModel(spec, seed=0)
         toks = mg.teacher_tokens(spec.vocab_size, N_TOKENS)
