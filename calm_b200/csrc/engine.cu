@@ -19,6 +19,7 @@
 namespace {
 
 #define MAX_STAMPS (2 + 5 * MAX_LAYERS)
+#define TP_MAX_CAND 2048 // greedy candidates (classifier CTAs) per rank in the tensor-parallel gather area
 enum Stage { ST_EMBED, ST_QKV, ST_ATTN, ST_WO, ST_FFN_UP, ST_FFN_DOWN, ST_OUTPUT, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"embed", "matmul_qkv", "attention", "matmul_attn", "matmul_ffn_up", "matmul_ffn_down", "output"};
 
@@ -73,7 +74,10 @@ struct Engine {
 	void* tp_comm = nullptr;         // ncclComm_t
 	float* xpart = nullptr;          // partial of wo / w2 before the all-reduce (NCCL path)
 	bool tp_fused = false;           // wo / w2 sum their partials inside k_matres over peer memory (stages.cuh TpExchange)
-	void* tp_area = nullptr;         // this rank's exchange area: {partial, epoch} cells
+	size_t up_expert_stride = 0;     // 16-byte vectors between experts of w1 / w3 once the rows are sharded
+	int out_row0 = 0, out_row1 = 0;  // classifier rows of this rank (vocabulary split; the whole vocabulary without tensor parallelism)
+	size_t tp_off_logits = 0, tp_off_cval = 0, tp_off_cidx = 0, tp_off_flags = 0; // byte offsets of the gather area inside every rank's exchange area
+	void* tp_area = nullptr;         // this rank's exchange area: {partial, epoch} cells, then the logits gather area
 	void* tp_peer[TP_MAX_WORLD] = {}; // every rank's area as mapped here (own entry == tp_area)
 	int* tp_err = nullptr;           // mapped host word for the exchange watchdog
 	std::vector<void*> tp_owned;     // shard copies made by prepare_cuda (wo / w2 column slices, packed biases)
@@ -220,7 +224,13 @@ void tp_allreduce(float* buf, size_t count) {
 // back to ncclAllReduce + k_addvec when peer mapping is unavailable on ANY rank (the ranks agree via an all-reduce).
 void tp_setup_exchange() {
 	const int W = g.tp_world, dim = g.cfg.dim;
-	const size_t bytes = (size_t)2 * W * dim * sizeof(uint2); // cell[slot][src][row]
+	// cell[slot][src][row] | logits[vocab] | cand_val[W][TP_MAX_CAND] | cand_idx[W][TP_MAX_CAND] | flags[W]
+	auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+	g.tp_off_logits = up((size_t)2 * W * dim * sizeof(uint2));
+	g.tp_off_cval = g.tp_off_logits + up((size_t)g.cfg.vocab_size * sizeof(float));
+	g.tp_off_cidx = g.tp_off_cval + up((size_t)W * TP_MAX_CAND * sizeof(float));
+	g.tp_off_flags = g.tp_off_cidx + up((size_t)W * TP_MAX_CAND * sizeof(int));
+	const size_t bytes = g.tp_off_flags + up((size_t)W * sizeof(unsigned));
 	bool ok = W <= TP_MAX_WORLD && !(getenv("CALM_B200_TP_FUSED") && atoi(getenv("CALM_B200_TP_FUSED")) == 0);
 	g.tp_area = dev_alloc(bytes);
 	CUDA_CHECK(cudaMemset(g.tp_area, 0, bytes));
@@ -462,6 +472,7 @@ int run_token(int mode) {
 			a.dim = dim, a.hidden = hidden, a.n_experts = c.n_experts, a.nact = g.nact;
 			a.eps = c.norm_eps, a.ln = c.norm_ln, a.gelu = c.act_gelu;
 			a.tile_ctr = g.tile_ctr ? g.tile_ctr + l : nullptr;
+			a.expert_stride = g.up_expert_stride;
 			a.stamp = t.slot;
 			if (dense && g.pf_up_down) a.pf.p[0] = w.w2[l], a.pf.bytes[0] = (g.pf_up_down < down_bytes ? g.pf_up_down : down_bytes) & ~(size_t)15;
 			bool done = false;
@@ -502,17 +513,38 @@ int run_token(int mode) {
 		a.dim = dim, a.vocab = c.vocab_size, a.eps = c.norm_eps, a.ln = c.norm_ln;
 		a.stamp = t.slot;
 		int grid = g.grid_out;
+		const bool split = g.tp_fused; // classifier rows divided over the ranks, slices pushed into every rank's gather area
+		int ncand = grid;
+		const float* cand_val = g.cand_val;
+		const int* cand_idx = g.cand_idx;
+		if (split) {
+			a.row0 = g.out_row0, a.row1 = g.out_row1, a.world = g.tp_world, a.rank = g.tp_rank;
+			for (int p = 0; p < g.tp_world; ++p) {
+				char* area = (char*)g.tp_peer[p];
+				a.peer_logits[p] = (float*)(area + g.tp_off_logits), a.peer_cand_val[p] = (float*)(area + g.tp_off_cval), a.peer_cand_idx[p] = (int*)(area + g.tp_off_cidx);
+			}
+			ncand = grid * g.tp_world;
+			cand_val = (const float*)((char*)g.tp_area + g.tp_off_cval), cand_idx = (const int*)((char*)g.tp_area + g.tp_off_cidx);
+		}
 		launch_pdl(k_output<DBITS>, grid, 256, g.smem_dim, a);
 		++nl;
+		if (split) {
+			TpGatherArgs ga = {};
+			ga.world = g.tp_world, ga.rank = g.tp_rank, ga.tp = g.tp, ga.err = g.tp_err;
+			for (int p = 0; p < g.tp_world; ++p) ga.flags[p] = (unsigned*)((char*)g.tp_peer[p] + g.tp_off_flags);
+			ga.src = (const float*)((char*)g.tp_area + g.tp_off_logits), ga.dst = a.logits, ga.n = c.vocab_size;
+			launch_pdl(k_tp_gather, 32, 256, 0, ga);
+			++nl;
+		}
 		if (mode == 4) { // min-p sampling on the device (reference sampler.c:44-90), then the bookkeeping of k_advance
 			SampleArgs sa;
-			sa.logits = g.logits_dev, sa.cand_val = g.cand_val, sa.ncand = grid, sa.vocab = c.vocab_size, sa.nchunks = g.sample_chunks;
+			sa.logits = g.logits_dev, sa.cand_val = cand_val, sa.ncand = ncand, sa.vocab = c.vocab_size, sa.nchunks = g.sample_chunks;
 			sa.st = g.sample_state, sa.count = g.sample_count, sa.csum = g.sample_csum, sa.sidx = g.sample_idx, sa.sprob = g.sample_prob;
 			launch_pdl(k_sample_scan, g.sample_chunks, 256, 0, sa);
-			launch_pdl(k_sample_pick, 1, 32, 0, sa, g.sample_state, g.tp, g.out_tokens, g.last_token, 1);
+			launch_pdl(k_sample_pick, 1, 256, 0, sa, g.sample_state, g.tp, g.out_tokens, g.last_token, 1);
 			nl += 2;
 		} else if (mode >= 2) {
-			launch_pdl(k_advance, 1, 256, 0, (const float*)g.cand_val, (const int*)g.cand_idx, grid, g.tp, g.out_tokens, g.last_token, (int)(mode == 2), c.vocab_size);
+			launch_pdl(k_advance, 1, 256, 0, cand_val, cand_idx, ncand, g.tp, g.out_tokens, g.last_token, (int)(mode == 2), c.vocab_size);
 			++nl;
 		}
 	}
@@ -533,7 +565,7 @@ void tp_shard_model() {
 	Config& c = g.cfg;
 	Weights& w = g.w;
 	const int N = g.tp_world, r = g.tp_rank;
-	if (c.n_experts) CALM_FATAL("tensor parallelism: MoE models are not sharded yet");
+	const int ne = c.n_experts ? c.n_experts : 1; // MoE: the same split inside every expert (all ranks serve both active experts)
 	if (c.n_heads % N || c.n_kv_heads % N || c.hidden_dim % (32 * N)) CALM_FATAL("tensor parallelism: %d ranks do not divide heads %d/%d or hidden %d", N, c.n_heads, c.n_kv_heads, c.hidden_dim);
 	const size_t wb = (size_t)w.dbits;
 	const int q_dim = c.head_dim * c.n_heads, kv_dim = c.head_dim * c.n_kv_heads;
@@ -549,10 +581,10 @@ void tp_shard_model() {
 		w.wq[l] = rows(w.wq[l], (size_t)r * ql, c.dim);
 		w.wk[l] = rows(w.wk[l], (size_t)r * kl, c.dim);
 		w.wv[l] = rows(w.wv[l], (size_t)r * kl, c.dim);
-		w.w1[l] = rows(w.w1[l], (size_t)r * hl, c.dim);
+		w.w1[l] = rows(w.w1[l], (size_t)r * hl, c.dim); // expert e's rows start e * (full hidden) rows further: up_expert_stride
 		w.w3[l] = rows(w.w3[l], (size_t)r * hl, c.dim);
 		w.wo[l] = col_slice(w.wo[l], c.dim, q_dim, (size_t)r * ql, ql);
-		w.w2[l] = col_slice(w.w2[l], c.dim, c.hidden_dim, (size_t)r * hl, hl);
+		w.w2[l] = col_slice(w.w2[l], ne * c.dim, c.hidden_dim, (size_t)r * hl, hl); // [expert][dim][hl], packed
 		if (w.bqkv[l]) { // [q | k | v] -> this rank's [q_r | k_r | v_r]
 			float* b = (float*)dev_alloc((size_t)(ql + 2 * kl) * sizeof(float));
 			CUDA_CHECK(cudaMemcpy(b, w.bqkv[l] + (size_t)r * ql, ql * sizeof(float), cudaMemcpyDeviceToDevice));
@@ -562,6 +594,7 @@ void tp_shard_model() {
 			w.bqkv[l] = b;
 		}
 	}
+	if (c.n_experts) g.up_expert_stride = (size_t)c.hidden_dim * c.dim * wb / 8 / 16;
 	c.n_heads /= N, c.n_kv_heads /= N, c.hidden_dim = hl;
 }
 
@@ -600,7 +633,15 @@ void make_plan() {
 			g.grid_up_mma = imin(max_ctas(k_ffn_up_mma<DBITS>, 256, g.smem_dim), c.hidden_dim / 8);
 		}
 	}
-	g.grid_out = balanced_grid(cdiv(c.vocab_size, 32), max_ctas(k_output<DBITS>, 256, g.smem_dim));
+	g.out_row0 = 0, g.out_row1 = c.vocab_size;
+	if (g.tp_fused) { // vocabulary split: equal slices of whole 32-row CTA iterations (the last rank's may be short)
+		const int per = cdiv(cdiv(c.vocab_size, g.tp_world), 32) * 32;
+		g.out_row0 = imin(c.vocab_size, g.tp_rank * per), g.out_row1 = imin(c.vocab_size, g.out_row0 + per);
+		g.grid_out = balanced_grid(cdiv(per, 32), max_ctas(k_output<DBITS>, 256, g.smem_dim)); // the same grid on every rank
+		if (g.grid_out > TP_MAX_CAND) CALM_FATAL("tensor parallelism: %d classifier CTAs exceed the gather area", g.grid_out);
+	} else {
+		g.grid_out = balanced_grid(cdiv(c.vocab_size, 32), max_ctas(k_output<DBITS>, 256, g.smem_dim));
+	}
 	g.ncand = g.grid_out;
 }
 
@@ -974,6 +1015,63 @@ extern "C" int calm_b200_forward_sample(struct Transformer* transformer, int tok
 	int tok = 0;
 	calm_b200_decode_sample(transformer, token, pos, 1, temperature, minp, rng_state, &tok);
 	return tok;
+}
+
+// The device sampler on its own: logits given by the host, any vocabulary size; returns the token and advances *rng_state.
+// Same kernels as the decode loop (k_sample_scan + k_sample_pick); device_us (optional) receives their mean duration.
+extern "C" int calm_b200_sample_logits(const float* logits_host, int vocab, float temperature, float minp, unsigned long long* rng_state, float* device_us) {
+	select_device();
+	if (vocab <= 0) CALM_FATAL("sample_logits: empty vocabulary");
+	if (temperature == 0.0f || minp >= 1.0f) { // greedy, first maximum (sampler.c:34-42); the generator is not touched
+		int best = 0;
+		for (int i = 1; i < vocab; ++i)
+			if (logits_host[i] > logits_host[best]) best = i;
+		if (device_us) *device_us = 0.f;
+		return best;
+	}
+	const int nchunks = cdiv(vocab, SAMPLE_CHUNK);
+	cudaStream_t st;
+	CUDA_CHECK(cudaStreamCreate(&st));
+	float* logits = (float*)dev_alloc((size_t)vocab * sizeof(float));
+	float* cmax = (float*)dev_alloc(nchunks * sizeof(float));
+	SampleState* sst = (SampleState*)dev_alloc(sizeof(SampleState));
+	int* count = (int*)dev_alloc(nchunks * sizeof(int));
+	float* csum = (float*)dev_alloc(nchunks * sizeof(float));
+	int* sidx = (int*)dev_alloc((size_t)nchunks * SAMPLE_CHUNK * sizeof(int));
+	float* sprob = (float*)dev_alloc((size_t)nchunks * SAMPLE_CHUNK * sizeof(float));
+	int* tok = (int*)dev_alloc(sizeof(int));
+	TokenParams* tp = (TokenParams*)dev_alloc(sizeof(TokenParams));
+	CUDA_CHECK(cudaMemcpyAsync(logits, logits_host, (size_t)vocab * sizeof(float), cudaMemcpyHostToDevice, st));
+	SampleState hs;
+	hs.rng = *rng_state, hs.temperature = temperature, hs.cut_delta = logf(minp) * temperature;
+	SampleArgs sa;
+	sa.logits = logits, sa.cand_val = cmax, sa.ncand = nchunks, sa.vocab = vocab, sa.nchunks = nchunks;
+	sa.st = sst, sa.count = count, sa.csum = csum, sa.sidx = sidx, sa.sprob = sprob;
+	cudaEvent_t e0, e1;
+	CUDA_CHECK(cudaEventCreate(&e0));
+	CUDA_CHECK(cudaEventCreate(&e1));
+	const int reps = device_us ? 5 : 1;
+	float ms = 0;
+	for (int r = 0; r < reps; ++r) { // every repetition restarts from the caller's generator state: same draw
+		CUDA_CHECK(cudaMemcpyAsync(sst, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+		k_chunk_max<<<nchunks, 256, 0, st>>>(logits, vocab, cmax);
+		CUDA_CHECK(cudaEventRecord(e0, st));
+		k_sample_scan<<<nchunks, 256, 0, st>>>(sa);
+		k_sample_pick<<<1, 256, 0, st>>>(sa, sst, tp, nullptr, tok, 0);
+		CUDA_CHECK(cudaEventRecord(e1, st));
+		CUDA_CHECK(cudaEventSynchronize(e1));
+		CUDA_CHECK(cudaGetLastError());
+		CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+		g_launches += 3;
+	}
+	if (device_us) *device_us = ms * 1e3f;
+	int htok = 0;
+	CUDA_CHECK(cudaMemcpy(&htok, tok, sizeof(int), cudaMemcpyDeviceToHost));
+	CUDA_CHECK(cudaMemcpy(&hs, sst, sizeof(hs), cudaMemcpyDeviceToHost));
+	*rng_state = hs.rng;
+	cudaFree(logits), cudaFree(cmax), cudaFree(sst), cudaFree(count), cudaFree(csum), cudaFree(sidx), cudaFree(sprob), cudaFree(tok), cudaFree(tp);
+	cudaEventDestroy(e0), cudaEventDestroy(e1), cudaStreamDestroy(st);
+	return htok;
 }
 
 // the logits of the last device-resident step (decode_greedy / decode_sample keep them in HBM): copy for tests

@@ -855,8 +855,9 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 			else
 				warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
 			if (lane == 0) {
-				if (a.tpx.world > 1) { // this rank's partial: summed over the ranks below
-					tp_part[it * 16 + warp * 2] = v[0], tp_part[it * 16 + warp * 2 + 1] = v[1];
+				if (a.tpx.world > 1) { // this rank's partial (router-weighted over the active experts, in selection order): summed over the ranks below
+					float* tpp = tp_part + it * 16 + warp * 2;
+					tpp[0] = (e ? tpp[0] : 0.f) + v[0] * ew, tpp[1] = (e ? tpp[1] : 0.f) + v[1] * ew;
 					continue;
 				}
 				float2* dst = reinterpret_cast<float2*>(a.y + 2 * p);
@@ -867,7 +868,7 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 			}
 		}
 	}
-	if (a.tpx.world > 1) { // dense models only (nact == 1); blockDim.x == 256, i.e. 16 rows per CTA and iteration
+	if (a.tpx.world > 1) { // blockDim.x == 256, i.e. 16 rows per CTA and iteration
 		const int per = gridDim.x * 8;
 		tp_exchange_add(a.tpx, tp_part, (a.d / 2 - blockIdx.x * 8 + per - 1) / per, a.y, a.d);
 	}
@@ -893,6 +894,7 @@ struct FfnUpArgs {
 	float eps;
 	int ln, gelu;
 	int* tile_ctr;      // k_ffn_up_mma: tiles beyond the first round are handed out through this counter (NULL: static stride)
+	size_t expert_stride; // 16-byte vectors between experts in w1 / w3 (tensor parallelism: a rank's rows are a slice of every expert)
 };
 
 template <int DBITS, int EARLY>
@@ -946,7 +948,7 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpA
 		__syncthreads();
 	}
 
-	const size_t esize = (size_t)a.hidden * nvec;
+	const size_t esize = a.expert_stride ? a.expert_stride : (size_t)a.hidden * nvec;
 	const int total = a.nact * a.hidden;
 	for (int p = blockIdx.x * nwarps + warp; p < total; p += gridDim.x * nwarps) {
 		int e = p / a.hidden, i = p % a.hidden;
@@ -1183,6 +1185,13 @@ struct OutputArgs {
 	float eps;
 	int ln;
 	unsigned long long* stamp;
+	// tensor parallelism ("lm_head: rows split by vocab"): this rank owns classifier rows [row0, row1) and
+	// stores its logits and per-CTA greedy candidates straight into EVERY rank's gather area over NVLink (peer[rank] is
+	// its own); k_tp_gather then waits for all slices.  world <= 1: rows [0, vocab) into `logits` / `cand_*`.
+	int row0, row1, world, rank;
+	float* peer_logits[TP_MAX_WORLD];
+	float* peer_cand_val[TP_MAX_WORLD]; // [world][gridDim.x]
+	int* peer_cand_idx[TP_MAX_WORLD];
 };
 
 template <int DBITS>
@@ -1204,11 +1213,12 @@ __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
 	float best = -FLT_MAX;
 	int besti = 0x7fffffff;
 
-	for (int base = blockIdx.x * rows_per_iter; base < a.vocab; base += gridDim.x * rows_per_iter) {
+	const int row_end = a.world > 1 ? a.row1 : a.vocab;
+	for (int base = (a.world > 1 ? a.row0 : 0) + blockIdx.x * rows_per_iter; base < row_end; base += gridDim.x * rows_per_iter) {
 		int r0 = base + warp * R;
 		const uint4* rp[R];
 #pragma unroll
-		for (int r = 0; r < R; ++r) rp[r] = reinterpret_cast<const uint4*>(a.wcls) + (size_t)min(r0 + r, a.vocab - 1) * nvec;
+		for (int r = 0; r < R; ++r) rp[r] = reinterpret_cast<const uint4*>(a.wcls) + (size_t)min(r0 + r, row_end - 1) * nvec;
 		float v[R];
 		warp_dot_rows<DBITS, R>(rp, nvec, reinterpret_cast<const float4*>(xs), v);
 		if (lane == 0) {
@@ -1216,25 +1226,85 @@ __global__ void __launch_bounds__(256) k_output(const OutputArgs a) {
 			for (int r = 0; r < R; ++r) {
 				v[r] *= post;
 				outbuf[warp * R + r] = v[r];
-				if (r0 + r < a.vocab && v[r] > best) best = v[r], besti = r0 + r;
+				if (r0 + r < row_end && v[r] > best) best = v[r], besti = r0 + r;
 			}
 		}
 		__syncthreads();
-		if (threadIdx.x < rows_per_iter && base + (int)threadIdx.x < a.vocab) a.logits[base + threadIdx.x] = outbuf[threadIdx.x];
+		if (threadIdx.x < rows_per_iter && base + (int)threadIdx.x < row_end) {
+			if (a.world > 1) {
+				for (int p = 0; p < a.world; ++p) a.peer_logits[p][base + threadIdx.x] = outbuf[threadIdx.x];
+			} else {
+				a.logits[base + threadIdx.x] = outbuf[threadIdx.x];
+			}
+		}
 		__syncthreads();
 	}
 
-	if (a.cand_val) {
+	if (a.cand_val || a.world > 1) {
 		if (lane == 0) bval[warp] = best, bidx[warp] = besti;
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			for (int w = 1; w < nwarps; ++w)
 				if (bval[w] > best || (bval[w] == best && bidx[w] < besti)) best = bval[w], besti = bidx[w];
-			a.cand_val[blockIdx.x] = best;
-			a.cand_idx[blockIdx.x] = besti;
+			if (a.world > 1) {
+				for (int p = 0; p < a.world; ++p) a.peer_cand_val[p][a.rank * gridDim.x + blockIdx.x] = best, a.peer_cand_idx[p][a.rank * gridDim.x + blockIdx.x] = besti;
+			} else {
+				a.cand_val[blockIdx.x] = best;
+				a.cand_idx[blockIdx.x] = besti;
+			}
 		}
 	}
+	if (a.world > 1) __threadfence_system(); // the slices must be visible to the peers before k_tp_gather raises this rank's flag
 	stamp_end(a.stamp);
+}
+
+// Tensor parallelism, after k_output: tell every peer that this rank's logits slice has landed, wait for theirs, then
+// copy the complete vector from the gather area to where the caller wants it (mapped host memory or the device copy).
+// flag cell [src rank] in every rank's area holds the token sequence number of the last complete slice from that rank.
+// A rank cannot overwrite a peer's gather area before the peer has copied it out: its next classifier launch lies behind a
+// full token of per-layer exchanges with that peer.
+struct TpGatherArgs {
+	int world, rank;
+	const TokenParams* tp;
+	unsigned* flags[TP_MAX_WORLD]; // rank p's flag cells [world]
+	const float* src;
+	float* dst; // NULL: no copy
+	int n;
+	int* err;
+};
+
+__global__ void __launch_bounds__(256) k_tp_gather(const TpGatherArgs a) {
+	pdl_enter();
+	const unsigned epoch = (unsigned)a.tp->tp_seq;
+	if (blockIdx.x == 0 && (int)threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
+		__threadfence_system();
+		asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(a.flags[threadIdx.x] + a.rank), "r"(epoch) : "memory");
+	}
+	if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
+		unsigned v, spins = 0;
+		unsigned long long t0 = 0;
+		for (;;) {
+			asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags[a.rank] + threadIdx.x) : "memory");
+			if (v == epoch) break;
+			if ((++spins & 1023) == 0) {
+				const unsigned long long now = globaltimer_ns();
+				if (!t0) t0 = now;
+				if (now - t0 > 20000000000ull) { // 20 s: a peer died or the ranks diverged -- fail loudly, never hang the GPU
+					if (a.err) *reinterpret_cast<volatile int*>(a.err) = 9100 + threadIdx.x;
+					__threadfence_system();
+					__trap();
+				}
+			}
+		}
+	}
+	__syncthreads();
+	if (a.dst) {
+		const float4* s4 = reinterpret_cast<const float4*>(a.src);
+		float4* d4 = reinterpret_cast<float4*>(a.dst);
+		const int n4 = a.n >> 2;
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) d4[i] = __ldcg(s4 + i);
+		for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) a.dst[i] = __ldcg(a.src + i);
+	}
 }
 
 // Fold the per-CTA candidates, publish the greedy token, and advance the token parameters so the
@@ -1376,36 +1446,53 @@ __device__ __forceinline__ unsigned xorshift_u32(unsigned long long& s) { // ref
 	return (unsigned)((s * 0x2545F4914F6CDD1Dull) >> 32);
 }
 
-// one thread: the reference's two sequential passes; then the bookkeeping of k_advance
-__global__ void k_sample_pick(const SampleArgs a, SampleState* st, TokenParams* tp, int* out_tokens, int* last_token, int advance) {
+// The reference's two sequential passes (sum, then walk to the coin), then the bookkeeping of k_advance.  One CTA: up to
+// SAMPLE_EXACT survivors are first gathered -- in index order, coalesced -- into shared memory by all threads, and thread 0
+// then performs exactly the reference's left-to-right float additions on them (4 cycles each instead of a global-memory
+// round trip); with more survivors the per-chunk sums of k_sample_scan are walked and only the chunk holding the coin is
+// expanded.
+__global__ void __launch_bounds__(256) k_sample_pick(const SampleArgs a, SampleState* st, TokenParams* tp, int* out_tokens, int* last_token, int advance) {
 	pdl_enter();
-	if (threadIdx.x != 0) return;
+	__shared__ float sp[SAMPLE_EXACT];
+	__shared__ int si[SAMPLE_EXACT];
+	__shared__ int coff[256]; // exclusive prefix of the chunk counts (nchunks <= 256: vocabularies up to 262144)
+	__shared__ int stotal;
+	const int tid = threadIdx.x;
+	const bool small_tab = a.nchunks <= 256;
+	if (tid == 0) {
+		int total = 0;
+		for (int c = 0; c < a.nchunks; ++c) {
+			if (small_tab) coff[c] = total;
+			total += a.count[c];
+		}
+		stotal = total;
+	}
+	__syncthreads();
+	const int total = stotal;
+	const bool exact = total <= SAMPLE_EXACT && small_tab;
+	if (exact) {
+		for (int c = 0; c < a.nchunks; ++c) {
+			const int n = a.count[c], o = coff[c];
+			for (int j = tid; j < n; j += blockDim.x) sp[o + j] = a.sprob[(size_t)c * SAMPLE_CHUNK + j], si[o + j] = a.sidx[(size_t)c * SAMPLE_CHUNK + j];
+		}
+	}
+	__syncthreads();
+	if (tid != 0) return;
 	unsigned long long rng = st->rng;
 	const float coin = (float)(xorshift_u32(rng) >> 8) / 16777216.0f; // sampler.c:15-17
 	st->rng = rng;
-	int total = 0;
-	for (int c = 0; c < a.nchunks; ++c) total += a.count[c];
-	int tok = 0, fallback = 0;
-	if (total <= SAMPLE_EXACT) {
+	int tok = -1, fallback = 0;
+	if (exact) {
 		float cum = 0.f;
-		for (int c = 0; c < a.nchunks; ++c) {
-			const float* lp = a.sprob + (size_t)c * SAMPLE_CHUNK;
-			const int n = a.count[c];
-			for (int j = 0; j < n; ++j) cum += lp[j];
-			if (n) fallback = a.sidx[(size_t)c * SAMPLE_CHUNK + n - 1];
-		}
+		for (int j = 0; j < total; ++j) cum += sp[j];
+		if (total) fallback = si[total - 1];
 		const float r = coin * cum;
 		float cdf = 0.f;
-		tok = -1;
-		for (int c = 0; c < a.nchunks && tok < 0; ++c) {
-			const float* lp = a.sprob + (size_t)c * SAMPLE_CHUNK;
-			const int n = a.count[c];
-			for (int j = 0; j < n; ++j) {
-				cdf += lp[j];
-				if (r < cdf) {
-					tok = a.sidx[(size_t)c * SAMPLE_CHUNK + j];
-					break;
-				}
+		for (int j = 0; j < total; ++j) {
+			cdf += sp[j];
+			if (r < cdf) {
+				tok = si[j];
+				break;
 			}
 		}
 	} else {
@@ -1416,7 +1503,6 @@ __global__ void k_sample_pick(const SampleArgs a, SampleState* st, TokenParams* 
 		}
 		const float r = coin * cum;
 		float cdf = 0.f;
-		tok = -1;
 		for (int c = 0; c < a.nchunks && tok < 0; ++c) {
 			if (r < cdf + a.csum[c]) {
 				const float* lp = a.sprob + (size_t)c * SAMPLE_CHUNK;
@@ -1446,6 +1532,20 @@ __global__ void k_sample_pick(const SampleArgs a, SampleState* st, TokenParams* 
 		tp->kv_pos = sink + (pos - sink) % (seq_len - sink);
 		tp->kv_len = pos >= seq_len ? seq_len : pos + 1;
 		tp->step += 1;
+	}
+}
+
+// per-chunk maxima of a logits vector (stand-alone sampler entry point: what k_output's candidates are in a token)
+__global__ void __launch_bounds__(256) k_chunk_max(const float* logits, int vocab, float* out) {
+	__shared__ float red[8];
+	float mx = -FLT_MAX;
+	for (int i = blockIdx.x * SAMPLE_CHUNK + threadIdx.x; i < min(vocab, (int)(blockIdx.x + 1) * SAMPLE_CHUNK); i += blockDim.x) mx = fmaxf(mx, logits[i]);
+	mx = warp_max(mx);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+		out[blockIdx.x] = mx;
 	}
 }
 

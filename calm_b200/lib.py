@@ -28,7 +28,7 @@ SYMBOLS = [
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
     "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_perf_token_ms",
     "calm_b200_tp_unique_id", "calm_b200_tp_init", "calm_b200_tp_world", "calm_b200_tp_mode",
-    "calm_b200_decode_sample", "calm_b200_forward_sample", "calm_b200_read_device_logits",
+    "calm_b200_decode_sample", "calm_b200_forward_sample", "calm_b200_read_device_logits", "calm_b200_sample_logits",
 ]
 
 _lib = None
@@ -74,6 +74,8 @@ def load() -> C.CDLL:
     L.calm_b200_forward_sample.argtypes = [T, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_ulonglong)]
     L.calm_b200_forward_sample.restype = C.c_int
     L.calm_b200_read_device_logits.argtypes, L.calm_b200_read_device_logits.restype = [_fptr], None
+    L.calm_b200_sample_logits.argtypes = [_fptr, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_ulonglong), _fptr]
+    L.calm_b200_sample_logits.restype = C.c_int
     _lib = L
     return L
 
@@ -207,3 +209,13 @@ def matvec(dbits: int, w_dev_ptr: int, x: np.ndarray, n: int, d: int, warmup: in
     y = np.zeros(d, np.float32)
     ms = L.calm_b200_matvec(dbits, w_dev_ptr, x.ctypes.data_as(_fptr), y.ctypes.data_as(_fptr), n, d, warmup, iters)
     return y, ms
+
+
+def sample_logits(logits: np.ndarray, temperature: float, minp: float, rng_state: int, timed: bool = False):
+    """The device sampler on host logits; returns (token, new rng state[, microseconds of the sampler kernels])."""
+    L = load()
+    buf = np.ascontiguousarray(logits, np.float32)
+    rng = C.c_ulonglong(rng_state)
+    us = C.c_float(0)
+    tok = L.calm_b200_sample_logits(buf.ctypes.data_as(_fptr), len(buf), temperature, minp, C.byref(rng), C.byref(us) if timed else None)
+    return (tok, int(rng.value), us.value) if timed else (tok, int(rng.value))

@@ -105,6 +105,9 @@ SPECS.update({
     "tiny-mha": replace(_T, name="tiny-mha", n_heads=8, n_kv_heads=8),
     # QKV bias + tied classifier on a shape two tensor-parallel ranks can split (tiny-qwen has a single kv head)
     "tiny-bias2": replace(_T, name="tiny-bias2", dtype="fp16", n_heads=4, n_kv_heads=2, head_dim=64, qkv_bias=True, tied=True),
+    # a shape that 2, 4 and 8 tensor-parallel ranks can split (8 kv heads, hidden = 4 * 32 * 8), and its MoE twin
+    "tiny-tp8": replace(_T, name="tiny-tp8", n_heads=8, n_kv_heads=8, head_dim=32, hidden_dim=1024),
+    "tiny-tp8-moe": replace(_T, name="tiny-tp8-moe", n_heads=8, n_kv_heads=8, head_dim=32, hidden_dim=1024, n_experts=4, n_experts_active=2),
     # Gemma-style multi-query attention: 8 query heads on ONE kv head of 256 dims (the attention kernel's merge
     # records exceed the default 48 KB of dynamic shared memory)
     # (hidden >= dim >= q_dim: the reference CPU backend reuses xb2[dim] and hb[hidden] as scratch, infer.c:152-153, 404, 409)

@@ -24,8 +24,6 @@ def shard_dims(spec: mg.ModelSpec, world: int) -> Dict[str, int]:
     """Per-rank shapes, or ValueError with the reason prepare_cuda would abort for."""
     if world < 1:
         raise ValueError("world must be >= 1")
-    if spec.n_experts and world > 1:
-        raise ValueError("tensor parallelism: MoE models are not sharded yet")
     if spec.n_heads % world or spec.n_kv_heads % world:
         raise ValueError(f"{world} ranks do not divide heads {spec.n_heads}/{spec.n_kv_heads}")
     if spec.hidden_dim % (32 * world):
@@ -43,10 +41,10 @@ def local_spec(spec: mg.ModelSpec, world: int) -> mg.ModelSpec:
 
 
 def _cols(t, c0: int, n: int, dbits: int):
-    """Column range [c0, c0+n) of a row-major quantised matrix; gf4 packs 8 weights per stored u32."""
+    """Column range [c0, c0+n) of a row-major quantised matrix (last axis); gf4 packs 8 weights per stored u32."""
     per = 8 if dbits == 4 else 1
     assert c0 % per == 0 and n % per == 0
-    return t[:, c0 // per:(c0 + n) // per].contiguous()
+    return t[..., c0 // per:(c0 + n) // per].contiguous()
 
 
 def shard_tensors(spec: mg.ModelSpec, tensors: Dict[str, "object"], rank: int, world: int) -> Dict[str, "object"]:
@@ -61,7 +59,7 @@ def shard_tensors(spec: mg.ModelSpec, tensors: Dict[str, "object"], rank: int, w
         elif name.endswith("attn.wk.weight") or name.endswith("attn.wv.weight"):
             t = t[rank * kl:(rank + 1) * kl].contiguous()
         elif name.endswith("mlp.w1.weight") or name.endswith("mlp.w3.weight"):
-            t = t[rank * hl:(rank + 1) * hl].contiguous()
+            t = t[..., rank * hl:(rank + 1) * hl, :].contiguous()  # MoE: the same row range of every expert
         elif name.endswith("attn.wo.weight"):
             t = _cols(t, rank * ql, ql, spec.dbits)
         elif name.endswith("mlp.w2.weight"):
@@ -105,6 +103,7 @@ def main(argv=None):
     ap.add_argument("--tokens", type=int, default=24)
     ap.add_argument("--out", required=True)
     ap.add_argument("--greedy", type=int, default=0, help="also run the device-resident greedy loop for this many tokens")
+    ap.add_argument("--seq-len", type=int, default=None)
     a = ap.parse_args(argv)
 
     import faulthandler
@@ -122,7 +121,7 @@ def main(argv=None):
     else:
         ident = wait_id(a.idfile)
     model = mg.HostModel(spec, seed=0)
-    dm = lib.DeviceModel(spec, model.tensors, device=a.rank, tp=(a.rank, a.world, ident))
+    dm = lib.DeviceModel(spec, model.tensors, device=a.rank, tp=(a.rank, a.world, ident), seq_len=a.seq_len)
     toks = mg.teacher_tokens(spec.vocab_size, a.tokens)
     logits = np.stack([dm.forward(int(t), i) for i, t in enumerate(toks)])
     greedy = dm.decode_greedy(int(toks[0]), 0, a.greedy) if a.greedy else np.zeros(0, np.int32)

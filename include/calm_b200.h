@@ -115,6 +115,10 @@ void calm_b200_decode_sample(struct Transformer* transformer, int token0, int po
 int calm_b200_forward_sample(struct Transformer* transformer, int token, int pos, float temperature, float minp, unsigned long long* rng_state);
 void calm_b200_read_device_logits(float* out_vocab);
 
+/* The same sampler kernels on logits supplied by the host (any vocabulary size, no model needed): returns the token,
+ * advances *rng_state exactly as sample() does; *device_us (optional) = duration of the two sampler kernels. */
+int calm_b200_sample_logits(const float* logits_host, int vocab, float temperature, float minp, unsigned long long* rng_state, float* device_us);
+
 /* Device timer on the library's stream (CUDA events): start, ..., stop -> ms. */
 void calm_b200_timer_start(void);
 float calm_b200_timer_stop(void);

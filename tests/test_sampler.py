@@ -82,6 +82,32 @@ def test_device_sampler_follows_the_restatement(oracle_pkg, temperature, minp):
         dm.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("vocab,scale,temperature,minp", [(128256, 0.3, 1.0, 0.1), (128256, 0.3, 1.0, 0.02), (128256, 4.0, 0.8, 0.05), (128256, 0.05, 1.0, 0.3),
+                                                          (151936, 1.0, 1.2, 0.01), (32000, 0.5, 1.0, 0.1), (1000, 0.3, 1.0, 0.1)])
+def test_device_sampler_at_real_vocabulary(oracle_pkg, vocab, scale, temperature, minp):
+    """The sampler KERNELS (k_sample_scan + k_sample_pick) on Llama-3 / Qwen2 / Mistral sized vocabularies: flat logits
+    (tens of thousands of survivors -> the chunk-sum walk), peaked logits (a handful), many chunks and a ragged tail,
+    against the oracle's restatement of sample() with the same generator state."""
+    from calm_b200 import lib
+
+    rng = np.random.default_rng(vocab + int(scale * 100))
+    ref = oracle_pkg.Sampler("port", temperature, minp, 4242)
+    state, agree, n, surv = 4242, 0, 24, []
+    us_max = 0.0
+    for i in range(n):
+        logits = (rng.standard_normal(vocab) * scale).astype(np.float32)
+        surv.append(int((logits >= logits.max() + np.log(minp) * temperature).sum()))
+        tok, state, us = lib.sample_logits(logits, temperature, minp, state, timed=True)
+        us_max = max(us_max, us)
+        want = ref.sample(logits)
+        assert state == ref.rng_state  # xorshift*: bit exact
+        agree += int(tok == want)
+    print(f"vocab {vocab} scale {scale} T {temperature} minp {minp}: survivors {min(surv)}..{max(surv)}, agree {agree}/{n}, sampler kernels <= {us_max:.1f} us")
+    # <= 2048 survivors: the reference's own additions, at most a stray expf-vs-libm bin edge; beyond, chunk sums move an edge by ulps
+    assert agree >= n - (1 if max(surv) <= 2048 else 2), (agree, n, max(surv))
+
+
 def _device_algorithm(logits, temperature, minp, rng_state, chunk=1024, exact=2048):
     """Python mirror of k_sample_scan + k_sample_pick (stages.cuh): chunked compaction in index order, then the exact walk
     (<= `exact` survivors) or the chunk-sum walk.  float32 arithmetic step by step, like the one device thread."""

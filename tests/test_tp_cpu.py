@@ -20,13 +20,26 @@ def test_shard_dims_rules():
     assert tp.shard_dims(mg.SPECS["llama3-8b-fp8"], 1)["n_heads"] == 32
     with pytest.raises(ValueError):
         tp.shard_dims(mg.SPECS["llama3-70b-fp8"], 16)      # 8 kv heads
-    with pytest.raises(ValueError):
-        tp.shard_dims(mg.SPECS["mixtral-8x7b-fp8"], 2)     # MoE
+    assert tp.shard_dims(mg.SPECS["mixtral-8x7b-fp8"], 8)["hidden_dim"] == 1792  # MoE: the same split inside every expert
     with pytest.raises(ValueError):
         tp.shard_dims(mg.SPECS["tiny-qwen"], 2)            # one kv head
     with pytest.raises(ValueError):
         tp.shard_dims(mg.SPECS["tiny-fp8"], 4)             # hidden 704 = 22 * 32, not a multiple of 128
     assert tp.local_spec(mg.SPECS["tiny-fp8"], 2).kv_dim == 64
+
+
+def test_moe_shards_partition_every_expert(oracle_pkg):
+    spec = mg.SPECS["tiny-moe"]
+    model = mg.HostModel(spec, seed=0)
+    shards = [tp.shard_tensors(spec, model.tensors, r, 2) for r in range(2)]
+    hl = spec.hidden_dim // 2
+    for leaf in ("mlp.w1", "mlp.w3"):
+        full = model.tensors[f"model.layers.0.{leaf}.weight"].numpy()
+        got = np.concatenate([s[f"model.layers.0.{leaf}.weight"].numpy() for s in shards], axis=1)
+        assert got.shape == full.shape == (spec.n_experts, spec.hidden_dim, spec.dim) and np.array_equal(got, full)
+    full = model.tensors["model.layers.0.mlp.w2.weight"].numpy()
+    got = np.concatenate([s["model.layers.0.mlp.w2.weight"].numpy() for s in shards], axis=2)
+    assert shards[0]["model.layers.0.mlp.w2.weight"].shape == (spec.n_experts, spec.dim, hl) and np.array_equal(got, full)
 
 
 @pytest.mark.parametrize("name", ["tiny-fp8", "tiny-fp16", "tiny-gf4", "tiny-bias2"])
