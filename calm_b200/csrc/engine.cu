@@ -61,12 +61,15 @@ struct Engine {
 	int attn_nsplit_cap = 1 << 30;
 
 	// L2 prefetch schedule (common.cuh Prefetch): what each stage requests for the stages after it.  Bytes, or flags.
-	bool pf_kv = true;            // k_qkv / w2 request the KV prefix the next attention kernel reads
-	bool pf_attn_wo = true;       // k_attn requests wo
-	size_t pf_attn_up = 40 << 20; // ... and this much of w1 + w3
+	// Measured (profiles/r02_sweep_l2_prefetch_schedule.jsonl): no setting beats "off" -- the stage kernels are not waiting for
+	// DRAM behind their boundaries, and requests for later stages only compete with the running one -- so the default is off;
+	// CALM_B200_PF keeps the experiment reproducible.
+	bool pf_kv = false;           // k_qkv / w2 request the KV prefix the next attention kernel reads
+	bool pf_attn_wo = false;      // k_attn requests wo
+	size_t pf_attn_up = 0;        // ... and this much of w1 + w3
 	size_t pf_wo_up = 0;          // wo requests this much more of w1 + w3
 	size_t pf_up_down = 0;        // k_ffn_up requests this much of w2
-	bool pf_down_qkv = true;      // w2 requests the next layer's wq / wk / wv
+	bool pf_down_qkv = false;     // w2 requests the next layer's wq / wk / wv
 
 
 	// tensor parallelism (staged engine): this process owns 1/tp_world of the heads and of the FFN rows
@@ -783,7 +786,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	if (g.debug) g.use_graph = false;
 	g.perf = (getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF"))) || getenv("CUDA_INJECTION64_PATH");
 	if (const char* e = getenv("CALM_B200_PF")) { // kv,attn_wo,attn_up_MB,wo_up_MB,up_down_MB,down_qkv  (experiments; defaults in struct Engine)
-		int kv = 1, awo = 1, aup = 40, wup = 0, ud = 0, dq = 1;
+		int kv = 0, awo = 0, aup = 0, wup = 0, ud = 0, dq = 0;
 		sscanf(e, "%d,%d,%d,%d,%d,%d", &kv, &awo, &aup, &wup, &ud, &dq);
 		g.pf_kv = kv != 0, g.pf_attn_wo = awo != 0, g.pf_attn_up = (size_t)aup << 20, g.pf_wo_up = (size_t)wup << 20, g.pf_up_down = (size_t)ud << 20, g.pf_down_qkv = dq != 0;
 	}
