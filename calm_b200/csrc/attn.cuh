@@ -1,0 +1,197 @@
+// attn.cuh -- k_attn2: flash-decoding with the KV slice brought into shared memory by bulk TMA copies that are issued
+// BEFORE the dependency wait.
+//
+// Why: the cache prefix of a layer is immutable while k_qkv of the same layer runs (k_qkv only writes slot kv_pos), so the
+// attention kernel -- resident early thanks to programmatic dependent launch -- can request its whole K/V slice while the
+// q/k/v matvec is still streaming weights.  When the dependency wait returns, the 16.8 MB a Llama-3-8B layer reads at
+// position 4095 are already on chip, and what remains on the critical path is q -> scores -> softmax -> values out of
+// shared memory (no DRAM round trips) plus the slice merge of stages.cuh (attn_tail).
+//
+// Work split: unit = kv head x group of HG query heads (as k_attn); the positions of a unit are cut into blocks of
+// ATTN2_BP = 16 positions and dealt round-robin to the unit's `nsplit` CTAs (block b belongs to CTA b % nsplit), so the
+// split is balanced for every kv_len and does NOT depend on kv_len -- which the pre-wait code only knows as a hint
+// (TokenParams may still be about to be rewritten by the previous token's tail; the hint decides what to request early,
+// never what is computed).  One mbarrier per block; a 16-position K block and V block are one bulk copy each
+// ([position][head_dim] is contiguous per (layer, kv head)).  The slot written this step and the attention sinks that
+// k_embed re-rotates are read from global memory after the wait instead of from the early copy.
+//
+// Lane layout and arithmetic are k_attn's transposing score path: LPP = head_dim / 8 lanes own a position (8 dims per
+// lane), P = LPP / HG positions per lane group and step, so the HG * P partial dot products of a step transpose onto the
+// LPP lanes of the group (one complete score per lane), the two exponentials are evaluated once per lane, and the
+// probabilities are broadcast back for the value accumulation.  Reference arithmetic: infer.c:238-267.
+#pragma once
+
+#include "stages.cuh"
+
+#define ATTN2_BP 16   // positions per block (one bulk copy of K, one of V)
+#define ATTN2_MAXB 32 // blocks per CTA
+
+// shared memory: K blocks | V blocks | q [HG][head_dim] | merge scratch
+template <typename KVT>
+__host__ __device__ inline size_t attn2_smem_bytes(int hg, int head_dim, int nbmax, int nsplit) {
+	size_t kv = (size_t)2 * nbmax * ATTN2_BP * head_dim * sizeof(KVT);
+	size_t scratch = (size_t)(ATTN_THREADS / 32) * hg * (head_dim + 2);
+	size_t scratch2 = (size_t)(2 * nsplit + 1) * hg;
+	if (scratch2 > scratch) scratch = scratch2;
+	return kv + ((size_t)hg * head_dim + scratch) * sizeof(float);
+}
+
+template <typename KVT, int HG, int LPP>
+__global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
+	typedef typename KvRaw<KVT>::type raw_t;
+	constexpr int HD = LPP * 8, P = LPP / HG, G = 32 / LPP, NW = ATTN_THREADS / 32, NC = LPP;
+	static_assert(HG * P == LPP && P >= 1 && P <= 4 && ATTN2_BP % P == 0, "unsupported head grouping");
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ __align__(8) uint64_t bars[ATTN2_MAXB];
+	__shared__ int flag;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nbmax = a.nbmax, nsplit = a.nsplit;
+	const int unit = blockIdx.x / nsplit, split = blockIdx.x % nsplit;
+	const int kvh = unit / a.qgroups;
+	const int hbase = kvh * a.kv_mul + (unit % a.qgroups) * HG;
+	constexpr uint32_t BLK = ATTN2_BP * HD * sizeof(KVT); // bytes of a whole block
+	KVT* Ks = reinterpret_cast<KVT*>(smem_raw);
+	KVT* Vs = Ks + (size_t)nbmax * ATTN2_BP * HD;
+	float* qs = reinterpret_cast<float*>(Vs + (size_t)nbmax * ATTN2_BP * HD);
+	float* scratch = qs + HG * HD;
+	const KVT* kglob = reinterpret_cast<const KVT*>(a.kc) + (size_t)kvh * a.seq_len * HD;
+	const KVT* vglob = reinterpret_cast<const KVT*>(a.vc) + (size_t)kvh * a.seq_len * HD;
+
+	pdl_launch_next();
+	if (tid == 0) {
+		for (int j = 0; j < nbmax; ++j) mbar_init(&bars[j], 1);
+		mbar_init_fence();
+	}
+	__syncthreads();
+	// request the slice while the previous kernel (k_qkv of this layer) is still running: thread j owns block j
+	bool issued = false;
+	auto request = [&](int j) {
+		const int b = split + j * nsplit;
+		const uint32_t bytes = (uint32_t)min(ATTN2_BP, a.seq_len - b * ATTN2_BP) * HD * sizeof(KVT);
+		mbar_expect_tx(&bars[j], 2 * bytes);
+		tma_load_1d(Ks + (size_t)j * ATTN2_BP * HD, kglob + (size_t)b * ATTN2_BP * HD, bytes, &bars[j]);
+		tma_load_1d(Vs + (size_t)j * ATTN2_BP * HD, vglob + (size_t)b * ATTN2_BP * HD, bytes, &bars[j]);
+	};
+	if (tid < nbmax) {
+		const int hint = min(*reinterpret_cast<const volatile int*>(&a.tp->kv_len), a.seq_len);
+		if ((split + tid * nsplit) * ATTN2_BP < hint) request(tid), issued = true;
+	}
+	pdl_wait_prev();
+	stamp_begin(a.stamp);
+	const int kv_len = a.tp->kv_len, kv_pos = a.tp->kv_pos, kv_sink = a.tp->kv_sink;
+	if (tid < nbmax && !issued && (split + tid * nsplit) * ATTN2_BP < kv_len) request(tid), issued = true;
+	for (int i = tid; i < HG * HD; i += ATTN_THREADS) qs[i] = __ldcg(a.q + (size_t)hbase * HD + i);
+	__syncthreads();
+
+	// blocks of this CTA that hold cached positions
+	const int nblk = (kv_len + ATTN2_BP - 1) / ATTN2_BP;
+	const int nb = nblk > split ? (nblk - split + nsplit - 1) / nsplit : 0;
+	const int nslots = nb * ATTN2_BP;
+	const int grp = lane / LPP, li = lane % LPP;
+
+	float acc[HG][8], m[HG], l[HG];
+#pragma unroll
+	for (int h = 0; h < HG; ++h) {
+		m[h] = -FLT_MAX, l[h] = 0.f;
+#pragma unroll
+		for (int d = 0; d < 8; ++d) acc[h][d] = 0.f;
+	}
+	float mh = -FLT_MAX, lh = 0.f; // running max / sum of THIS lane's head (li / P)
+
+	for (int s0 = (warp * G + grp) * P; s0 - grp * P < nslots; s0 += NW * G * P) { // warp-uniform trip count (full-warp shuffles inside)
+		const bool inr = s0 < nslots;
+		const int j = inr ? s0 / ATTN2_BP : 0, o = s0 % ATTN2_BP;
+		const int t0 = (split + j * nsplit) * ATTN2_BP + o;
+		if (inr) mbar_wait(&bars[j], 0);
+		raw_t kr[P], vr[P];
+		bool ok[P];
+#pragma unroll
+		for (int i = 0; i < P; ++i) {
+			const int t = t0 + i;
+			ok[i] = inr && t < kv_len;
+			if (ok[i]) {
+				if (t == kv_pos || t < kv_sink) { // written during this token (k_qkv / k_embed): not in the early copy
+					kr[i] = KvRaw<KVT>::load(kglob + (size_t)t * HD + li * 8);
+					vr[i] = KvRaw<KVT>::load(vglob + (size_t)t * HD + li * 8);
+				} else {
+					kr[i] = *reinterpret_cast<const raw_t*>(Ks + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
+					vr[i] = *reinterpret_cast<const raw_t*>(Vs + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
+				}
+			} else {
+				kr[i] = KvRaw<KVT>::zero(), vr[i] = KvRaw<KVT>::zero();
+			}
+		}
+		// partial dot products of this lane's 8 dims: combo c = h * P + i
+		float part[NC];
+		{
+			float kf[P][8];
+#pragma unroll
+			for (int i = 0; i < P; ++i) KvRaw<KVT>::unpack(kr[i], kf[i]);
+#pragma unroll
+			for (int h = 0; h < HG; ++h) {
+				const float4 q0 = *reinterpret_cast<const float4*>(qs + h * HD + li * 8), q1 = *reinterpret_cast<const float4*>(qs + h * HD + li * 8 + 4);
+#pragma unroll
+				for (int i = 0; i < P; ++i) {
+					float d = q0.x * kf[i][0];
+					d = fmaf(q0.y, kf[i][1], d), d = fmaf(q0.z, kf[i][2], d), d = fmaf(q0.w, kf[i][3], d);
+					d = fmaf(q1.x, kf[i][4], d), d = fmaf(q1.y, kf[i][5], d), d = fmaf(q1.z, kf[i][6], d), d = fmaf(q1.w, kf[i][7], d);
+					part[h * P + i] = d;
+				}
+			}
+		}
+		// transposing reduction over the LPP lanes of the group: after the step with stride s a lane keeps the half selected by bit s
+#pragma unroll
+		for (int s_ = NC / 2; s_ >= 1; s_ >>= 1) {
+			const bool up = li & s_;
+#pragma unroll
+			for (int k = 0; k < s_; ++k) {
+				float send = up ? part[k] : part[k + s_];
+				float recv = __shfl_xor_sync(0xffffffffu, send, s_);
+				part[k] = (up ? part[k + s_] : part[k]) + recv;
+			}
+		}
+		// lane li owns combo li: head li / P, position li % P
+		bool valid = false;
+#pragma unroll
+		for (int i = 0; i < P; ++i) valid = (li % P == i) ? ok[i] : valid;
+		const float sc = valid ? part[0] * a.inv_sqrt_hd : -FLT_MAX;
+		float gmax = sc;
+#pragma unroll
+		for (int o2 = 1; o2 < P; o2 <<= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o2));
+		const float mnew = fmaxf(mh, gmax);
+		const float corr = __expf(mh - mnew);
+		const float pr = valid ? __expf(sc - mnew) : 0.f;
+		float ps = pr;
+#pragma unroll
+		for (int o2 = 1; o2 < P; o2 <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o2);
+		lh = fmaf(lh, corr, ps);
+		mh = mnew;
+		const int gbase = grp * LPP;
+		float vf[P][8];
+#pragma unroll
+		for (int i = 0; i < P; ++i) KvRaw<KVT>::unpack(vr[i], vf[i]);
+#pragma unroll
+		for (int h = 0; h < HG; ++h) {
+			const float ch = __shfl_sync(0xffffffffu, corr, gbase + h * P);
+			float pw[P];
+#pragma unroll
+			for (int i = 0; i < P; ++i) pw[i] = __shfl_sync(0xffffffffu, pr, gbase + h * P + i);
+#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				float v = acc[h][e] * ch;
+#pragma unroll
+				for (int i = 0; i < P; ++i) v = fmaf(pw[i], vf[i][e], v);
+				acc[h][e] = v;
+			}
+		}
+	}
+#pragma unroll
+	for (int h = 0; h < HG; ++h) { // running max / sum live in the lanes that own the head: hand them to every lane of the group
+		m[h] = __shfl_sync(0xffffffffu, mh, grp * LPP + h * P);
+		l[h] = __shfl_sync(0xffffffffu, lh, grp * LPP + h * P);
+	}
+	attn_tail<HG>(a, HG, unit, split, hbase, 0, HG, warp, NW, m, l, acc, scratch, &flag);
+	// no bulk copy may still be in flight into this CTA's shared memory when it exits (a block requested on a stale hint)
+	if (tid < nbmax && issued) mbar_wait(&bars[tid], 0);
+	stamp_end(a.stamp);
+}

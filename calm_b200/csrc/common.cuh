@@ -65,6 +65,53 @@ __device__ __forceinline__ void l2_prefetch_row(const void* row, int rowbytes) {
 	for (int off = 0; off < rowbytes; off += 16384) l2_prefetch((const char*)row + off, (uint32_t)min(16384, rowbytes - off));
 }
 
+// ---------------------------------------------------------------- bulk async copies (TMA, 1-D) and mbarriers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make freshly initialised barriers visible to the async proxy (the TMA unit) before the first copy names them
+__device__ __forceinline__ void mbar_init_fence() {
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	while (!mbar_try_wait(bar, parity)) {
+	}
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on `bar` (SASS UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+	             "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+	             : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
 // ---------------------------------------------------------------- L2 prefetch schedule
 // Every stage kernel of a token can be handed byte ranges that LATER kernels of the same token will stream
 // (weights are immutable; the KV prefix of a layer only gains the slot k_qkv writes).  One lane per warp turns

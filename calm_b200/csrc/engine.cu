@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "stages.cuh"
+#include "attn.cuh"
 
 namespace {
 
@@ -39,6 +40,7 @@ struct Engine {
 	float* logits_host = nullptr; // pinned + mapped
 	void *kc = nullptr, *vc = nullptr;
 	float* rope_freq = nullptr;
+	float2* rope_cs = nullptr; // (cos, sin) of the current token's RoPE angles, written by k_embed
 	float* attn_partial = nullptr;
 	unsigned* attn_counter = nullptr;
 	MoeSel* moe_sel = nullptr;
@@ -52,6 +54,9 @@ struct Engine {
 
 	// attention launch shape
 	int attn_hg = 1, attn_qgroups = 1, attn_nsplit = 1, attn_lpp = 1;
+	bool attn2 = false; // k_attn2 (attn.cuh): KV slice requested into shared memory ahead of the dependency wait
+	int attn_nbmax = 0;
+	size_t attn2_smem = 0;
 
 	// launch plan (grid sizes / dynamic shared memory), fixed at prepare time
 	int grid_qkv = 0, grid_wo = 0, grid_up = 0, grid_down = 0, grid_out = 0;
@@ -366,8 +371,32 @@ void launch_attn(const AttnArgs& a, int nunits, int* nl) {
 	++*nl;
 }
 
+template <typename KVT, int HG, int LPP>
+void launch_attn2(const AttnArgs& a, int nunits, int* nl) {
+	if (!nl) {
+		smem_optin(k_attn2<KVT, HG, LPP>, g.attn2_smem);
+		return;
+	}
+	launch_pdl(k_attn2<KVT, HG, LPP>, nunits * a.nsplit, ATTN_THREADS, g.attn2_smem, a);
+	++*nl;
+}
+
+// shapes k_attn2 is instantiated for: head_dim 128 with 4 or 8 query heads per kv head, head_dim 64 with 2, 4 or 8
+bool attn2_shape_ok(int hg, int lpp, int head_dim) {
+	return head_dim == lpp * 8 && ((lpp == 16 && (hg == 4 || hg == 8)) || (lpp == 8 && (hg == 2 || hg == 4 || hg == 8)));
+}
+
 template <typename KVT>
 void dispatch_attn(const AttnArgs& a, int nunits, int* nl) {
+	if (g.attn2) {
+		switch (g.attn_lpp * 100 + g.attn_hg) {
+		case 1604: launch_attn2<KVT, 4, 16>(a, nunits, nl); return;
+		case 1608: launch_attn2<KVT, 8, 16>(a, nunits, nl); return;
+		case 802: launch_attn2<KVT, 2, 8>(a, nunits, nl); return;
+		case 804: launch_attn2<KVT, 4, 8>(a, nunits, nl); return;
+		case 808: launch_attn2<KVT, 8, 8>(a, nunits, nl); return;
+		}
+	}
 	switch (g.attn_hg) {
 	case 1: launch_attn<KVT, 1>(a, nunits, nl); break;
 	case 2: launch_attn<KVT, 2>(a, nunits, nl); break;
@@ -416,7 +445,7 @@ int run_token(int mode) {
 		a.x = g.x, a.table = w.token_embedding_table, a.tp = g.tp, a.dim = dim;
 		a.embed_blocks = cdiv(dim, 256);
 		a.tile_ctr = g.tile_ctr, a.n_ctr = c.n_layers;
-		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq;
+		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq, a.rope_cs = g.rope_cs;
 		a.n_layers = c.n_layers, a.n_kv_heads = c.n_kv_heads, a.head_dim = hd, a.seq_len = c.seq_len;
 		a.stamp = nullptr, a.stamp_reset = g.perf ? g.stamps : nullptr, a.n_stamps = MAX_STAMPS;
 		if (g.pf_down_qkv) qkv_weights(a.pf, 0);
@@ -430,12 +459,12 @@ int run_token(int mode) {
 			QkvArgs<KVT> a = {};
 			a.x = g.x, a.normw = w.rms_att_weight[l], a.wq = w.wq[l], a.wk = w.wk[l], a.wv = w.wv[l], a.bias = w.bqkv[l];
 			a.q_out = g.q, a.kc = (KVT*)g.kc + l * kv_layer, a.vc = (KVT*)g.vc + l * kv_layer;
-			a.rope_freq = g.rope_freq, a.xb_out = c.norm_par ? g.xb : nullptr, a.tp = g.tp;
+			a.rope_cs = g.rope_cs, a.xb_out = c.norm_par ? g.xb : nullptr, a.tp = g.tp;
 			a.dim = dim, a.q_dim = g.q_dim, a.kv_dim = g.kv_dim, a.head_dim = hd, a.seq_len = c.seq_len;
 			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln;
 			a.stamp = t.slot;
 			if (g.pf_kv && (l == 0 || !g.pf_down_qkv)) kv_prefix(a.pf, l); // later layers: requested by the previous w2 kernel
-			launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, 256, g.smem_dim, a);
+			launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, QKV_THREADS, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -446,6 +475,7 @@ int run_token(int mode) {
 			a.head_dim = hd, a.seq_len = c.seq_len, a.nsplit = g.attn_nsplit, a.lpp = g.attn_lpp;
 			a.kv_mul = g.kv_mul, a.qgroups = g.attn_qgroups;
 			a.inv_sqrt_hd = 1.0f / sqrtf((float)hd);
+			a.nbmax = g.attn_nbmax;
 			a.stamp = t.slot;
 			if (g.pf_attn_wo) a.pf.p[0] = w.wo[l], a.pf.bytes[0] = wo_bytes;
 			if (dense && g.pf_attn_up) pf_up_prefix(a.pf, 1, w.w1[l], w.w3[l], 0, g.pf_attn_up, up_bytes);
@@ -613,11 +643,16 @@ void make_plan() {
 	smem_optin(k_qkv<DBITS, KVT, EARLY>, g.smem_dim), smem_optin(k_ffn_up<DBITS, EARLY>, g.smem_dim), smem_optin(k_output<DBITS>, g.smem_dim);
 	smem_optin(k_matres<DBITS, EARLY>, smem_res); // ONE attribute per kernel: the larger of its two launch shapes (wo, w2)
 	{
+		// k_attn2 when the shape is instantiated and the CTA's share of the context fits in shared memory
+		g.attn_nbmax = cdiv(cdiv(c.seq_len, ATTN2_BP), g.attn_nsplit);
+		g.attn2_smem = attn2_smem_bytes<KVT>(g.attn_hg, c.head_dim, g.attn_nbmax, g.attn_nsplit);
+		const bool want = !(getenv("CALM_B200_ATTN2") && atoi(getenv("CALM_B200_ATTN2")) == 0);
+		g.attn2 = want && attn2_shape_ok(g.attn_hg, g.attn_lpp, c.head_dim) && g.attn_nbmax <= ATTN2_MAXB && g.attn2_smem <= 200 * 1024;
 		AttnArgs aa = {};
 		aa.head_dim = c.head_dim, aa.nsplit = g.attn_nsplit_cap;
 		dispatch_attn<KVT>(aa, 0, nullptr);
 	}
-	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT, EARLY>, 256, g.smem_dim));
+	g.grid_qkv = imin(g.sms, cdiv((g.q_dim + 2 * g.kv_dim) / 2, QKV_THREADS / 32)); // one 12-warp CTA per SM, equal contiguous shares
 	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_qdim));
 	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_hidden));
 	if (g.tp_fused) { // the in-kernel exchange needs co-resident grids (they are: balanced_grid stays under the cap) within its tables
@@ -823,6 +858,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	// RoPE frequencies with the host libm, exactly as the CPU reference forms them (infer.c:225-226)
 	std::vector<float> freq(c.head_dim / 2);
 	for (int i = 0; i < c.head_dim; i += 2) freq[i / 2] = i >= c.rotary_dim ? 0.f : 1.0f / powf(c.rope_theta, (float)i / (float)c.rotary_dim);
+	g.rope_cs = (float2*)dev_alloc(freq.size() * sizeof(float2));
 	g.rope_freq = (float*)dev_alloc(freq.size() * sizeof(float));
 	CUDA_CHECK(cudaMemcpyAsync(g.rope_freq, freq.data(), freq.size() * sizeof(float), cudaMemcpyHostToDevice, g.stream));
 	CUDA_CHECK(cudaStreamSynchronize(g.stream)); // freq is a local
@@ -918,7 +954,7 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 	cudaFree(g.stamps), cudaFree(g.stamp_acc);
 	cudaFree(g.x), cudaFree(g.xb), cudaFree(g.q), cudaFree(g.att), cudaFree(g.hb), cudaFree(g.logits_dev);
 	cudaFreeHost(g.logits_host), cudaFreeHost(g.last_token);
-	cudaFree(g.kc), cudaFree(g.vc), cudaFree(g.rope_freq), cudaFree(g.attn_partial), cudaFree(g.attn_counter);
+	cudaFree(g.kc), cudaFree(g.vc), cudaFree(g.rope_freq), cudaFree(g.rope_cs), cudaFree(g.attn_partial), cudaFree(g.attn_counter);
 	cudaFree(g.moe_sel), cudaFree(g.tp), cudaFree(g.cand_val), cudaFree(g.cand_idx), cudaFree(g.out_tokens);
 	for (int p = 0; p < TP_MAX_WORLD; ++p)
 		if (g.tp_peer[p] && g.tp_peer[p] != g.tp_area) cudaIpcCloseMemHandle(g.tp_peer[p]);

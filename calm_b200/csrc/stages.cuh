@@ -223,6 +223,7 @@ struct EmbedArgs {
 	int embed_blocks;
 	int* tile_ctr; // per-layer work counters of k_ffn_up_mma, zeroed here once per token
 	int n_ctr;
+	float2* rope_cs;           // [head_dim / 2]: (cos, sin)(pos * freq) of this token, written here for every layer's k_qkv
 	unsigned long long* stamp; // perf_cuda: {min start, max end} of this launch, or NULL
 	unsigned long long* stamp_reset; // perf_cuda: all slots of the token, re-armed here
 	int n_stamps;
@@ -246,6 +247,11 @@ __global__ void k_embed(const EmbedArgs<KVT> a) {
 		if (i < a.dim) a.x[i] = weight_at<DBITS>(a.table, (size_t)a.tp->token * a.dim + i);
 		if (blockIdx.x == 0 && a.tile_ctr)
 			for (int j = threadIdx.x; j < a.n_ctr; j += blockDim.x) a.tile_ctr[j] = 0;
+		if (blockIdx.x == 0 && (int)threadIdx.x < a.head_dim / 2) { // RoPE angles (reference infer.c:223-236), once per token instead of once per row pair
+			float fcr, fci;
+			sincosf((float)a.tp->pos * a.rope_freq[threadIdx.x], &fci, &fcr);
+			a.rope_cs[threadIdx.x] = make_float2(fcr, fci);
+		}
 		return;
 	}
 	const int kv_sink = a.tp->kv_sink;
@@ -280,7 +286,7 @@ struct QkvArgs {
 	float* q_out;
 	KVT* kc; // this layer: [n_kv_heads][seq_len][head_dim]
 	KVT* vc;
-	const float* rope_freq; // [head_dim/2], theta^(-j/rotary_dim) or 0 beyond rotary_dim
+	const float2* rope_cs;  // [head_dim/2]: (cos, sin) of pos * theta^(-j/rotary_dim) (angle 0 beyond rotary_dim), from k_embed
 	float* xb_out;          // normalised x for the FFN when norm_par, else NULL
 	const TokenParams* tp;
 	int dim, q_dim, kv_dim, head_dim, seq_len;
@@ -295,8 +301,13 @@ struct QkvArgs {
 // no registers); 2 the same, and k_ffn_up keeps 8 vectors per row in flight at 2 CTAs per SM instead of 4 at 3.
 // (Issuing the first loads into registers instead was measured 25 % slower: 32 more live registers across the
 // staging cost a CTA per SM or spills.)
+#define QKV_THREADS 384
+// One CTA per SM, 12 warps at 80 registers per thread: half of the register file and most of the shared memory stay free
+// for the attention kernel, whose CTAs become resident while this kernel runs and request their KV slices (attn.cuh).
+// CTA c owns the contiguous row pairs [c * npairs / G, (c + 1) * npairs / G) -- every SM streams the same number of
+// bytes to within one pair -- and its warps take them round-robin.
 template <int DBITS, typename KVT, int EARLY>
-__global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
+__global__ void __launch_bounds__(QKV_THREADS, 2) k_qkv(const QkvArgs<KVT> a) {
 	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	float* red = smem;
@@ -305,6 +316,7 @@ __global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 	const int nvec = a.dim / WFmt<DBITS>::VW;
 	const size_t rowvecs = (size_t)nvec; // 16-byte vectors per row
 	const int npairs = (a.q_dim + 2 * a.kv_dim) / 2;
+	const int p_lo = (int)(((long long)blockIdx.x * npairs) / gridDim.x), p_hi = (int)(((long long)(blockIdx.x + 1) * npairs) / gridDim.x);
 	auto rows_of = [&](int p, const uint4* (&rp)[2], int& j, int& k) {
 		j = 2 * p; // row in the concatenated [wq; wk; wv]
 		const void* w;
@@ -318,8 +330,8 @@ __global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 		rp[0] = reinterpret_cast<const uint4*>(w) + (size_t)k * rowvecs, rp[1] = rp[0] + rowvecs;
 	};
 	// weights first: they do not depend on the previous kernel, so their latency hides its tail and the staging of x
-	const int p0 = blockIdx.x * nwarps + warp;
-	if (EARLY != 0 && p0 < npairs && lane == 0) {
+	const int p0 = p_lo + warp;
+	if (EARLY != 0 && p0 < p_hi && lane == 0) {
 		const uint4* rp[2];
 		int j, k;
 		rows_of(p0, rp, j, k);
@@ -329,10 +341,10 @@ __global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 	pdl_wait_prev();
 	stamp_begin(a.stamp);
 	const float post = stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, blockIdx.x == 0 ? a.xb_out : nullptr);
-	const int pos = a.tp->pos, kv_pos = a.tp->kv_pos;
+	const int kv_pos = a.tp->kv_pos;
 	prefetch_kv(a.pf, a.tp->kv_len); // this layer's cache prefix, for the attention kernel that follows
 
-	for (int p = p0; p < npairs; p += gridDim.x * nwarps) {
+	for (int p = p0; p < p_hi; p += nwarps) {
 		const uint4* rp[2];
 		int j, k;
 		rows_of(p, rp, j, k);
@@ -345,9 +357,8 @@ __global__ void __launch_bounds__(256, 3) k_qkv(const QkvArgs<KVT> a) {
 			v0 = fminf(fmaxf(v0, -a.clip), a.clip);
 			v1 = fminf(fmaxf(v1, -a.clip), a.clip);
 			if (j < a.q_dim + a.kv_dim) { // rotate q and k (reference infer.c:223-236)
-				float fcr, fci;
-				sincosf((float)pos * a.rope_freq[(j % a.head_dim) >> 1], &fci, &fcr);
-				float r0 = v0 * fcr - v1 * fci, r1 = v0 * fci + v1 * fcr;
+				const float2 cs = a.rope_cs[(j % a.head_dim) >> 1];
+				float r0 = v0 * cs.x - v1 * cs.y, r1 = v0 * cs.y + v1 * cs.x;
 				v0 = r0, v1 = r1;
 			}
 			if (j < a.q_dim) {
@@ -385,6 +396,7 @@ struct AttnArgs {
 	int head_dim, seq_len, nsplit, lpp; // lpp: lanes per position (power of two >= head_dim/8)
 	int kv_mul, qgroups;                // query heads per kv head; qgroups = kv_mul / HG
 	float inv_sqrt_hd;
+	int nbmax;                          // k_attn2: 16-position blocks per CTA = ceil(ceil(seq_len / 16) / nsplit)
 	unsigned long long* stamp;
 	Prefetch pf;
 };
@@ -412,6 +424,117 @@ struct KvRaw<uint8_t> {
 		o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y, o[4] = c.x, o[5] = c.y, o[6] = d.x, o[7] = d.y;
 	}
 };
+
+// Everything after the position loop of a work item: merge the lane groups of a warp, the warps of the CTA (shared memory),
+// write the slice's partial (m, l, acc) and let the last slice of the unit fold all slices into the normalised output.
+// m / l / acc: per-lane state of this warp's HH heads (8 head dims per lane, li = lane % lpp).
+template <int HH>
+__device__ __forceinline__ void attn_tail(const AttnArgs& a, int HG, int unit, int split, int hbase, int h0, int nh, int warp, int nwarps, float (&m)[HH], float (&l)[HH],
+                                          float (&acc)[HH][8], float* scratch, int* flag) {
+	const int lane = threadIdx.x & 31;
+	const int hd = a.head_dim, lpp = a.lpp;
+	const int grp = lane / lpp, li = lane % lpp;
+	const bool dact = li * 8 < hd;
+	// merge the position groups of a warp
+	for (int o = lpp; o < 32; o <<= 1) {
+#pragma unroll
+		for (int h = 0; h < HH; ++h) {
+			float mo = __shfl_xor_sync(0xffffffffu, m[h], o), lo = __shfl_xor_sync(0xffffffffu, l[h], o);
+			float mn = fmaxf(m[h], mo);
+			float ca = expf(m[h] - mn), cb = expf(mo - mn);
+			l[h] = l[h] * ca + lo * cb;
+#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				float ao = __shfl_xor_sync(0xffffffffu, acc[h][e], o);
+				acc[h][e] = acc[h][e] * ca + ao * cb;
+			}
+			m[h] = mn;
+		}
+	}
+
+	// merge warps through shared memory: rec[warp][h][hd+2]
+	const int rec = hd + 2;
+	__syncthreads(); // scratch may still be in use by a previous item
+	if (grp == 0) {
+#pragma unroll
+		for (int h = 0; h < HH; ++h) {
+			if (h < nh) { // the warp sets write disjoint heads
+				float* r = scratch + ((size_t)warp * HG + h0 + h) * rec;
+				if (dact) {
+#pragma unroll
+					for (int e = 0; e < 8; ++e) r[li * 8 + e] = acc[h][e];
+				}
+				if (li == 0) r[hd] = m[h], r[hd + 1] = l[h];
+			}
+		}
+	}
+	__syncthreads();
+	float* part = a.partial + ((size_t)unit * a.nsplit + split) * HG * rec;
+	for (int idx = threadIdx.x; idx < HG * rec; idx += blockDim.x) {
+		int h = idx / rec, e = idx % rec;
+		float mn = -FLT_MAX;
+		for (int w = 0; w < nwarps; ++w) mn = fmaxf(mn, scratch[((size_t)w * HG + h) * rec + hd]);
+		float v;
+		if (e == hd) {
+			v = mn;
+		} else {
+			v = 0.f;
+			for (int w = 0; w < nwarps; ++w) {
+				const float* r = scratch + ((size_t)w * HG + h) * rec;
+				v += r[e] * expf(r[hd] - mn); // e == hd+1 merges the sums the same way
+			}
+		}
+		__stcg(part + idx, v);
+	}
+
+	// the last slice of this unit to finish folds all slices and writes the normalised output
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned old = atomicAdd(a.counter + unit, 1u);
+		*flag = (old == (unsigned)a.nsplit - 1);
+	}
+	__syncthreads();
+	if (!*flag) return;
+	__threadfence();
+	const int ns = a.nsplit;
+	const float* pk = a.partial + (size_t)unit * ns * HG * rec;
+	float* coef = scratch;                  // [ns][HG]: l_s, then exp(m_s - M)
+	float* msv = scratch + (size_t)ns * HG; // [ns][HG]: m_s; msv[ns*HG + h]: 1 / L_h
+	for (int i = threadIdx.x; i < ns * HG; i += blockDim.x) {
+		const float* r = pk + (size_t)i * rec; // i = s * HG + h
+		coef[i] = __ldcg(r + hd + 1);
+		msv[i] = __ldcg(r + hd);
+	}
+	__syncthreads();
+	if ((int)threadIdx.x < HG) {
+		const int h = threadIdx.x;
+		float M = -FLT_MAX;
+		for (int s_ = 0; s_ < ns; ++s_) M = fmaxf(M, msv[s_ * HG + h]);
+		float L = 0.f;
+		for (int s_ = 0; s_ < ns; ++s_) {
+			float c = expf(msv[s_ * HG + h] - M);
+			L = fmaf(coef[s_ * HG + h], c, L);
+			coef[s_ * HG + h] = c;
+		}
+		msv[h] = 1.0f / L; // msv[0..HG) is dead by now (each thread only read its own column... see sync below)
+	}
+	__syncthreads();
+	for (int idx = threadIdx.x; idx < HG * hd; idx += blockDim.x) {
+		int h = idx / hd, e = idx % hd;
+		float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+		int s_ = 0;
+		for (; s_ + 4 <= ns; s_ += 4) {
+			float p0 = __ldcg(pk + ((size_t)(s_ + 0) * HG + h) * rec + e), p1 = __ldcg(pk + ((size_t)(s_ + 1) * HG + h) * rec + e);
+			float p2 = __ldcg(pk + ((size_t)(s_ + 2) * HG + h) * rec + e), p3 = __ldcg(pk + ((size_t)(s_ + 3) * HG + h) * rec + e);
+			n0 = fmaf(p0, coef[(s_ + 0) * HG + h], n0), n1 = fmaf(p1, coef[(s_ + 1) * HG + h], n1);
+			n2 = fmaf(p2, coef[(s_ + 2) * HG + h], n2), n3 = fmaf(p3, coef[(s_ + 3) * HG + h], n3);
+		}
+		for (; s_ < ns; ++s_) n0 = fmaf(__ldcg(pk + ((size_t)s_ * HG + h) * rec + e), coef[s_ * HG + h], n0);
+		__stcg(a.out + (size_t)(hbase + h) * hd + e, ((n0 + n1) + (n2 + n3)) * msv[h]);
+	}
+	if (threadIdx.x == 0) a.counter[unit] = 0;
+}
 
 // One work item, executed by all warps of the calling CTA.  The warps form `hsets` equal sets (1 or 2);
 // every set walks all positions of the slice and serves HH of the unit's HG query heads (set s: heads
@@ -597,105 +720,7 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int HG, int hsets, 
 		}
 	}
 
-	// merge the position groups of a warp
-	for (int o = lpp; o < 32; o <<= 1) {
-#pragma unroll
-		for (int h = 0; h < HH; ++h) {
-			float mo = __shfl_xor_sync(0xffffffffu, m[h], o), lo = __shfl_xor_sync(0xffffffffu, l[h], o);
-			float mn = fmaxf(m[h], mo);
-			float ca = expf(m[h] - mn), cb = expf(mo - mn);
-			l[h] = l[h] * ca + lo * cb;
-#pragma unroll
-			for (int e = 0; e < 8; ++e) {
-				float ao = __shfl_xor_sync(0xffffffffu, acc[h][e], o);
-				acc[h][e] = acc[h][e] * ca + ao * cb;
-			}
-			m[h] = mn;
-		}
-	}
-
-	// merge warps through shared memory: rec[warp][h][hd+2]
-	const int rec = hd + 2;
-	__syncthreads(); // scratch may still be in use by a previous item
-	if (grp == 0) {
-#pragma unroll
-		for (int h = 0; h < HH; ++h) {
-			if (h < nh) { // the warp sets write disjoint heads
-				float* r = scratch + ((size_t)warp * HG + h0 + h) * rec;
-				if (dact) {
-#pragma unroll
-					for (int e = 0; e < 8; ++e) r[li * 8 + e] = acc[h][e];
-				}
-				if (li == 0) r[hd] = m[h], r[hd + 1] = l[h];
-			}
-		}
-	}
-	__syncthreads();
-	float* part = a.partial + ((size_t)unit * a.nsplit + split) * HG * rec;
-	for (int idx = threadIdx.x; idx < HG * rec; idx += blockDim.x) {
-		int h = idx / rec, e = idx % rec;
-		float mn = -FLT_MAX;
-		for (int w = 0; w < nwarps; ++w) mn = fmaxf(mn, scratch[((size_t)w * HG + h) * rec + hd]);
-		float v;
-		if (e == hd) {
-			v = mn;
-		} else {
-			v = 0.f;
-			for (int w = 0; w < nwarps; ++w) {
-				const float* r = scratch + ((size_t)w * HG + h) * rec;
-				v += r[e] * expf(r[hd] - mn); // e == hd+1 merges the sums the same way
-			}
-		}
-		__stcg(part + idx, v);
-	}
-
-	// the last slice of this unit to finish folds all slices and writes the normalised output
-	__threadfence();
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		unsigned old = atomicAdd(a.counter + unit, 1u);
-		*flag = (old == (unsigned)a.nsplit - 1);
-	}
-	__syncthreads();
-	if (!*flag) return;
-	__threadfence();
-	const int ns = a.nsplit;
-	const float* pk = a.partial + (size_t)unit * ns * HG * rec;
-	float* coef = scratch;                  // [ns][HG]: l_s, then exp(m_s - M)
-	float* msv = scratch + (size_t)ns * HG; // [ns][HG]: m_s; msv[ns*HG + h]: 1 / L_h
-	for (int i = threadIdx.x; i < ns * HG; i += blockDim.x) {
-		const float* r = pk + (size_t)i * rec; // i = s * HG + h
-		coef[i] = __ldcg(r + hd + 1);
-		msv[i] = __ldcg(r + hd);
-	}
-	__syncthreads();
-	if ((int)threadIdx.x < HG) {
-		const int h = threadIdx.x;
-		float M = -FLT_MAX;
-		for (int s_ = 0; s_ < ns; ++s_) M = fmaxf(M, msv[s_ * HG + h]);
-		float L = 0.f;
-		for (int s_ = 0; s_ < ns; ++s_) {
-			float c = expf(msv[s_ * HG + h] - M);
-			L = fmaf(coef[s_ * HG + h], c, L);
-			coef[s_ * HG + h] = c;
-		}
-		msv[h] = 1.0f / L; // msv[0..HG) is dead by now (each thread only read its own column... see sync below)
-	}
-	__syncthreads();
-	for (int idx = threadIdx.x; idx < HG * hd; idx += blockDim.x) {
-		int h = idx / hd, e = idx % hd;
-		float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-		int s_ = 0;
-		for (; s_ + 4 <= ns; s_ += 4) {
-			float p0 = __ldcg(pk + ((size_t)(s_ + 0) * HG + h) * rec + e), p1 = __ldcg(pk + ((size_t)(s_ + 1) * HG + h) * rec + e);
-			float p2 = __ldcg(pk + ((size_t)(s_ + 2) * HG + h) * rec + e), p3 = __ldcg(pk + ((size_t)(s_ + 3) * HG + h) * rec + e);
-			n0 = fmaf(p0, coef[(s_ + 0) * HG + h], n0), n1 = fmaf(p1, coef[(s_ + 1) * HG + h], n1);
-			n2 = fmaf(p2, coef[(s_ + 2) * HG + h], n2), n3 = fmaf(p3, coef[(s_ + 3) * HG + h], n3);
-		}
-		for (; s_ < ns; ++s_) n0 = fmaf(__ldcg(pk + ((size_t)s_ * HG + h) * rec + e), coef[s_ * HG + h], n0);
-		__stcg(a.out + (size_t)(hbase + h) * hd + e, ((n0 + n1) + (n2 + n3)) * msv[h]);
-	}
-	if (threadIdx.x == 0) a.counter[unit] = 0;
+	attn_tail<HH>(a, HG, unit, split, hbase, h0, nh, warp, nwarps, m, l, acc, scratch, flag);
 }
 
 #define ATTN_THREADS 256
