@@ -26,17 +26,35 @@
 #define ATTN2_BP 16   // positions per block (one bulk copy of K, one of V)
 #define ATTN2_MAXB 32 // blocks per CTA
 
-// shared memory: K blocks | V blocks | q [HG][head_dim] | merge scratch
+// ---- thread-block cluster helpers (the CTAs of a unit form one cluster when CLUSTER: nsplit <= 16)
+__device__ __forceinline__ void cluster_sync_all() { // every thread of every CTA of the cluster; release / acquire at cluster scope
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local_ptr, uint32_t cta_rank) { // the same shared-memory location in CTA `cta_rank` of this cluster
+	uint32_t raddr;
+	float v;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_ptr)), "r"(cta_rank));
+	asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+	return v;
+}
+
+#define ATTN2_MAX_CLUSTER 16
+
+// shared memory: K blocks | V blocks | q [HG][head_dim] | merge scratch | this CTA's merged record [HG][head_dim + 2]
 template <typename KVT>
 __host__ __device__ inline size_t attn2_smem_bytes(int hg, int head_dim, int nbmax, int nsplit) {
 	size_t kv = (size_t)2 * nbmax * ATTN2_BP * head_dim * sizeof(KVT);
 	size_t scratch = (size_t)(ATTN_THREADS / 32) * hg * (head_dim + 2);
 	size_t scratch2 = (size_t)(2 * nsplit + 1) * hg;
 	if (scratch2 > scratch) scratch = scratch2;
-	return kv + ((size_t)hg * head_dim + scratch) * sizeof(float);
+	return kv + ((size_t)hg * head_dim + scratch + (size_t)hg * (head_dim + 2)) * sizeof(float);
 }
 
-template <typename KVT, int HG, int LPP>
+// CLUSTER: the nsplit CTAs of a unit are one thread-block cluster; the slices are folded through distributed shared memory
+// (one cluster barrier, each CTA normalises 1/nsplit of the unit's outputs from its peers' records) instead of through
+// global partials, a grid-scope fence, an atomic counter and a last-CTA pass that re-reads everything from L2.
+template <typename KVT, int HG, int LPP, bool CLUSTER>
 __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	typedef typename KvRaw<KVT>::type raw_t;
 	constexpr int HD = LPP * 8, P = LPP / HG, G = 32 / LPP, NW = ATTN_THREADS / 32, NC = LPP;
@@ -54,6 +72,7 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	KVT* Vs = Ks + (size_t)nbmax * ATTN2_BP * HD;
 	float* qs = reinterpret_cast<float*>(Vs + (size_t)nbmax * ATTN2_BP * HD);
 	float* scratch = qs + HG * HD;
+	float* myrec = scratch + max(NW * HG * (HD + 2), (2 * nsplit + 1) * HG); // [HG][HD + 2]
 	const KVT* kglob = reinterpret_cast<const KVT*>(a.kc) + (size_t)kvh * a.seq_len * HD;
 	const KVT* vglob = reinterpret_cast<const KVT*>(a.vc) + (size_t)kvh * a.seq_len * HD;
 
@@ -190,7 +209,46 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 		m[h] = __shfl_sync(0xffffffffu, mh, grp * LPP + h * P);
 		l[h] = __shfl_sync(0xffffffffu, lh, grp * LPP + h * P);
 	}
-	attn_tail<HG>(a, HG, unit, split, hbase, 0, HG, warp, NW, m, l, acc, scratch, &flag);
+	if constexpr (CLUSTER) {
+		constexpr int REC = HD + 2;
+		__shared__ float mls[ATTN2_MAX_CLUSTER][HG][2]; // (m, l) of every slice, then (coefficient, -) in place
+		__shared__ float invl[HG];
+		attn_cta_merge<HG>(a, HG, 0, HG, warp, NW, m, l, acc, scratch, myrec);
+		cluster_sync_all(); // every CTA's record is complete and visible cluster-wide
+		for (int i = tid; i < nsplit * HG; i += ATTN_THREADS) {
+			const int s = i / HG, h = i % HG;
+			mls[s][h][0] = ld_dsmem(myrec + h * REC + HD, s), mls[s][h][1] = ld_dsmem(myrec + h * REC + HD + 1, s);
+		}
+		__syncthreads();
+		if (tid < HG) {
+			float M = -FLT_MAX;
+			for (int s = 0; s < nsplit; ++s) M = fmaxf(M, mls[s][tid][0]);
+			float L = 0.f;
+			for (int s = 0; s < nsplit; ++s) {
+				const float c = expf(mls[s][tid][0] - M);
+				L = fmaf(mls[s][tid][1], c, L);
+				mls[s][tid][0] = c;
+			}
+			invl[tid] = 1.0f / L;
+		}
+		__syncthreads();
+		// CTA `split` normalises outputs [split * per, (split + 1) * per): 8 adjacent lanes share an output, each sums every 8th slice
+		const int nout = HG * HD, per = (nout + nsplit - 1) / nsplit;
+		const int o_end = min(nout, (split + 1) * per);
+		for (int o0 = split * per; o0 < o_end; o0 += ATTN_THREADS / 8) {
+			const int o = o0 + tid / 8, sg = tid & 7;
+			float v = 0.f;
+			if (o < o_end) {
+				const int h = o / HD, e = o % HD;
+				for (int s = sg; s < nsplit; s += 8) v = fmaf(ld_dsmem(myrec + h * REC + e, s), mls[s][h][0], v);
+			}
+			v += __shfl_xor_sync(0xffffffffu, v, 1), v += __shfl_xor_sync(0xffffffffu, v, 2), v += __shfl_xor_sync(0xffffffffu, v, 4);
+			if (o < o_end && sg == 0) __stcg(a.out + (size_t)hbase * HD + o, v * invl[o / HD]);
+		}
+		cluster_sync_all(); // no CTA may exit (and free its shared memory) while a peer still reads its record
+	} else {
+		attn_tail<HG>(a, HG, unit, split, hbase, 0, HG, warp, NW, m, l, acc, scratch, &flag);
+	}
 	// no bulk copy may still be in flight into this CTA's shared memory when it exits (a block requested on a stale hint)
 	if (tid < nbmax && issued) mbar_wait(&bars[tid], 0);
 	stamp_end(a.stamp);

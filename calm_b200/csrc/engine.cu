@@ -16,6 +16,7 @@
 
 #include "stages.cuh"
 #include "attn.cuh"
+#include "ring.cuh"
 
 namespace {
 
@@ -54,6 +55,12 @@ struct Engine {
 
 	// attention launch shape
 	int attn_hg = 1, attn_qgroups = 1, attn_nsplit = 1, attn_lpp = 1;
+	// TMA-ring matvec kernels (ring.cuh): slots per warp / CTAs per SM for FFN-up and for wo / w2; u = 512-byte units per row and chunk (0: not used)
+	int ring_up_ns = 2, ring_up_cps = 2, ring_res_ns = 3, ring_res_cps = 1;
+	int ring_up_u = 0, ring_wo_u = 0, ring_down_u = 0, ring_wo_s = 1, ring_down_s = 1;
+	int grid_up_ring = 0, grid_wo_ring = 0, grid_down_ring = 0;
+	size_t smem_up_ring = 0, smem_wo_ring = 0, smem_down_ring = 0;
+	bool attn2_cluster = false; // ... with the CTAs of a unit as one thread-block cluster (slices folded through distributed shared memory)
 	bool attn2 = false; // k_attn2 (attn.cuh): KV slice requested into shared memory ahead of the dependency wait
 	int attn_nbmax = 0;
 	size_t attn2_smem = 0;
@@ -373,11 +380,39 @@ void launch_attn(const AttnArgs& a, int nunits, int* nl) {
 
 template <typename KVT, int HG, int LPP>
 void launch_attn2(const AttnArgs& a, int nunits, int* nl) {
-	if (!nl) {
-		smem_optin(k_attn2<KVT, HG, LPP>, g.attn2_smem);
+	if (!nl) { // prepare time: opt-ins, and whether the cluster form can be scheduled at all
+		smem_optin(k_attn2<KVT, HG, LPP, false>, g.attn2_smem);
+		if (g.attn2_cluster) {
+			smem_optin(k_attn2<KVT, HG, LPP, true>, g.attn2_smem);
+			if (a.nsplit > 8) CUDA_CHECK(cudaFuncSetAttribute(k_attn2<KVT, HG, LPP, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+			cudaLaunchConfig_t cfg = {};
+			cfg.gridDim = dim3(nunits * a.nsplit), cfg.blockDim = dim3(ATTN_THREADS), cfg.dynamicSmemBytes = g.attn2_smem;
+			cudaLaunchAttribute at[1];
+			at[0].id = cudaLaunchAttributeClusterDimension;
+			at[0].val.clusterDim.x = a.nsplit, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+			cfg.attrs = at, cfg.numAttrs = 1;
+			int nclusters = 0;
+			if (cudaOccupancyMaxActiveClusters(&nclusters, k_attn2<KVT, HG, LPP, true>, &cfg) != cudaSuccess || nclusters < 1) {
+				(void)cudaGetLastError();
+				g.attn2_cluster = false; // e.g. no GPC with nsplit free SMs: fold the slices through global partials instead
+			}
+		}
 		return;
 	}
-	launch_pdl(k_attn2<KVT, HG, LPP>, nunits * a.nsplit, ATTN_THREADS, g.attn2_smem, a);
+	if (g.attn2_cluster) {
+		same_carveout((const void*)k_attn2<KVT, HG, LPP, true>);
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(nunits * a.nsplit), cfg.blockDim = dim3(ATTN_THREADS), cfg.dynamicSmemBytes = g.attn2_smem, cfg.stream = g.stream;
+		cudaLaunchAttribute at[2];
+		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
+		at[1].id = cudaLaunchAttributeClusterDimension;
+		at[1].val.clusterDim.x = a.nsplit, at[1].val.clusterDim.y = 1, at[1].val.clusterDim.z = 1;
+		cfg.attrs = at, cfg.numAttrs = 2;
+		CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_attn2<KVT, HG, LPP, true>, a));
+	} else {
+		launch_pdl(k_attn2<KVT, HG, LPP, false>, nunits * a.nsplit, ATTN_THREADS, g.attn2_smem, a);
+	}
 	++*nl;
 }
 
@@ -406,6 +441,40 @@ void dispatch_attn(const AttnArgs& a, int nunits, int* nl) {
 	case 6: launch_attn<KVT, 6>(a, nunits, nl); break;
 	case 7: launch_attn<KVT, 7>(a, nunits, nl); break;
 	default: launch_attn<KVT, 8>(a, nunits, nl); break;
+	}
+}
+
+// ring kernels are instantiated for U in {2, 4} (1 KB / 2 KB per row and chunk) and NS in {2, 3, 4}
+template <int DBITS, int U, int NS>
+void ring_up_launch(const FfnUpArgs& a, bool attr_only) {
+	if (attr_only) return smem_optin(k_ffn_up_ring<DBITS, U, NS>, g.smem_up_ring);
+	launch_pdl(k_ffn_up_ring<DBITS, U, NS>, g.grid_up_ring, RING_THREADS, g.smem_up_ring, a);
+}
+template <int DBITS, int U, int NS>
+void ring_res_launch(const MatResArgs& a, int S, int grid, size_t smem, bool attr_only) {
+	if (attr_only) return smem_optin(k_matres_ring<DBITS, U, NS>, smem);
+	launch_pdl(k_matres_ring<DBITS, U, NS>, grid, RING_THREADS, smem, a, S);
+}
+template <int DBITS>
+void ring_up_dispatch(const FfnUpArgs& a, bool attr_only) {
+	switch (g.ring_up_u * 10 + g.ring_up_ns) {
+	case 22: return ring_up_launch<DBITS, 2, 2>(a, attr_only);
+	case 23: return ring_up_launch<DBITS, 2, 3>(a, attr_only);
+	case 24: return ring_up_launch<DBITS, 2, 4>(a, attr_only);
+	case 42: return ring_up_launch<DBITS, 4, 2>(a, attr_only);
+	case 43: return ring_up_launch<DBITS, 4, 3>(a, attr_only);
+	default: return ring_up_launch<DBITS, 4, 4>(a, attr_only);
+	}
+}
+template <int DBITS>
+void ring_res_dispatch(const MatResArgs& a, int u, int S, int grid, size_t smem, bool attr_only) {
+	switch (u * 10 + g.ring_res_ns) {
+	case 22: return ring_res_launch<DBITS, 2, 2>(a, S, grid, smem, attr_only);
+	case 23: return ring_res_launch<DBITS, 2, 3>(a, S, grid, smem, attr_only);
+	case 24: return ring_res_launch<DBITS, 2, 4>(a, S, grid, smem, attr_only);
+	case 42: return ring_res_launch<DBITS, 4, 2>(a, S, grid, smem, attr_only);
+	case 43: return ring_res_launch<DBITS, 4, 3>(a, S, grid, smem, attr_only);
+	default: return ring_res_launch<DBITS, 4, 4>(a, S, grid, smem, attr_only);
 	}
 }
 
@@ -489,7 +558,8 @@ int run_token(int mode) {
 			if (dense && g.pf_wo_up) pf_up_prefix(a.pf, 0, w.w1[l], w.w3[l], g.pf_attn_up, g.pf_wo_up, up_bytes);
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l); // partial over this rank's heads, summed over the ranks in the kernel
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			launch_pdl(k_matres<DBITS, EARLY>, g.grid_wo, 256, g.smem_qdim, a);
+			if (g.ring_wo_u) ring_res_dispatch<DBITS>(a, g.ring_wo_u, g.ring_wo_s, g.grid_wo_ring, g.smem_wo_ring, false);
+			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
@@ -509,8 +579,9 @@ int run_token(int mode) {
 			a.stamp = t.slot;
 			if (dense && g.pf_up_down) a.pf.p[0] = w.w2[l], a.pf.bytes[0] = (g.pf_up_down < down_bytes ? g.pf_up_down : down_bytes) & ~(size_t)15;
 			bool done = false;
+			if (g.ring_up_u) ring_up_dispatch<DBITS>(a, false), done = true;
 			if constexpr (DBITS != 4) {
-				if (g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
+				if (!done && g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
 			}
 			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, 256, g.smem_dim, a);
 			++nl;
@@ -527,7 +598,8 @@ int run_token(int mode) {
 			}
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
+			if (g.ring_down_u) ring_res_dispatch<DBITS>(a, g.ring_down_u, g.ring_down_s, g.grid_down_ring, g.smem_down_ring, false);
+			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
@@ -648,11 +720,12 @@ void make_plan() {
 		g.attn2_smem = attn2_smem_bytes<KVT>(g.attn_hg, c.head_dim, g.attn_nbmax, g.attn_nsplit);
 		const bool want = !(getenv("CALM_B200_ATTN2") && atoi(getenv("CALM_B200_ATTN2")) == 0);
 		g.attn2 = want && attn2_shape_ok(g.attn_hg, g.attn_lpp, c.head_dim) && g.attn_nbmax <= ATTN2_MAXB && g.attn2_smem <= 200 * 1024;
+		g.attn2_cluster = g.attn2 && g.attn_nsplit <= ATTN2_MAX_CLUSTER && !(getenv("CALM_B200_ATTN_CLUSTER") && atoi(getenv("CALM_B200_ATTN_CLUSTER")) == 0);
 		AttnArgs aa = {};
-		aa.head_dim = c.head_dim, aa.nsplit = g.attn_nsplit_cap;
-		dispatch_attn<KVT>(aa, 0, nullptr);
+		aa.head_dim = c.head_dim, aa.nsplit = g.attn_nsplit;
+		dispatch_attn<KVT>(aa, c.n_kv_heads * g.attn_qgroups, nullptr);
 	}
-	g.grid_qkv = imin(g.sms, cdiv((g.q_dim + 2 * g.kv_dim) / 2, QKV_THREADS / 32)); // one 12-warp CTA per SM, equal contiguous shares
+	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT, EARLY>, QKV_THREADS, g.smem_dim));
 	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_qdim));
 	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_hidden));
 	if (g.tp_fused) { // the in-kernel exchange needs co-resident grids (they are: balanced_grid stays under the cap) within its tables
@@ -670,6 +743,50 @@ void make_plan() {
 			smem_optin(k_ffn_up_mma<DBITS>, g.smem_dim);
 			g.grid_up_mma = imin(max_ctas(k_ffn_up_mma<DBITS>, 256, g.smem_dim), c.hidden_dim / 8);
 		}
+	}
+	// TMA-ring kernels for the dense single-GPU stages whose rows are whole 1 KB / 2 KB chunks (ring.cuh)
+	g.ring_up_u = g.ring_wo_u = g.ring_down_u = 0;
+	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_cps);
+	const bool ring_on = g.ring_up_ns >= 2 && g.ring_res_ns >= 2 && g.ring_up_ns <= RING_MAX_NS && g.ring_res_ns <= RING_MAX_NS && c.n_experts == 0 && g.tp_world == 1;
+	auto chunk_units = [](size_t rowbytes) { return rowbytes % 2048 == 0 ? 4 : (rowbytes % 1024 == 0 ? 2 : 0); };
+	if (ring_on && !g.mma_up) {
+		const int u = chunk_units((size_t)c.dim * DBITS / 8);
+		if (u) {
+			g.smem_up_ring = ring_smem_bytes<DBITS>(c.dim, u, g.ring_up_ns);
+			if (g.smem_up_ring <= 200 * 1024) {
+				g.ring_up_u = u;
+				g.grid_up_ring = imin(g.sms * imin(g.ring_up_cps, (int)(220 * 1024 / g.smem_up_ring)), c.hidden_dim);
+				if (g.grid_up_ring < 1) g.grid_up_ring = 1;
+				FfnUpArgs fa = {};
+				ring_up_dispatch<DBITS>(fa, true);
+			}
+		}
+	}
+	if (ring_on) {
+		auto plan_res = [&](int n, int& u_out, int& s_out, int& grid_out, size_t& smem_out) {
+			const size_t rowbytes = (size_t)n * DBITS / 8;
+			const int u = chunk_units(rowbytes);
+			if (!u) return;
+			const size_t smem = ring_smem_bytes<DBITS>(n, u, g.ring_res_ns);
+			if (smem > 200 * 1024) return;
+			const int grid = imin(g.sms * imin(g.ring_res_cps, (int)(220 * 1024 / smem)), c.dim / 2);
+			const int cpt = (int)(rowbytes / (u * 512));
+			const bool split = cdiv(c.dim / 2, grid) + 1 <= RING_MAX_PAIRS && cpt <= RING_MAX_SLICES; // K-slices of one chunk, folded in shared memory
+			u_out = u, s_out = split ? 1 : cpt, grid_out = grid < 1 ? 1 : grid, smem_out = smem;
+			MatResArgs ma = {};
+			ring_res_dispatch<DBITS>(ma, u, s_out, grid_out, smem, true);
+		};
+		// ONE shared-memory attribute per kernel instantiation: wo and w2 may share one (same U): opt in to the larger first
+		int uw = 0, ud = 0, sw = 1, sd = 1, gw = 0, gd = 0;
+		size_t mw = 0, md = 0;
+		plan_res(g.q_dim, uw, sw, gw, mw);
+		plan_res(c.hidden_dim, ud, sd, gd, md);
+		if (uw && ud && uw == ud) { // same instantiation: its attribute must cover both launches
+			MatResArgs ma = {};
+			ring_res_dispatch<DBITS>(ma, uw, 1, 1, mw > md ? mw : md, true);
+		}
+		g.ring_wo_u = uw, g.ring_wo_s = sw, g.grid_wo_ring = gw, g.smem_wo_ring = mw;
+		g.ring_down_u = ud, g.ring_down_s = sd, g.grid_down_ring = gd, g.smem_down_ring = md;
 	}
 	g.out_row0 = 0, g.out_row1 = c.vocab_size;
 	if (g.tp_fused) { // vocabulary split: equal slices of whole 32-row CTA iterations (the last rank's may be short)
@@ -877,6 +994,12 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	int want = g.sms / units;                           // about one 256-thread CTA per SM
 	int maxsplit = cdiv(c.seq_len, 64);                 // at least 64 positions per slice at full context
 	g.attn_nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
+	if (attn2_shape_ok(g.attn_hg, g.attn_lpp, c.head_dim) && !(getenv("CALM_B200_ATTN_CLUSTER") && atoi(getenv("CALM_B200_ATTN_CLUSTER")) == 0) &&
+	    !(getenv("CALM_B200_ATTN2") && atoi(getenv("CALM_B200_ATTN2")) == 0)) {
+		int ns = 1; // the slices of a unit will be one thread-block cluster: a power of two, at most 16 CTAs
+		while (ns * 2 <= g.attn_nsplit && ns * 2 <= ATTN2_MAX_CLUSTER) ns *= 2;
+		g.attn_nsplit = ns;
+	}
 	g.attn_partial = (float*)dev_alloc((size_t)units * g.attn_nsplit * g.attn_hg * (c.head_dim + 2) * sizeof(float));
 	g.attn_counter = (unsigned*)dev_alloc(units * sizeof(unsigned));
 	CUDA_CHECK(cudaMemset(g.attn_counter, 0, units * sizeof(unsigned)));

@@ -301,13 +301,12 @@ struct QkvArgs {
 // no registers); 2 the same, and k_ffn_up keeps 8 vectors per row in flight at 2 CTAs per SM instead of 4 at 3.
 // (Issuing the first loads into registers instead was measured 25 % slower: 32 more live registers across the
 // staging cost a CTA per SM or spills.)
-#define QKV_THREADS 384
-// One CTA per SM, 12 warps at 80 registers per thread: half of the register file and most of the shared memory stay free
-// for the attention kernel, whose CTAs become resident while this kernel runs and request their KV slices (attn.cuh).
-// CTA c owns the contiguous row pairs [c * npairs / G, (c + 1) * npairs / G) -- every SM streams the same number of
-// bytes to within one pair -- and its warps take them round-robin.
+#define QKV_THREADS 256
+// One warp per row pair (the whole 2 x rowbytes pair is requested in one batch), 3 CTAs per SM.  (A one-CTA-per-SM form with
+// equal contiguous shares, meant to leave half the register file to an early attention CTA, measured 2.8 us slower per
+// launch: most warps then need a second DRAM round trip -- profiles/README.md, round 2.)
 template <int DBITS, typename KVT, int EARLY>
-__global__ void __launch_bounds__(QKV_THREADS, 2) k_qkv(const QkvArgs<KVT> a) {
+__global__ void __launch_bounds__(QKV_THREADS, 3) k_qkv(const QkvArgs<KVT> a) {
 	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	float* red = smem;
@@ -316,7 +315,6 @@ __global__ void __launch_bounds__(QKV_THREADS, 2) k_qkv(const QkvArgs<KVT> a) {
 	const int nvec = a.dim / WFmt<DBITS>::VW;
 	const size_t rowvecs = (size_t)nvec; // 16-byte vectors per row
 	const int npairs = (a.q_dim + 2 * a.kv_dim) / 2;
-	const int p_lo = (int)(((long long)blockIdx.x * npairs) / gridDim.x), p_hi = (int)(((long long)(blockIdx.x + 1) * npairs) / gridDim.x);
 	auto rows_of = [&](int p, const uint4* (&rp)[2], int& j, int& k) {
 		j = 2 * p; // row in the concatenated [wq; wk; wv]
 		const void* w;
@@ -330,8 +328,8 @@ __global__ void __launch_bounds__(QKV_THREADS, 2) k_qkv(const QkvArgs<KVT> a) {
 		rp[0] = reinterpret_cast<const uint4*>(w) + (size_t)k * rowvecs, rp[1] = rp[0] + rowvecs;
 	};
 	// weights first: they do not depend on the previous kernel, so their latency hides its tail and the staging of x
-	const int p0 = p_lo + warp;
-	if (EARLY != 0 && p0 < p_hi && lane == 0) {
+	const int p0 = blockIdx.x * nwarps + warp;
+	if (EARLY != 0 && p0 < npairs && lane == 0) {
 		const uint4* rp[2];
 		int j, k;
 		rows_of(p0, rp, j, k);
@@ -344,7 +342,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 2) k_qkv(const QkvArgs<KVT> a) {
 	const int kv_pos = a.tp->kv_pos;
 	prefetch_kv(a.pf, a.tp->kv_len); // this layer's cache prefix, for the attention kernel that follows
 
-	for (int p = p0; p < p_hi; p += nwarps) {
+	for (int p = p0; p < npairs; p += gridDim.x * nwarps) {
 		const uint4* rp[2];
 		int j, k;
 		rows_of(p, rp, j, k);
@@ -356,7 +354,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 2) k_qkv(const QkvArgs<KVT> a) {
 			if (a.bias) v0 += a.bias[j], v1 += a.bias[j + 1];
 			v0 = fminf(fmaxf(v0, -a.clip), a.clip);
 			v1 = fminf(fmaxf(v1, -a.clip), a.clip);
-			if (j < a.q_dim + a.kv_dim) { // rotate q and k (reference infer.c:223-236)
+			if (j < a.q_dim + a.kv_dim) { // rotate q and k (reference infer.c:223-236); angles from k_embed's table
 				const float2 cs = a.rope_cs[(j % a.head_dim) >> 1];
 				float r0 = v0 * cs.x - v1 * cs.y, r1 = v0 * cs.y + v1 * cs.x;
 				v0 = r0, v1 = r1;
@@ -425,12 +423,12 @@ struct KvRaw<uint8_t> {
 	}
 };
 
-// Everything after the position loop of a work item: merge the lane groups of a warp, the warps of the CTA (shared memory),
-// write the slice's partial (m, l, acc) and let the last slice of the unit fold all slices into the normalised output.
+// After the position loop of a work item: merge the lane groups of a warp and the warps of the CTA (shared memory) into ONE
+// record (m, l, acc) per head, written to `dst` [HG][head_dim + 2] (the slice's global partial, or shared memory).
 // m / l / acc: per-lane state of this warp's HH heads (8 head dims per lane, li = lane % lpp).
 template <int HH>
-__device__ __forceinline__ void attn_tail(const AttnArgs& a, int HG, int unit, int split, int hbase, int h0, int nh, int warp, int nwarps, float (&m)[HH], float (&l)[HH],
-                                          float (&acc)[HH][8], float* scratch, int* flag) {
+__device__ __forceinline__ void attn_cta_merge(const AttnArgs& a, int HG, int h0, int nh, int warp, int nwarps, float (&m)[HH], float (&l)[HH], float (&acc)[HH][8],
+                                               float* scratch, float* dst) {
 	const int lane = threadIdx.x & 31;
 	const int hd = a.head_dim, lpp = a.lpp;
 	const int grp = lane / lpp, li = lane % lpp;
@@ -469,7 +467,6 @@ __device__ __forceinline__ void attn_tail(const AttnArgs& a, int HG, int unit, i
 		}
 	}
 	__syncthreads();
-	float* part = a.partial + ((size_t)unit * a.nsplit + split) * HG * rec;
 	for (int idx = threadIdx.x; idx < HG * rec; idx += blockDim.x) {
 		int h = idx / rec, e = idx % rec;
 		float mn = -FLT_MAX;
@@ -484,8 +481,17 @@ __device__ __forceinline__ void attn_tail(const AttnArgs& a, int HG, int unit, i
 				v += r[e] * expf(r[hd] - mn); // e == hd+1 merges the sums the same way
 			}
 		}
-		__stcg(part + idx, v);
+		dst[idx] = v;
 	}
+}
+
+// attn_cta_merge into the slice's global partial, then the last slice of the unit to arrive folds all slices into the
+// normalised output (two passes, all loads independent; deterministic).
+template <int HH>
+__device__ __forceinline__ void attn_tail(const AttnArgs& a, int HG, int unit, int split, int hbase, int h0, int nh, int warp, int nwarps, float (&m)[HH], float (&l)[HH],
+                                          float (&acc)[HH][8], float* scratch, int* flag) {
+	const int hd = a.head_dim, rec = hd + 2;
+	attn_cta_merge<HH>(a, HG, h0, nh, warp, nwarps, m, l, acc, scratch, a.partial + ((size_t)unit * a.nsplit + split) * HG * rec);
 
 	// the last slice of this unit to finish folds all slices and writes the normalised output
 	__threadfence();
