@@ -76,6 +76,11 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	const KVT* kglob = reinterpret_cast<const KVT*>(a.kc) + (size_t)kvh * a.seq_len * HD;
 	const KVT* vglob = reinterpret_cast<const KVT*>(a.vc) + (size_t)kvh * a.seq_len * HD;
 
+#define ATTN_DBG(i)                                                          \
+	do {                                                                     \
+		if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[i] = globaltimer_ns(); \
+	} while (0)
+	ATTN_DBG(0);
 	pdl_launch_next();
 	if (tid == 0) {
 		for (int j = 0; j < nbmax; ++j) mbar_init(&bars[j], 1);
@@ -97,10 +102,13 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	}
 	pdl_wait_prev();
 	stamp_begin(a.stamp);
+	ATTN_DBG(1);
+	if (a.dbg && tid == 0) atomicMin(a.dbg + 10, globaltimer_ns());
 	const int kv_len = a.tp->kv_len, kv_pos = a.tp->kv_pos, kv_sink = a.tp->kv_sink;
 	if (tid < nbmax && !issued && (split + tid * nsplit) * ATTN2_BP < kv_len) request(tid), issued = true;
 	for (int i = tid; i < HG * HD; i += ATTN_THREADS) qs[i] = __ldcg(a.q + (size_t)hbase * HD + i);
 	__syncthreads();
+	ATTN_DBG(2);
 
 	// blocks of this CTA that hold cached positions
 	const int nblk = (kv_len + ATTN2_BP - 1) / ATTN2_BP;
@@ -122,6 +130,7 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 		const int j = inr ? s0 / ATTN2_BP : 0, o = s0 % ATTN2_BP;
 		const int t0 = (split + j * nsplit) * ATTN2_BP + o;
 		if (inr) mbar_wait(&bars[j], 0);
+		if (s0 == 0) ATTN_DBG(3);
 		raw_t kr[P], vr[P];
 		bool ok[P];
 #pragma unroll
@@ -204,6 +213,7 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 			}
 		}
 	}
+	ATTN_DBG(4);
 #pragma unroll
 	for (int h = 0; h < HG; ++h) { // running max / sum live in the lanes that own the head: hand them to every lane of the group
 		m[h] = __shfl_sync(0xffffffffu, mh, grp * LPP + h * P);
@@ -251,5 +261,7 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	}
 	// no bulk copy may still be in flight into this CTA's shared memory when it exits (a block requested on a stale hint)
 	if (tid < nbmax && issued) mbar_wait(&bars[tid], 0);
+	ATTN_DBG(7);
+	if (a.dbg && tid == 0) atomicMax(a.dbg + 9, globaltimer_ns());
 	stamp_end(a.stamp);
 }

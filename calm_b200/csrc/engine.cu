@@ -56,7 +56,7 @@ struct Engine {
 	// attention launch shape
 	int attn_hg = 1, attn_qgroups = 1, attn_nsplit = 1, attn_lpp = 1;
 	// TMA-ring matvec kernels (ring.cuh): slots per warp / CTAs per SM for FFN-up and for wo / w2; u = 512-byte units per row and chunk (0: not used)
-	int ring_up_ns = 2, ring_up_cps = 2, ring_res_ns = 3, ring_res_cps = 1;
+	int ring_up_ns = 2, ring_up_cps = 2, ring_res_ns = 2, ring_res_warps = 16; // measured: 16 consuming warps per SM are needed (profiles/r02_sweep_ring_*.jsonl)
 	int ring_up_u = 0, ring_wo_u = 0, ring_down_u = 0, ring_wo_s = 1, ring_down_s = 1;
 	int grid_up_ring = 0, grid_wo_ring = 0, grid_down_ring = 0;
 	size_t smem_up_ring = 0, smem_wo_ring = 0, smem_down_ring = 0;
@@ -448,12 +448,12 @@ void dispatch_attn(const AttnArgs& a, int nunits, int* nl) {
 template <int DBITS, int U, int NS>
 void ring_up_launch(const FfnUpArgs& a, bool attr_only) {
 	if (attr_only) return smem_optin(k_ffn_up_ring<DBITS, U, NS>, g.smem_up_ring);
-	launch_pdl(k_ffn_up_ring<DBITS, U, NS>, g.grid_up_ring, RING_THREADS, g.smem_up_ring, a);
+	launch_pdl(k_ffn_up_ring<DBITS, U, NS>, g.grid_up_ring, 256, g.smem_up_ring, a);
 }
 template <int DBITS, int U, int NS>
 void ring_res_launch(const MatResArgs& a, int S, int grid, size_t smem, bool attr_only) {
 	if (attr_only) return smem_optin(k_matres_ring<DBITS, U, NS>, smem);
-	launch_pdl(k_matres_ring<DBITS, U, NS>, grid, RING_THREADS, smem, a, S);
+	launch_pdl(k_matres_ring<DBITS, U, NS>, grid, g.ring_res_warps * 32, smem, a, S);
 }
 template <int DBITS>
 void ring_up_dispatch(const FfnUpArgs& a, bool attr_only) {
@@ -516,7 +516,7 @@ int run_token(int mode) {
 		a.tile_ctr = g.tile_ctr, a.n_ctr = c.n_layers;
 		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq, a.rope_cs = g.rope_cs;
 		a.n_layers = c.n_layers, a.n_kv_heads = c.n_kv_heads, a.head_dim = hd, a.seq_len = c.seq_len;
-		a.stamp = nullptr, a.stamp_reset = g.perf ? g.stamps : nullptr, a.n_stamps = MAX_STAMPS;
+		a.stamp = nullptr, a.stamp_reset = g.perf ? g.stamps : nullptr, a.n_stamps = MAX_STAMPS + 8; // + the 16 debug stamps
 		if (g.pf_down_qkv) qkv_weights(a.pf, 0);
 		launch_pdl(k_embed<DBITS, KVT>, a.embed_blocks + 8, 256, 0, a);
 		++nl;
@@ -545,6 +545,7 @@ int run_token(int mode) {
 			a.kv_mul = g.kv_mul, a.qgroups = g.attn_qgroups;
 			a.inv_sqrt_hd = 1.0f / sqrtf((float)hd);
 			a.nbmax = g.attn_nbmax;
+			a.dbg = (g.perf && l == c.n_layers / 2) ? g.stamps + 2 * (size_t)MAX_STAMPS : nullptr;
 			a.stamp = t.slot;
 			if (g.pf_attn_wo) a.pf.p[0] = w.wo[l], a.pf.bytes[0] = wo_bytes;
 			if (dense && g.pf_attn_up) pf_up_prefix(a.pf, 1, w.w1[l], w.w3[l], 0, g.pf_attn_up, up_bytes);
@@ -720,7 +721,7 @@ void make_plan() {
 		g.attn2_smem = attn2_smem_bytes<KVT>(g.attn_hg, c.head_dim, g.attn_nbmax, g.attn_nsplit);
 		const bool want = !(getenv("CALM_B200_ATTN2") && atoi(getenv("CALM_B200_ATTN2")) == 0);
 		g.attn2 = want && attn2_shape_ok(g.attn_hg, g.attn_lpp, c.head_dim) && g.attn_nbmax <= ATTN2_MAXB && g.attn2_smem <= 200 * 1024;
-		g.attn2_cluster = g.attn2 && g.attn_nsplit <= ATTN2_MAX_CLUSTER && !(getenv("CALM_B200_ATTN_CLUSTER") && atoi(getenv("CALM_B200_ATTN_CLUSTER")) == 0);
+		g.attn2_cluster = g.attn2 && g.attn_nsplit <= ATTN2_MAX_CLUSTER && getenv("CALM_B200_ATTN_CLUSTER") && atoi(getenv("CALM_B200_ATTN_CLUSTER")) != 0;
 		AttnArgs aa = {};
 		aa.head_dim = c.head_dim, aa.nsplit = g.attn_nsplit;
 		dispatch_attn<KVT>(aa, c.n_kv_heads * g.attn_qgroups, nullptr);
@@ -746,13 +747,15 @@ void make_plan() {
 	}
 	// TMA-ring kernels for the dense single-GPU stages whose rows are whole 1 KB / 2 KB chunks (ring.cuh)
 	g.ring_up_u = g.ring_wo_u = g.ring_down_u = 0;
-	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_cps);
-	const bool ring_on = g.ring_up_ns >= 2 && g.ring_res_ns >= 2 && g.ring_up_ns <= RING_MAX_NS && g.ring_res_ns <= RING_MAX_NS && c.n_experts == 0 && g.tp_world == 1;
+	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_warps); // 0 slots: stage not ring-fed
+	const bool ring_ok = c.n_experts == 0 && g.tp_world == 1;
+	const bool ring_up_on = ring_ok && g.ring_up_ns >= 2 && g.ring_up_ns <= RING_MAX_NS;
+	const bool ring_res_on = ring_ok && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) && DBITS != 4;
 	auto chunk_units = [](size_t rowbytes) { return rowbytes % 2048 == 0 ? 4 : (rowbytes % 1024 == 0 ? 2 : 0); };
-	if (ring_on && !g.mma_up) {
+	if (ring_up_on && !g.mma_up) {
 		const int u = chunk_units((size_t)c.dim * DBITS / 8);
 		if (u) {
-			g.smem_up_ring = ring_smem_bytes<DBITS>(c.dim, u, g.ring_up_ns);
+			g.smem_up_ring = ring_smem_bytes<DBITS>(c.dim, u, g.ring_up_ns, 8);
 			if (g.smem_up_ring <= 200 * 1024) {
 				g.ring_up_u = u;
 				g.grid_up_ring = imin(g.sms * imin(g.ring_up_cps, (int)(220 * 1024 / g.smem_up_ring)), c.hidden_dim);
@@ -762,14 +765,14 @@ void make_plan() {
 			}
 		}
 	}
-	if (ring_on) {
+	if (ring_res_on) {
 		auto plan_res = [&](int n, int& u_out, int& s_out, int& grid_out, size_t& smem_out) {
 			const size_t rowbytes = (size_t)n * DBITS / 8;
 			const int u = chunk_units(rowbytes);
 			if (!u) return;
-			const size_t smem = ring_smem_bytes<DBITS>(n, u, g.ring_res_ns);
-			if (smem > 200 * 1024) return;
-			const int grid = imin(g.sms * imin(g.ring_res_cps, (int)(220 * 1024 / smem)), c.dim / 2);
+			const size_t smem = ring_smem_bytes<DBITS>(n, u, g.ring_res_ns, g.ring_res_warps);
+			if (smem > 220 * 1024) return;
+			const int grid = imin(g.sms * imin(16 / g.ring_res_warps, (int)(224 * 1024 / smem)), c.dim / 2);
 			const int cpt = (int)(rowbytes / (u * 512));
 			const bool split = cdiv(c.dim / 2, grid) + 1 <= RING_MAX_PAIRS && cpt <= RING_MAX_SLICES; // K-slices of one chunk, folded in shared memory
 			u_out = u, s_out = split ? 1 : cpt, grid_out = grid < 1 ? 1 : grid, smem_out = smem;
@@ -945,9 +948,9 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 
 	CUDA_CHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventCreate(&g.timer[i]));
-	g.stamps = (unsigned long long*)dev_alloc((size_t)MAX_STAMPS * 2 * sizeof(unsigned long long));
+	g.stamps = (unsigned long long*)dev_alloc((size_t)(MAX_STAMPS * 2 + 16) * sizeof(unsigned long long));
 	g.stamp_acc = (unsigned long long*)dev_alloc((size_t)(MAX_STAMPS + 2) * sizeof(unsigned long long));
-	CUDA_CHECK(cudaMemset(g.stamps, 0, (size_t)MAX_STAMPS * 2 * sizeof(unsigned long long)));
+	CUDA_CHECK(cudaMemset(g.stamps, 0, (size_t)(MAX_STAMPS * 2 + 16) * sizeof(unsigned long long)));
 	CUDA_CHECK(cudaMemset(g.stamp_acc, 0, (size_t)(MAX_STAMPS + 2) * sizeof(unsigned long long)));
 	if (g.tp_world > 1) { // first collective outside any graph capture: NCCL sets up its channels and buffers here
 		CUDA_CHECK(cudaMemsetAsync(g.xpart, 0, c.dim * sizeof(float), g.stream));
@@ -994,8 +997,10 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	int want = g.sms / units;                           // about one 256-thread CTA per SM
 	int maxsplit = cdiv(c.seq_len, 64);                 // at least 64 positions per slice at full context
 	g.attn_nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
-	if (attn2_shape_ok(g.attn_hg, g.attn_lpp, c.head_dim) && !(getenv("CALM_B200_ATTN_CLUSTER") && atoi(getenv("CALM_B200_ATTN_CLUSTER")) == 0) &&
-	    !(getenv("CALM_B200_ATTN2") && atoi(getenv("CALM_B200_ATTN2")) == 0)) {
+	// (measured 9 us per launch SLOWER than the global-partial fold: a 16-CTA cluster needs 16 SMs of one GPC at once, which the
+	// still-resident q/k/v CTAs delay; kept selectable for the record -- profiles/r02_sweep_ring_and_attention_variants.jsonl)
+	const bool want_cluster = getenv("CALM_B200_ATTN_CLUSTER") && atoi(getenv("CALM_B200_ATTN_CLUSTER")) != 0;
+	if (want_cluster && attn2_shape_ok(g.attn_hg, g.attn_lpp, c.head_dim) && !(getenv("CALM_B200_ATTN2") && atoi(getenv("CALM_B200_ATTN2")) == 0)) {
 		int ns = 1; // the slices of a unit will be one thread-block cluster: a power of two, at most 16 CTAs
 		while (ns * 2 <= g.attn_nsplit && ns * 2 <= ATTN2_MAX_CLUSTER) ns *= 2;
 		g.attn_nsplit = ns;
@@ -1375,6 +1380,12 @@ extern "C" int calm_b200_stage_stats(int stage, char* name, int name_cap, double
 	if (g.perf) perf_collect();
 	*ms_total = g.stage_ms[stage], *bytes_total = g.stage_bytes[stage], *launches = g.stage_launches[stage];
 	return 1;
+}
+
+// (debug) the 16 in-kernel timestamps the middle layer's attention kernel left during the last profiled token
+extern "C" void calm_b200_debug_stamps(unsigned long long* out16) {
+	CUDA_CHECK(cudaStreamSynchronize(g.stream));
+	CUDA_CHECK(cudaMemcpy(out16, g.stamps + 2 * (size_t)MAX_STAMPS, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 }
 
 extern "C" double calm_b200_perf_token_ms(void) {

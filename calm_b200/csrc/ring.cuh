@@ -23,24 +23,23 @@
 
 #include "stages.cuh"
 
-#define RING_WARPS 8
-#define RING_THREADS (RING_WARPS * 32)
+#define RING_MAX_WARPS 16 // warps per CTA: 8 (two CTAs per SM) or 16 (one CTA per SM when the activation vector is long: w2)
 #define RING_MAX_NS 4
 #define RING_MAX_PAIRS 48 // row pairs per CTA when K-slices are folded through shared memory
 #define RING_MAX_SLICES 16
 
 struct RingCtl {
-	uint64_t bar[RING_WARPS][RING_MAX_NS];
-	int slot_task[RING_WARPS][RING_MAX_NS];
-	int slot_piece[RING_WARPS][RING_MAX_NS];
+	uint64_t bar[RING_MAX_WARPS][RING_MAX_NS];
+	int slot_task[RING_MAX_WARPS][RING_MAX_NS];
+	int slot_piece[RING_MAX_WARPS][RING_MAX_NS];
 	int ctr; // next task of this CTA
 };
 
 // shared memory of a ring kernel: [32 floats block-reduce][activation vector][ring: warps x NS x 2 rows x CH bytes]
 template <int DBITS>
-__host__ __device__ inline size_t ring_smem_bytes(int n, int u, int ns) {
+__host__ __device__ inline size_t ring_smem_bytes(int n, int u, int ns, int warps) {
 	size_t xs = ((size_t)(32 + xs_floats<DBITS>(n)) * sizeof(float) + 127) & ~(size_t)127;
-	return xs + (size_t)RING_WARPS * ns * 2 * u * 512;
+	return xs + (size_t)warps * ns * 2 * u * 512;
 }
 
 // The streaming loop of one warp.  rows(task, rp0, rp1, chunk0): byte pointers of the task's two rows and its first chunk
@@ -141,7 +140,7 @@ struct RingWarp {
 template <int NS>
 __device__ __forceinline__ void ring_init(RingCtl* ctl, int t_lo) {
 	if (threadIdx.x == 0) ctl->ctr = t_lo;
-	if (threadIdx.x < RING_WARPS * NS) mbar_init(&ctl->bar[threadIdx.x / NS][threadIdx.x % NS], 1);
+	if (threadIdx.x < (blockDim.x >> 5) * NS) mbar_init(&ctl->bar[threadIdx.x / NS][threadIdx.x % NS], 1);
 	if (threadIdx.x == 0) mbar_init_fence();
 	__syncthreads();
 }
@@ -150,7 +149,7 @@ __device__ __forceinline__ void ring_init(RingCtl* ctl, int t_lo) {
 // FFN up: hb[i] = act(w1[i] . xn) * (w3[i] . xn)   (reference infer.c:437-450); task i = rows (w1[i], w3[i]), whole rows.
 
 template <int DBITS, int U, int NS>
-__global__ void __launch_bounds__(RING_THREADS) k_ffn_up_ring(const FfnUpArgs a) {
+__global__ void __launch_bounds__(256, 2) k_ffn_up_ring(const FfnUpArgs a) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ RingCtl ctl;
 	float* red = reinterpret_cast<float*>(smem_raw);
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__(RING_THREADS) k_ffn_up_ring(const FfnUpArgs a)
 // slices of a pair land in part[][] and the last one to arrive adds them up in slice order.
 
 template <int DBITS, int U, int NS>
-__global__ void __launch_bounds__(RING_THREADS) k_matres_ring(const MatResArgs a, const int S) {
+__global__ void __launch_bounds__(512, 1) k_matres_ring(const MatResArgs a, const int S) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ RingCtl ctl;
 	__shared__ float2 part[RING_MAX_PAIRS][RING_MAX_SLICES];

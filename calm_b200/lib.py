@@ -26,7 +26,7 @@ SYMBOLS = [
     "calm_b200_abi_version", "calm_b200_set_device", "calm_b200_free", "calm_b200_release",
     "calm_b200_forward_argmax", "calm_b200_decode_greedy", "calm_b200_timer_start", "calm_b200_timer_stop",
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
-    "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_perf_token_ms",
+    "calm_b200_set_perf", "calm_b200_stage_stats", "calm_b200_perf_token_ms", "calm_b200_debug_stamps",
     "calm_b200_tp_unique_id", "calm_b200_tp_init", "calm_b200_tp_world", "calm_b200_tp_mode",
     "calm_b200_decode_sample", "calm_b200_forward_sample", "calm_b200_read_device_logits", "calm_b200_sample_logits",
 ]
@@ -65,6 +65,7 @@ def load() -> C.CDLL:
     L.calm_b200_stage_stats.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]
     L.calm_b200_stage_stats.restype = C.c_int
     L.calm_b200_perf_token_ms.argtypes, L.calm_b200_perf_token_ms.restype = [], C.c_double
+    L.calm_b200_debug_stamps.argtypes, L.calm_b200_debug_stamps.restype = [C.POINTER(C.c_ulonglong)], None
     L.calm_b200_tp_unique_id.argtypes, L.calm_b200_tp_unique_id.restype = [C.c_void_p], None
     L.calm_b200_tp_init.argtypes, L.calm_b200_tp_init.restype = [C.c_int, C.c_int, C.c_void_p], None
     L.calm_b200_tp_world.argtypes, L.calm_b200_tp_world.restype = [], C.c_int

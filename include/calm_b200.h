@@ -149,6 +149,8 @@ void calm_b200_fill_kv(struct Transformer* transformer, int n_pos, uint64_t seed
 void calm_b200_set_perf(int on);
 int calm_b200_stage_stats(int stage, char* name, int name_cap, double* ms_total, double* bytes_total, long* launches);
 double calm_b200_perf_token_ms(void);
+/* (debug) 16 raw %globaltimer stamps the attention kernel of the middle layer left during the last profiled token. */
+void calm_b200_debug_stamps(unsigned long long* out16);
 
 /* Stand-alone run of the production matvec kernel: y[d] = W[d,n] . x[n] with W
  * in the `dbits` format at device pointer `w_device`; x and y are HOST arrays.

@@ -53,9 +53,15 @@ def main():
                 dm.decode_greedy(23, pos0 + W, K)
                 best = min(best, L.calm_b200_timer_stop() / K)
             stats, span = dm.profile(23, seq_len - 16, 8)
+            import ctypes as C
+            dbg = (C.c_ulonglong * 16)()
+            L.calm_b200_debug_stamps(dbg)
+            d = [int(x) for x in dbg]
+            attn_dbg = {"entry->wait": d[1] - d[0], "wait->q": d[2] - d[1], "q->first_block": d[3] - d[2], "loop": d[4] - d[3], "tail": d[7] - d[4],
+                        "first_start->last_end": d[9] - d[10], "cta0_start_after_first": d[1] - d[10]} if d[1] else None
             dm.close()
             row = {k: round(v[0] / max(v[2], 1) * 1e3, 2) for k, v in stats.items() if v[2]}
-            print(json.dumps({"cfg": cfg, "ms_per_token": round(best, 4), "tok_s": round(1e3 / best, 1), "span_us_profiled": round(span * 1e3, 1), "us_per_launch": row}), flush=True)
+            print(json.dumps({"cfg": cfg, "ms_per_token": round(best, 4), "tok_s": round(1e3 / best, 1), "span_us_profiled": round(span * 1e3, 1), "us_per_launch": row, "attn_dbg_ns": attn_dbg}), flush=True)
         finally:
             for k, v in old.items():
                 if v is None:
