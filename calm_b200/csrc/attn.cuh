@@ -51,9 +51,33 @@ __host__ __device__ inline size_t attn2_smem_bytes(int hg, int head_dim, int nbm
 	return kv + ((size_t)hg * head_dim + scratch + (size_t)hg * (head_dim + 2)) * sizeof(float);
 }
 
-// CLUSTER: the nsplit CTAs of a unit are one thread-block cluster; the slices are folded through distributed shared memory
-// (one cluster barrier, each CTA normalises 1/nsplit of the unit's outputs from its peers' records) instead of through
-// global partials, a grid-scope fence, an atomic counter and a last-CTA pass that re-reads everything from L2.
+// How the slices of a unit are folded (measured on the in-kernel timeline, profiles/README.md round 2: with global partials,
+// a grid-scope fence, an atomic counter and a last-CTA pass the fold cost the last CTA 5.5 us of a 15 us kernel):
+//   CLUSTER = false (default): every CTA publishes its record as 8-byte {value, epoch} cells -- no fence, no atomic: a reader
+//     that sees the epoch sees the value -- and then normalises 1/nsplit of the unit's outputs itself, polling the cells
+//     of its peers (all CTAs of the grid are resident, so every cell arrives; a watchdog traps instead of hanging).
+//   CLUSTER = true: the nsplit CTAs of a unit are one thread-block cluster and read each other's records through
+//     distributed shared memory (measured slower: a 16-CTA cluster waits for 16 free SMs of one GPC; kept selectable).
+__device__ __forceinline__ float attn_cell_wait(const unsigned long long* cell, unsigned epoch, int* err) {
+	unsigned long long v;
+	unsigned spins = 0;
+	unsigned long long t0 = 0;
+	for (;;) {
+		asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(cell) : "memory");
+		if ((unsigned)(v >> 32) == epoch) break;
+		if ((++spins & 1023) == 0) {
+			const unsigned long long now = globaltimer_ns();
+			if (!t0) t0 = now;
+			if (now - t0 > 5000000000ull) { // 5 s: a slice never arrived -- fail loudly, never hang the GPU
+				if (err) *reinterpret_cast<volatile int*>(err) = 9200;
+				__threadfence_system();
+				__trap();
+			}
+		}
+	}
+	return __uint_as_float((unsigned)v);
+}
+
 template <typename KVT, int HG, int LPP, bool CLUSTER>
 __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	typedef typename KvRaw<KVT>::type raw_t;
@@ -104,9 +128,17 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	stamp_begin(a.stamp);
 	ATTN_DBG(1);
 	if (a.dbg && tid == 0) atomicMin(a.dbg + 10, globaltimer_ns());
+	// q and the token parameters are requested together (one L2 round trip, not two)
+	constexpr int QPT = (HG * HD + ATTN_THREADS - 1) / ATTN_THREADS;
+	float qreg[QPT];
+#pragma unroll
+	for (int i = 0; i < QPT; ++i) qreg[i] = (tid + i * ATTN_THREADS < HG * HD) ? __ldcg(a.q + (size_t)hbase * HD + tid + i * ATTN_THREADS) : 0.f;
 	const int kv_len = a.tp->kv_len, kv_pos = a.tp->kv_pos, kv_sink = a.tp->kv_sink;
+	const unsigned epoch = (unsigned)a.tp->tp_seq * a.epoch_stride + a.epoch_idx;
 	if (tid < nbmax && !issued && (split + tid * nsplit) * ATTN2_BP < kv_len) request(tid), issued = true;
-	for (int i = tid; i < HG * HD; i += ATTN_THREADS) qs[i] = __ldcg(a.q + (size_t)hbase * HD + i);
+#pragma unroll
+	for (int i = 0; i < QPT; ++i)
+		if (tid + i * ATTN_THREADS < HG * HD) qs[tid + i * ATTN_THREADS] = qreg[i];
 	__syncthreads();
 	ATTN_DBG(2);
 
@@ -257,7 +289,54 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 		}
 		cluster_sync_all(); // no CTA may exit (and free its shared memory) while a peer still reads its record
 	} else {
-		attn_tail<HG>(a, HG, unit, split, hbase, 0, HG, warp, NW, m, l, acc, scratch, &flag);
+		constexpr int REC = HD + 2;
+		__shared__ float mls[ATTN2_MAXB + 4][HG][2]; // (m, l) of every slice, then the coefficient in place  (nsplit <= 36)
+		__shared__ float invl[HG];
+		(void)flag;
+		attn_cta_merge<HG>(a, HG, 0, HG, warp, NW, m, l, acc, scratch, myrec);
+		__syncthreads();
+		ATTN_DBG(5);
+		unsigned long long* cells = a.cells + (size_t)unit * nsplit * HG * REC;
+		for (int i = tid; i < HG * REC; i += ATTN_THREADS) { // publish: ONE 8-byte store per value
+			const unsigned long long c = ((unsigned long long)epoch << 32) | __float_as_uint(myrec[i]);
+			asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(cells + (size_t)split * HG * REC + i), "l"(c) : "memory");
+		}
+		for (int i = tid; i < nsplit * HG; i += ATTN_THREADS) {
+			const int s = i / HG, h = i % HG;
+			const unsigned long long* c = cells + (size_t)s * HG * REC + h * REC + HD;
+			mls[s][h][0] = s == split ? myrec[h * REC + HD] : attn_cell_wait(c, epoch, a.err);
+			mls[s][h][1] = s == split ? myrec[h * REC + HD + 1] : attn_cell_wait(c + 1, epoch, a.err);
+		}
+		__syncthreads();
+		if (tid < HG) {
+			float M = -FLT_MAX;
+			for (int s = 0; s < nsplit; ++s) M = fmaxf(M, mls[s][tid][0]);
+			float L = 0.f;
+			for (int s = 0; s < nsplit; ++s) {
+				const float c = expf(mls[s][tid][0] - M);
+				L = fmaf(mls[s][tid][1], c, L);
+				mls[s][tid][0] = c;
+			}
+			invl[tid] = 1.0f / L;
+		}
+		__syncthreads();
+		ATTN_DBG(6);
+		// CTA `split` normalises outputs [split * per, (split + 1) * per): 8 adjacent lanes share an output, each sums every 8th slice
+		const int nout = HG * HD, per = (nout + nsplit - 1) / nsplit;
+		const int o_end = min(nout, (split + 1) * per);
+		for (int o0 = split * per; o0 < o_end; o0 += ATTN_THREADS / 8) {
+			const int o = o0 + tid / 8, sg = tid & 7;
+			float v = 0.f;
+			if (o < o_end) {
+				const int h = o / HD, e = o % HD;
+				for (int s = sg; s < nsplit; s += 8) {
+					const float x = s == split ? myrec[h * REC + e] : attn_cell_wait(cells + (size_t)s * HG * REC + h * REC + e, epoch, a.err);
+					v = fmaf(x, mls[s][h][0], v);
+				}
+			}
+			v += __shfl_xor_sync(0xffffffffu, v, 1), v += __shfl_xor_sync(0xffffffffu, v, 2), v += __shfl_xor_sync(0xffffffffu, v, 4);
+			if (o < o_end && sg == 0) __stcg(a.out + (size_t)hbase * HD + o, v * invl[o / HD]);
+		}
 	}
 	// no bulk copy may still be in flight into this CTA's shared memory when it exits (a block requested on a stale hint)
 	if (tid < nbmax && issued) mbar_wait(&bars[tid], 0);

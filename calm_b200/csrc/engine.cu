@@ -17,6 +17,7 @@
 #include "stages.cuh"
 #include "attn.cuh"
 #include "ring.cuh"
+#include "prefill.cuh"
 
 namespace {
 
@@ -42,6 +43,8 @@ struct Engine {
 	void *kc = nullptr, *vc = nullptr;
 	float* rope_freq = nullptr;
 	float2* rope_cs = nullptr; // (cos, sin) of the current token's RoPE angles, written by k_embed
+	unsigned long long* attn_cells = nullptr; // k_attn2's slice fold: {value, epoch} cells
+	int* dev_err = nullptr;                   // mapped host word: watchdog code of an in-kernel wait that gave up
 	float* attn_partial = nullptr;
 	unsigned* attn_counter = nullptr;
 	MoeSel* moe_sel = nullptr;
@@ -134,6 +137,17 @@ struct Engine {
 };
 
 Engine g;
+
+// batched prompt pass (prefill.cuh): buffers for up to `cap` tokens, allocated on first use
+struct Prefill {
+	int cap = 0;
+	float *X = nullptr, *Q = nullptr;
+	__half *Nhi = nullptr, *Nlo = nullptr, *Ahi = nullptr, *Alo = nullptr, *Hhi = nullptr, *Hlo = nullptr;
+	float2* rope = nullptr;
+	int* tokens = nullptr;
+	CUtensorMap tmN[2], tmA[2], tmH[2]; // (hi, lo) views of the three activation matrices the GEMMs read
+};
+Prefill pf;
 int g_device_override = -1;
 uint64_t g_launches = 0;
 
@@ -308,6 +322,18 @@ void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, Args
 	same_carveout((const void*)kernel);
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = g.stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
+	cfg.attrs = at, cfg.numAttrs = 1;
+	CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+
+template <typename... KArgs, typename... Args>
+void launch_pdl_grid(void (*kernel)(KArgs...), dim3 grid, int block, Args... args) {
+	same_carveout((const void*)kernel);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid, cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = 0, cfg.stream = g.stream;
 	cudaLaunchAttribute at[1];
 	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	at[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
@@ -545,6 +571,7 @@ int run_token(int mode) {
 			a.kv_mul = g.kv_mul, a.qgroups = g.attn_qgroups;
 			a.inv_sqrt_hd = 1.0f / sqrtf((float)hd);
 			a.nbmax = g.attn_nbmax;
+			a.cells = g.attn_cells, a.epoch_stride = (unsigned)c.n_layers + 1, a.epoch_idx = (unsigned)l + 1, a.err = g.dev_err;
 			a.dbg = (g.perf && l == c.n_layers / 2) ? g.stamps + 2 * (size_t)MAX_STAMPS : nullptr;
 			a.stamp = t.slot;
 			if (g.pf_attn_wo) a.pf.p[0] = w.wo[l], a.pf.bytes[0] = wo_bytes;
@@ -748,9 +775,9 @@ void make_plan() {
 	// TMA-ring kernels for the dense single-GPU stages whose rows are whole 1 KB / 2 KB chunks (ring.cuh)
 	g.ring_up_u = g.ring_wo_u = g.ring_down_u = 0;
 	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_warps); // 0 slots: stage not ring-fed
-	const bool ring_ok = c.n_experts == 0 && g.tp_world == 1;
-	const bool ring_up_on = ring_ok && g.ring_up_ns >= 2 && g.ring_up_ns <= RING_MAX_NS;
-	const bool ring_res_on = ring_ok && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) && DBITS != 4;
+	const bool ring_ok = c.n_experts == 0; // MoE: the expert rows are known only after the router
+	const bool ring_up_on = ring_ok && g.ring_up_ns >= 2 && g.ring_up_ns <= RING_MAX_NS; // (row shards of w1 / w3 under tensor parallelism are fine)
+	const bool ring_res_on = ring_ok && g.tp_world == 1 /* wo / w2 carry the in-kernel exchange there */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) && DBITS != 4;
 	auto chunk_units = [](size_t rowbytes) { return rowbytes % 2048 == 0 ? 4 : (rowbytes % 1024 == 0 ? 2 : 0); };
 	if (ring_up_on && !g.mma_up) {
 		const int u = chunk_units((size_t)c.dim * DBITS / 8);
@@ -999,6 +1026,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.attn_nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
 	// (measured 9 us per launch SLOWER than the global-partial fold: a 16-CTA cluster needs 16 SMs of one GPC at once, which the
 	// still-resident q/k/v CTAs delay; kept selectable for the record -- profiles/r02_sweep_ring_and_attention_variants.jsonl)
+	if (g.attn_nsplit > ATTN2_MAXB) g.attn_nsplit = ATTN2_MAXB; // k_attn2 keeps one (m, l) pair per slice in static shared memory
 	const bool want_cluster = getenv("CALM_B200_ATTN_CLUSTER") && atoi(getenv("CALM_B200_ATTN_CLUSTER")) != 0;
 	if (want_cluster && attn2_shape_ok(g.attn_hg, g.attn_lpp, c.head_dim) && !(getenv("CALM_B200_ATTN2") && atoi(getenv("CALM_B200_ATTN2")) == 0)) {
 		int ns = 1; // the slices of a unit will be one thread-block cluster: a power of two, at most 16 CTAs
@@ -1006,6 +1034,13 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 		g.attn_nsplit = ns;
 	}
 	g.attn_partial = (float*)dev_alloc((size_t)units * g.attn_nsplit * g.attn_hg * (c.head_dim + 2) * sizeof(float));
+	{
+		const size_t cell_bytes = (size_t)units * (g.sms / units > g.attn_nsplit ? g.sms / units : g.attn_nsplit) * g.attn_hg * (c.head_dim + 2) * sizeof(unsigned long long);
+		g.attn_cells = (unsigned long long*)dev_alloc(cell_bytes);
+		CUDA_CHECK(cudaMemset(g.attn_cells, 0, cell_bytes));
+		CUDA_CHECK(cudaHostAlloc((void**)&g.dev_err, sizeof(int), cudaHostAllocMapped));
+		*g.dev_err = 0;
+	}
 	g.attn_counter = (unsigned*)dev_alloc(units * sizeof(unsigned));
 	CUDA_CHECK(cudaMemset(g.attn_counter, 0, units * sizeof(unsigned)));
 
@@ -1079,7 +1114,12 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 	for (int v = 0; v < 2; ++v)
 		for (int i = 0; i < 5; ++i)
 			if (g.graph[v][i]) CUDA_CHECK(cudaGraphExecDestroy(g.graph[v][i]));
-	cudaFree(g.stamps), cudaFree(g.stamp_acc);
+	cudaFree(g.stamps), cudaFree(g.stamp_acc), cudaFree(g.attn_cells);
+	if (g.dev_err) cudaFreeHost(g.dev_err);
+	if (pf.cap) {
+		cudaFree(pf.X), cudaFree(pf.Q), cudaFree(pf.Nhi), cudaFree(pf.Nlo), cudaFree(pf.Ahi), cudaFree(pf.Alo), cudaFree(pf.Hhi), cudaFree(pf.Hlo), cudaFree(pf.rope), cudaFree(pf.tokens);
+		pf = Prefill();
+	}
 	cudaFree(g.x), cudaFree(g.xb), cudaFree(g.q), cudaFree(g.att), cudaFree(g.hb), cudaFree(g.logits_dev);
 	cudaFreeHost(g.logits_host), cudaFreeHost(g.last_token);
 	cudaFree(g.kc), cudaFree(g.vc), cudaFree(g.rope_freq), cudaFree(g.rope_cs), cudaFree(g.attn_partial), cudaFree(g.attn_counter);
@@ -1109,8 +1149,9 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 static void sync_stream() {
 	cudaError_t e = cudaStreamSynchronize(g.stream);
 	if (e != cudaSuccess) {
-		const int code = g.tp_err ? *(volatile int*)g.tp_err : 0; // 9000 + the rank never heard from
-		fprintf(stderr, "calm_b200: device failure: %s (%s); tensor-parallel watchdog code %d\n", cudaGetErrorString(e), cudaGetErrorName(e), code);
+		int code = g.tp_err ? *(volatile int*)g.tp_err : 0; // 9000 + the rank never heard from
+		if (!code && g.dev_err) code = *(volatile int*)g.dev_err; // 9200: a slice of the attention fold never arrived
+		fprintf(stderr, "calm_b200: device failure: %s (%s); watchdog code %d\n", cudaGetErrorString(e), cudaGetErrorName(e), code);
 		abort();
 	}
 }
@@ -1239,6 +1280,166 @@ extern "C" int calm_b200_sample_logits(const float* logits_host, int vocab, floa
 	cudaFree(logits), cudaFree(cmax), cudaFree(sst), cudaFree(count), cudaFree(csum), cudaFree(sidx), cudaFree(sprob), cudaFree(tok), cudaFree(tp);
 	cudaEventDestroy(e0), cudaEventDestroy(e1), cudaStreamDestroy(st);
 	return htok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward_prefill_cuda: the prompt as one batched pass (SURVEY.md s.8b "additive entry points"; reference run.c:206-209 calls
+// forward(..., FF_UPDATE_KV_ONLY) once per prompt token).
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static void pf_make_map(CUtensorMap* map, void* base, int rows, int cols) { // f16 [rows][cols], box = 128 rows x 64 columns, 128-byte swizzle
+	static EncodeTiledFn encode = nullptr;
+	if (!encode) {
+		cudaDriverEntryPointQueryResult qres;
+		void* fn = nullptr;
+		CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		if (!fn || qres != cudaDriverEntryPointSuccess) CALM_FATAL("cuTensorMapEncodeTiled is not available from this driver");
+		encode = (EncodeTiledFn)fn;
+	}
+	const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+	const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
+	const cuuint32_t box[2] = {PF_BK, PF_BN}, estr[2] = {1, 1};
+	CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+	                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) CALM_FATAL("cuTensorMapEncodeTiled failed (%d) for a %d x %d f16 matrix", (int)r, rows, cols);
+}
+
+static void pf_reserve(int n) {
+	const Config& c = g.cfg;
+	int cap = cdiv(n, PF_BN) * PF_BN;
+	if (cap <= pf.cap) return;
+	if (pf.cap) {
+		CUDA_CHECK(cudaStreamSynchronize(g.stream));
+		cudaFree(pf.X), cudaFree(pf.Q), cudaFree(pf.Nhi), cudaFree(pf.Nlo), cudaFree(pf.Ahi), cudaFree(pf.Alo), cudaFree(pf.Hhi), cudaFree(pf.Hlo), cudaFree(pf.rope), cudaFree(pf.tokens);
+	}
+	pf.cap = cap;
+	auto zalloc = [&](size_t bytes) {
+		void* p = dev_alloc(bytes);
+		CUDA_CHECK(cudaMemset(p, 0, bytes)); // padding rows of a partial token tile stay zero
+		return p;
+	};
+	pf.X = (float*)zalloc((size_t)cap * c.dim * sizeof(float));
+	pf.Q = (float*)zalloc((size_t)cap * g.q_dim * sizeof(float));
+	pf.Nhi = (__half*)zalloc((size_t)cap * c.dim * sizeof(__half)), pf.Nlo = (__half*)zalloc((size_t)cap * c.dim * sizeof(__half));
+	pf.Ahi = (__half*)zalloc((size_t)cap * g.q_dim * sizeof(__half)), pf.Alo = (__half*)zalloc((size_t)cap * g.q_dim * sizeof(__half));
+	pf.Hhi = (__half*)zalloc((size_t)cap * c.hidden_dim * sizeof(__half)), pf.Hlo = (__half*)zalloc((size_t)cap * c.hidden_dim * sizeof(__half));
+	pf.rope = (float2*)zalloc((size_t)cap * (c.head_dim / 2) * sizeof(float2));
+	pf.tokens = (int*)zalloc((size_t)cap * sizeof(int));
+	pf_make_map(&pf.tmN[0], pf.Nhi, cap, c.dim), pf_make_map(&pf.tmN[1], pf.Nlo, cap, c.dim);
+	pf_make_map(&pf.tmA[0], pf.Ahi, cap, g.q_dim), pf_make_map(&pf.tmA[1], pf.Alo, cap, g.q_dim);
+	pf_make_map(&pf.tmH[0], pf.Hhi, cap, c.hidden_dim), pf_make_map(&pf.tmH[1], pf.Hlo, cap, c.hidden_dim);
+}
+
+// which models the tensor-core pass serves; everything else is fed token by token (still on the GPU)
+static bool pf_supported() {
+	const Config& c = g.cfg;
+	return c.n_experts == 0 && g.tp_world == 1 && c.dim % PF_BM == 0 && g.q_dim % PF_BM == 0 && g.kv_dim % PF_BM == 0 && c.hidden_dim % PF_BM == 0 &&
+	       (c.head_dim == 64 || c.head_dim == 128) && !(getenv("CALM_B200_PREFILL") && atoi(getenv("CALM_B200_PREFILL")) == 0);
+}
+
+template <int MODE, int DBITS, typename KVT>
+static void pf_gemm(const CUtensorMap* tm, const PfGemmArgs& a, int rows, int n) {
+	static bool opted = false;
+	if (!opted) smem_optin(k_pf_gemm<MODE, DBITS, KVT>, pf_smem_bytes<MODE>()), opted = true;
+	same_carveout((const void*)k_pf_gemm<MODE, DBITS, KVT>);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(rows / PF_BM, cdiv(n, PF_BN)), cfg.blockDim = dim3(PF_THREADS), cfg.dynamicSmemBytes = pf_smem_bytes<MODE>(), cfg.stream = g.stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = g.use_pdl ? 1 : 0;
+	cfg.attrs = at, cfg.numAttrs = 1;
+	CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_pf_gemm<MODE, DBITS, KVT>, tm[0], tm[1], a));
+	++g_launches;
+}
+
+template <typename KVT, int HD>
+static void pf_attn(const PfAttnArgs& a, int n) {
+	const dim3 grid(cdiv(n, PFA_WARPS), g.cfg.n_kv_heads);
+	if (g.kv_mul % 4 == 0) launch_pdl_grid(k_pf_attn<KVT, HD, 4>, grid, PFA_WARPS * 32, a);
+	else if (g.kv_mul % 2 == 0) launch_pdl_grid(k_pf_attn<KVT, HD, 2>, grid, PFA_WARPS * 32, a);
+	else launch_pdl_grid(k_pf_attn<KVT, HD, 1>, grid, PFA_WARPS * 32, a);
+	++g_launches;
+}
+
+template <int DBITS, typename KVT>
+static void pf_run(int n, int pos0) {
+	const Config& c = g.cfg;
+	const Weights& w = g.w;
+	const size_t kv_layer = (size_t)c.n_kv_heads * c.seq_len * c.head_dim;
+	launch_pdl(k_pf_embed<DBITS>, n, 256, 0, pf.X, (const void*)w.token_embedding_table, (const int*)pf.tokens, n, c.dim);
+	launch_pdl(k_pf_rope, cdiv(n * (c.head_dim / 2), 256), 256, 0, pf.rope, (const float*)g.rope_freq, n, c.head_dim / 2, pos0);
+	g_launches += 2;
+	for (int l = 0; l < c.n_layers; ++l) {
+		launch_pdl(k_pf_norm, n, 256, 0, (const float*)pf.X, (const float*)w.rms_att_weight[l], pf.Nhi, pf.Nlo, n, c.dim, c.norm_eps, (int)c.norm_ln);
+		++g_launches;
+		PfGemmArgs a = {};
+		a.n_tokens = n;
+		a.w[0] = w.wq[l], a.w[1] = w.wk[l], a.w[2] = w.wv[l], a.K = c.dim;
+		a.Q = pf.Q, a.q_dim = g.q_dim, a.kv_dim = g.kv_dim, a.head_dim = c.head_dim, a.seq_len = c.seq_len, a.pos0 = pos0;
+		a.bias = w.bqkv[l], a.clip = c.qkv_clip, a.rope = pf.rope;
+		a.kc = (KVT*)g.kc + l * kv_layer, a.vc = (KVT*)g.vc + l * kv_layer;
+		pf_gemm<PF_QKV, DBITS, KVT>(pf.tmN, a, g.q_dim + 2 * g.kv_dim, n);
+
+		PfAttnArgs aa = {};
+		aa.Q = pf.Q, aa.kc = a.kc, aa.vc = a.vc, aa.Ohi = pf.Ahi, aa.Olo = pf.Alo;
+		aa.n_tokens = n, aa.pos0 = pos0, aa.seq_len = c.seq_len, aa.q_dim = g.q_dim, aa.kv_mul = g.kv_mul, aa.inv_sqrt_hd = 1.0f / sqrtf((float)c.head_dim);
+		if (c.head_dim == 128) pf_attn<KVT, 128>(aa, n);
+		else pf_attn<KVT, 64>(aa, n);
+
+		PfGemmArgs b = {};
+		b.n_tokens = n, b.w[0] = w.wo[l], b.K = g.q_dim, b.X = pf.X, b.dim = c.dim;
+		pf_gemm<PF_WO, DBITS, KVT>(pf.tmA, b, c.dim, n);
+
+		if (!c.norm_par) { // (parallel-norm models reuse the attention-norm output, reference infer.c:417-420)
+			launch_pdl(k_pf_norm, n, 256, 0, (const float*)pf.X, (const float*)w.rms_ffn_weight[l], pf.Nhi, pf.Nlo, n, c.dim, c.norm_eps, (int)c.norm_ln);
+			++g_launches;
+		}
+		PfGemmArgs u = {};
+		u.n_tokens = n, u.w[0] = w.w1[l], u.w[1] = w.w3[l], u.K = c.dim, u.Hhi = pf.Hhi, u.Hlo = pf.Hlo, u.hidden = c.hidden_dim, u.gelu = c.act_gelu;
+		pf_gemm<PF_UP, DBITS, KVT>(pf.tmN, u, c.hidden_dim, n);
+
+		PfGemmArgs d = {};
+		d.n_tokens = n, d.w[0] = w.w2[l], d.K = c.hidden_dim, d.X = pf.X, d.dim = c.dim;
+		pf_gemm<PF_DOWN, DBITS, KVT>(pf.tmH, d, c.dim, n);
+	}
+}
+
+// Feed `n` prompt tokens at positions pos0 .. pos0 + n - 1: the KV cache afterwards is what n calls of
+// forward_cuda(token, pos, FF_UPDATE_KV_ONLY) leave (within the stated tolerance); no logits, no synchronisation.
+// Returns 1 when the tensor-core pass ran, 0 when the tokens were fed one by one (unsupported model shape, MoE, tensor
+// parallelism, or a block that would roll the cache over).
+extern "C" int forward_prefill_cuda(struct Transformer* transformer, const int* tokens, int n, int pos0) {
+	if (n <= 0) return 1;
+	check_call(transformer, tokens[0], pos0);
+	for (int i = 0; i < n; ++i)
+		if (tokens[i] < 0 || tokens[i] >= g.cfg.vocab_size) CALM_FATAL("token %d out of range", tokens[i]);
+	if (!pf_supported() || pos0 + n > g.cfg.seq_len) {
+		for (int i = 0; i < n; ++i) {
+			set_params(tokens[i], pos0 + i, 0);
+			launch_token(0);
+		}
+		return 0;
+	}
+	const int chunk_cap = 2048;
+	for (int o = 0; o < n; o += chunk_cap) {
+		const int m = n - o < chunk_cap ? n - o : chunk_cap;
+		pf_reserve(m);
+		CUDA_CHECK(cudaMemcpyAsync(pf.tokens, tokens + o, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+		const int key = g.w.dbits * 100 + g.kvbits;
+		switch (key) {
+		case 1616: pf_run<16, __half>(m, pos0 + o); break;
+		case 1608: pf_run<16, uint8_t>(m, pos0 + o); break;
+		case 816: pf_run<8, __half>(m, pos0 + o); break;
+		case 808: pf_run<8, uint8_t>(m, pos0 + o); break;
+		case 416: pf_run<4, __half>(m, pos0 + o); break;
+		default: pf_run<4, uint8_t>(m, pos0 + o); break;
+		}
+		CUDA_CHECK(cudaStreamSynchronize(g.stream)); // `tokens` is the caller's memory (pageable): the copy above must have left it
+	}
+	CUDA_CHECK(cudaGetLastError());
+	return 1;
 }
 
 // the logits of the last device-resident step (decode_greedy / decode_sample keep them in HBM): copy for tests

@@ -395,6 +395,9 @@ struct AttnArgs {
 	int kv_mul, qgroups;                // query heads per kv head; qgroups = kv_mul / HG
 	float inv_sqrt_hd;
 	int nbmax;                          // k_attn2: 16-position blocks per CTA = ceil(ceil(seq_len / 16) / nsplit)
+	unsigned long long* cells;          // k_attn2: [units][nsplit][HG][head_dim + 2] {value, epoch} cells of the slice fold
+	unsigned epoch_stride, epoch_idx;   // epoch = tp_seq * stride + idx (unique per token and layer, never 0)
+	int* err;                           // mapped host word for the fold's watchdog
 	unsigned long long* dbg;            // perf: 16 timestamps of CTA 0 / extremes over CTAs (first layer only), or NULL
 	unsigned long long* stamp;
 	Prefetch pf;

@@ -22,7 +22,7 @@ _fptr = C.POINTER(C.c_float)
 
 # every symbol include/calm_b200.h declares
 SYMBOLS = [
-    "upload_cuda", "prepare_cuda", "forward_cuda", "perf_cuda",
+    "upload_cuda", "prepare_cuda", "forward_cuda", "perf_cuda", "forward_prefill_cuda",
     "calm_b200_abi_version", "calm_b200_set_device", "calm_b200_free", "calm_b200_release",
     "calm_b200_forward_argmax", "calm_b200_decode_greedy", "calm_b200_timer_start", "calm_b200_timer_stop",
     "calm_b200_stream", "calm_b200_launch_count", "calm_b200_read_kv", "calm_b200_fill_kv", "calm_b200_matvec",
@@ -47,6 +47,7 @@ def load() -> C.CDLL:
     L.prepare_cuda.argtypes, L.prepare_cuda.restype = [T], None
     L.forward_cuda.argtypes, L.forward_cuda.restype = [T, C.c_int, C.c_int, C.c_uint], _fptr
     L.perf_cuda.argtypes, L.perf_cuda.restype = [], None
+    L.forward_prefill_cuda.argtypes, L.forward_prefill_cuda.restype = [T, C.POINTER(C.c_int), C.c_int, C.c_int], C.c_int
     L.calm_b200_abi_version.argtypes, L.calm_b200_abi_version.restype = [], C.c_int
     L.calm_b200_set_device.argtypes, L.calm_b200_set_device.restype = [C.c_int], None
     L.calm_b200_free.argtypes, L.calm_b200_free.restype = [C.c_void_p], None
@@ -134,6 +135,11 @@ class DeviceModel:
         if not p:
             return None
         return np.ctypeslib.as_array(p, shape=(self.vocab,)).copy()
+
+    def prefill(self, tokens, pos0: int = 0) -> int:
+        """forward_prefill_cuda: the batched prompt pass; returns 1 (tensor-core pass) or 0 (fed token by token)."""
+        arr = np.ascontiguousarray(tokens, np.int32)
+        return self.lib.forward_prefill_cuda(C.byref(self.transformer), arr.ctypes.data_as(C.POINTER(C.c_int)), len(arr), pos0)
 
     def forward_raw(self, token: int, pos: int, flags: int = 0):
         return self.lib.forward_cuda(C.byref(self.transformer), token, pos, flags)

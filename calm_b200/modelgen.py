@@ -108,6 +108,9 @@ SPECS.update({
     # a shape that 2, 4 and 8 tensor-parallel ranks can split (8 kv heads, hidden = 4 * 32 * 8), and its MoE twin
     "tiny-tp8": replace(_T, name="tiny-tp8", n_heads=8, n_kv_heads=8, head_dim=32, hidden_dim=1024),
     "tiny-tp8-moe": replace(_T, name="tiny-tp8-moe", n_heads=8, n_kv_heads=8, head_dim=32, hidden_dim=1024, n_experts=4, n_experts_active=2),
+    # the smallest shapes the batched prompt pass serves (every dim a multiple of 128, head_dim 64 / 128)
+    "pf-tiny": ModelSpec("pf-tiny", 256, 512, 2, 4, 2, 64, 512, "fp8", rope_theta=1e4, max_seq_len=512),
+    "pf-tiny-hd128": ModelSpec("pf-tiny-hd128", 512, 1024, 2, 4, 1, 128, 512, "fp8", rope_theta=5e5, max_seq_len=512, qkv_bias=True),
     # Gemma-style multi-query attention: 8 query heads on ONE kv head of 256 dims (the attention kernel's merge
     # records exceed the default 48 KB of dynamic shared memory)
     # (hidden >= dim >= q_dim: the reference CPU backend reuses xb2[dim] and hb[hidden] as scratch, infer.c:152-153, 404, 409)

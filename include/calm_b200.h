@@ -93,6 +93,17 @@ int calm_b200_tp_world(void);
 int calm_b200_tp_mode(void);
 
 
+/* The prompt as ONE batched pass (the reference feeds prompt tokens one at a time through forward(.., FF_UPDATE_KV_ONLY),
+ * run.c:206-209, README.md:80): n tokens at positions pos0 .. pos0+n-1 go through every layer together; the projections
+ * are tensor-core GEMMs (tcgen05.mma, TMEM accumulators, weights dequantised on the fly, activations as an f16 hi + lo
+ * pair so inputs keep 22 bits), attention is causal over the block and the cache.  Afterwards the KV cache holds what n
+ * serial KV-only calls would have left (within the stated tolerance); no logits, no synchronisation with the host beyond
+ * reading `tokens`.  Returns 1 when the batched pass ran, 0 when the model shape is not served by it (MoE, tensor
+ * parallelism, dims not multiples of 128, head_dim other than 64 / 128, a block that would roll the cache over) and the
+ * tokens were fed one by one instead -- same result either way.  A host integrates it by replacing the prompt loop:
+ * forward_prefill_cuda(t, prompt, n - 1, 0); logits = forward_cuda(t, prompt[n - 1], n - 1, 0);  (INTEGRATION.md). */
+int forward_prefill_cuda(struct Transformer* transformer, const int* tokens, int n, int pos0);
+
 /* forward + device-side greedy sample.  Returns argmax(logits) with the
  * reference's tie rule (lowest index, sampler.c:34-42).  The logits are still
  * written to state.logits. */
