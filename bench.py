@@ -357,6 +357,29 @@ def main():
         "algorithmic_gb_per_token": bytes_per_tok / 1e9, "algorithmic_gb_per_token_per_gpu": per_gpu / 1e9, "hbm_gbs_whole_token_per_gpu": per_gpu / 1e9 / (ms / K / 1e3),
         "frac_of_peak_whole_token": per_gpu / 1e9 / (ms / K / 1e3) / peak, "tp_mode": {0: None, 1: "ncclAllReduce between kernels", 2: "all-reduce inside k_matres over peer memory"}[L.calm_b200_tp_mode()],
     }
+    if world == 1 and not spec.n_experts:
+        # ---- the prompt pass (configs[2]: "2048-token prefill"): forward_prefill_cuda, tcgen05 GEMMs; timed with CUDA events on the library's stream
+        try:
+            n_pf = min(2048, seq_len)
+            ptoks = np.array(mg.teacher_tokens(spec.vocab_size, n_pf), np.int32)
+            served = dm.prefill(ptoks[:256], 0)  # warm-up: buffers, tensor maps, attributes
+            torch.cuda.synchronize()
+            L.calm_b200_timer_start()
+            dm.prefill(ptoks, 0)
+            pf_ms = L.calm_b200_timer_stop()
+            mm_params = spec.n_layers * ((spec.q_dim + 2 * spec.kv_dim) * spec.dim + spec.dim * spec.q_dim + 3 * spec.hidden_dim * spec.dim)
+            flops = 2.0 * n_pf * mm_params + 2.0 * 2.0 * spec.n_layers * spec.q_dim * n_pf * (n_pf + 1) / 2
+            tf = flops / (pf_ms / 1e3) / 1e12
+            try:
+                tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+            except Exception:
+                tpeak = 1400.0
+            prefill = {"tokens": n_pf, "ms": pf_ms, "tok_s": n_pf / (pf_ms / 1e3), "tflops": tf, "frac_of_bf16_sustained": tf / tpeak,
+                       "path": "tcgen05 GEMMs (f16 hi + lo activations: two MMAs per k-step) + block-causal attention" if served else "fed token by token (shape not served by the batched pass)",
+                       "vs_serial_prompt": (n_pf / (pf_ms / 1e3)) / value}
+        except Exception as e:
+            prefill = {"unavailable": str(e)}
+        out["prefill"] = prefill
     dm.close()
 
     if rank == 0 and world == 1 and not args.no_ref_cuda and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcalm_ref_cuda.so")):

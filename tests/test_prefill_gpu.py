@@ -50,8 +50,10 @@ def _check(spec, serial, batched, kvbits, label):
     assert err <= tol * sigma
     for (ks, vs), (kb, vb) in zip(kvs, kvb):
         if kvbits == 16:
-            np.testing.assert_allclose(kb, ks, rtol=KV_RTOL, atol=KV_ATOL)
-            np.testing.assert_allclose(vb, vs, rtol=KV_RTOL, atol=KV_ATOL)
+            # entries are fp16 roundings of sums whose noise scales with the vector, not with the entry: two orders of summation may land
+            # one fp16 ulp of the LARGEST entries apart on a small entry of a deeper layer (KV_ATOL was sized for sigma ~ 0.3 models)
+            np.testing.assert_allclose(kb, ks, rtol=KV_RTOL, atol=max(KV_ATOL, 5e-4 * float(np.abs(ks).max())))
+            np.testing.assert_allclose(vb, vs, rtol=KV_RTOL, atol=max(KV_ATOL, 5e-4 * float(np.abs(vs).max())))
         else:  # e5m2 entries: equal or neighbouring values
             for a, b in ((kb, ks), (vb, vs)):
                 assert (np.abs(a - b) <= 0.26 * np.maximum(np.abs(a), np.abs(b)) + 2e-5).all() and (a == b).mean() > 0.95
