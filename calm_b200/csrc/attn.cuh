@@ -157,91 +157,114 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	}
 	float mh = -FLT_MAX, lh = 0.f; // running max / sum of THIS lane's head (li / P)
 
-	for (int s0 = (warp * G + grp) * P; s0 - grp * P < nslots; s0 += NW * G * P) { // warp-uniform trip count (full-warp shuffles inside)
-		const bool inr = s0 < nslots;
-		const int j = inr ? s0 / ATTN2_BP : 0, o = s0 % ATTN2_BP;
-		const int t0 = (split + j * nsplit) * ATTN2_BP + o;
-		if (inr) mbar_wait(&bars[j], 0);
-		if (s0 == 0) ATTN_DBG(3);
-		raw_t kr[P], vr[P];
-		bool ok[P];
+	// Steps are taken SC at a time: first ALL scores of the chunk (independent dot products and transposing reductions: no
+	// serial softmax state between them), then one max / exp / sum for the chunk, then the value pass.  With 8 warps per SM
+	// the per-step online softmax was a latency chain (5 us for 4 steps on the in-kernel timeline); this form rescales the
+	// accumulators once per chunk.
+	constexpr int SC = 4, STEP = NW * G * P;
+	const int gbase = grp * LPP;
+	auto slot_of = [&](int s0, int& j, int& o, int& t0) {
+		j = s0 / ATTN2_BP, o = s0 % ATTN2_BP;
+		t0 = (split + j * nsplit) * ATTN2_BP + o;
+	};
+	for (int sb = (warp * G + grp) * P; sb - grp * P < nslots; sb += SC * STEP) { // warp-uniform trip count (full-warp shuffles inside)
+		float sc[SC];
+		bool val[SC];
 #pragma unroll
-		for (int i = 0; i < P; ++i) {
-			const int t = t0 + i;
-			ok[i] = inr && t < kv_len;
-			if (ok[i]) {
-				if (t == kv_pos || t < kv_sink) { // written during this token (k_qkv / k_embed): not in the early copy
-					kr[i] = KvRaw<KVT>::load(kglob + (size_t)t * HD + li * 8);
-					vr[i] = KvRaw<KVT>::load(vglob + (size_t)t * HD + li * 8);
-				} else {
-					kr[i] = *reinterpret_cast<const raw_t*>(Ks + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
-					vr[i] = *reinterpret_cast<const raw_t*>(Vs + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
-				}
-			} else {
-				kr[i] = KvRaw<KVT>::zero(), vr[i] = KvRaw<KVT>::zero();
-			}
-		}
-		// partial dot products of this lane's 8 dims: combo c = h * P + i
-		float part[NC];
-		{
-			float kf[P][8];
-#pragma unroll
-			for (int i = 0; i < P; ++i) KvRaw<KVT>::unpack(kr[i], kf[i]);
-#pragma unroll
-			for (int h = 0; h < HG; ++h) {
-				const float4 q0 = *reinterpret_cast<const float4*>(qs + h * HD + li * 8), q1 = *reinterpret_cast<const float4*>(qs + h * HD + li * 8 + 4);
+		for (int c = 0; c < SC; ++c) {
+			const int s0 = sb + c * STEP;
+			const bool inr = s0 < nslots;
+			int j = 0, o = 0, t0 = 0;
+			if (inr) slot_of(s0, j, o, t0);
+			if (inr) mbar_wait(&bars[j], 0);
+			if (s0 == 0) ATTN_DBG(3);
+			float part[NC]; // combo h * P + i: partial dot product of this lane's 8 dims
+			{
+				float kf[P][8];
 #pragma unroll
 				for (int i = 0; i < P; ++i) {
-					float d = q0.x * kf[i][0];
-					d = fmaf(q0.y, kf[i][1], d), d = fmaf(q0.z, kf[i][2], d), d = fmaf(q0.w, kf[i][3], d);
-					d = fmaf(q1.x, kf[i][4], d), d = fmaf(q1.y, kf[i][5], d), d = fmaf(q1.z, kf[i][6], d), d = fmaf(q1.w, kf[i][7], d);
-					part[h * P + i] = d;
+					const int t = t0 + i;
+					raw_t kr = KvRaw<KVT>::zero();
+					if (inr && t < kv_len)
+						kr = (t == kv_pos || t < kv_sink) ? KvRaw<KVT>::load(kglob + (size_t)t * HD + li * 8) // written during this token: not in the early copy
+						                                  : *reinterpret_cast<const raw_t*>(Ks + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
+					KvRaw<KVT>::unpack(kr, kf[i]);
+				}
+#pragma unroll
+				for (int h = 0; h < HG; ++h) {
+					const float4 q0 = *reinterpret_cast<const float4*>(qs + h * HD + li * 8), q1 = *reinterpret_cast<const float4*>(qs + h * HD + li * 8 + 4);
+#pragma unroll
+					for (int i = 0; i < P; ++i) {
+						float d = q0.x * kf[i][0];
+						d = fmaf(q0.y, kf[i][1], d), d = fmaf(q0.z, kf[i][2], d), d = fmaf(q0.w, kf[i][3], d);
+						d = fmaf(q1.x, kf[i][4], d), d = fmaf(q1.y, kf[i][5], d), d = fmaf(q1.z, kf[i][6], d), d = fmaf(q1.w, kf[i][7], d);
+						part[h * P + i] = d;
+					}
 				}
 			}
-		}
-		// transposing reduction over the LPP lanes of the group: after the step with stride s a lane keeps the half selected by bit s
+			// transposing reduction over the LPP lanes of the group: after the step with stride s a lane keeps the half selected by bit s
 #pragma unroll
-		for (int s_ = NC / 2; s_ >= 1; s_ >>= 1) {
-			const bool up = li & s_;
+			for (int s_ = NC / 2; s_ >= 1; s_ >>= 1) {
+				const bool up = li & s_;
 #pragma unroll
-			for (int k = 0; k < s_; ++k) {
-				float send = up ? part[k] : part[k + s_];
-				float recv = __shfl_xor_sync(0xffffffffu, send, s_);
-				part[k] = (up ? part[k + s_] : part[k]) + recv;
+				for (int k = 0; k < s_; ++k) {
+					float send = up ? part[k] : part[k + s_];
+					float recv = __shfl_xor_sync(0xffffffffu, send, s_);
+					part[k] = (up ? part[k + s_] : part[k]) + recv;
+				}
 			}
+			// lane li owns combo li: head li / P, position li % P
+			val[c] = inr && (t0 + li % P) < kv_len;
+			sc[c] = val[c] ? part[0] * a.inv_sqrt_hd : -FLT_MAX;
 		}
-		// lane li owns combo li: head li / P, position li % P
-		bool valid = false;
+		float gmax = sc[0];
 #pragma unroll
-		for (int i = 0; i < P; ++i) valid = (li % P == i) ? ok[i] : valid;
-		const float sc = valid ? part[0] * a.inv_sqrt_hd : -FLT_MAX;
-		float gmax = sc;
+		for (int c = 1; c < SC; ++c) gmax = fmaxf(gmax, sc[c]);
 #pragma unroll
 		for (int o2 = 1; o2 < P; o2 <<= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o2));
 		const float mnew = fmaxf(mh, gmax);
 		const float corr = __expf(mh - mnew);
-		const float pr = valid ? __expf(sc - mnew) : 0.f;
-		float ps = pr;
+		float pr[SC], ps = 0.f;
+#pragma unroll
+		for (int c = 0; c < SC; ++c) pr[c] = val[c] ? __expf(sc[c] - mnew) : 0.f, ps += pr[c];
 #pragma unroll
 		for (int o2 = 1; o2 < P; o2 <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o2);
 		lh = fmaf(lh, corr, ps);
 		mh = mnew;
-		const int gbase = grp * LPP;
-		float vf[P][8];
-#pragma unroll
-		for (int i = 0; i < P; ++i) KvRaw<KVT>::unpack(vr[i], vf[i]);
 #pragma unroll
 		for (int h = 0; h < HG; ++h) {
 			const float ch = __shfl_sync(0xffffffffu, corr, gbase + h * P);
-			float pw[P];
 #pragma unroll
-			for (int i = 0; i < P; ++i) pw[i] = __shfl_sync(0xffffffffu, pr, gbase + h * P + i);
+			for (int e = 0; e < 8; ++e) acc[h][e] *= ch;
+		}
 #pragma unroll
-			for (int e = 0; e < 8; ++e) {
-				float v = acc[h][e] * ch;
+		for (int c = 0; c < SC; ++c) {
+			const int s0 = sb + c * STEP;
+			const bool inr = s0 < nslots;
+			int j = 0, o = 0, t0 = 0;
+			if (inr) slot_of(s0, j, o, t0);
+			float vf[P][8];
 #pragma unroll
-				for (int i = 0; i < P; ++i) v = fmaf(pw[i], vf[i][e], v);
-				acc[h][e] = v;
+			for (int i = 0; i < P; ++i) {
+				const int t = t0 + i;
+				raw_t vr = KvRaw<KVT>::zero();
+				if (inr && t < kv_len)
+					vr = (t == kv_pos || t < kv_sink) ? KvRaw<KVT>::load(vglob + (size_t)t * HD + li * 8)
+					                                  : *reinterpret_cast<const raw_t*>(Vs + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
+				KvRaw<KVT>::unpack(vr, vf[i]);
+			}
+#pragma unroll
+			for (int h = 0; h < HG; ++h) {
+				float pw[P];
+#pragma unroll
+				for (int i = 0; i < P; ++i) pw[i] = __shfl_sync(0xffffffffu, pr[c], gbase + h * P + i);
+#pragma unroll
+				for (int e = 0; e < 8; ++e) {
+					float v = acc[h][e];
+#pragma unroll
+					for (int i = 0; i < P; ++i) v = fmaf(pw[i], vf[i][e], v);
+					acc[h][e] = v;
+				}
 			}
 		}
 	}
