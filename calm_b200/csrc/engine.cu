@@ -18,6 +18,7 @@
 #include "attn.cuh"
 #include "ring.cuh"
 #include "prefill.cuh"
+#include "ring_gf4.cuh"
 
 namespace {
 
@@ -63,6 +64,10 @@ struct Engine {
 	int ring_up_u = 0, ring_wo_u = 0, ring_down_u = 0, ring_wo_s = 1, ring_down_s = 1;
 	int grid_up_ring = 0, grid_wo_ring = 0, grid_down_ring = 0;
 	size_t smem_up_ring = 0, smem_wo_ring = 0, smem_down_ring = 0;
+	// gf4: ring-fed tensor-core stages (ring_gf4.cuh): K-slice chunks per task (0: stage not served), tiles per CTA, grids, shared memory
+	int g4_up_s = 0, g4_wo_s = 0, g4_down_s = 0, g4_up_tpc = 0, g4_wo_tpc = 0, g4_down_tpc = 0;
+	int grid_up_g4 = 0, grid_wo_g4 = 0, grid_down_g4 = 0;
+	size_t smem_up_g4 = 0, smem_wo_g4 = 0, smem_down_g4 = 0;
 	bool attn2_cluster = false; // ... with the CTAs of a unit as one thread-block cluster (slices folded through distributed shared memory)
 	bool attn2 = false; // k_attn2 (attn.cuh): KV slice requested into shared memory ahead of the dependency wait
 	int attn_nbmax = 0;
@@ -586,7 +591,8 @@ int run_token(int mode) {
 			if (dense && g.pf_wo_up) pf_up_prefix(a.pf, 0, w.w1[l], w.w3[l], g.pf_attn_up, g.pf_wo_up, up_bytes);
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l); // partial over this rank's heads, summed over the ranks in the kernel
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			if (g.ring_wo_u) ring_res_dispatch<DBITS>(a, g.ring_wo_u, g.ring_wo_s, g.grid_wo_ring, g.smem_wo_ring, false);
+			if (g.g4_wo_s) launch_pdl(k_matres_g4<3>, g.grid_wo_g4, G4_WARPS * 32, g.smem_wo_g4, a, g.g4_wo_s, g.g4_wo_tpc);
+			else if (g.ring_wo_u) ring_res_dispatch<DBITS>(a, g.ring_wo_u, g.ring_wo_s, g.grid_wo_ring, g.smem_wo_ring, false);
 			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
@@ -607,7 +613,8 @@ int run_token(int mode) {
 			a.stamp = t.slot;
 			if (dense && g.pf_up_down) a.pf.p[0] = w.w2[l], a.pf.bytes[0] = (g.pf_up_down < down_bytes ? g.pf_up_down : down_bytes) & ~(size_t)15;
 			bool done = false;
-			if (g.ring_up_u) ring_up_dispatch<DBITS>(a, false), done = true;
+			if (g.g4_up_s) launch_pdl(k_ffn_up_g4<2>, g.grid_up_g4, G4_WARPS * 32, g.smem_up_g4, a, g.g4_up_s, g.g4_up_tpc), done = true;
+			if (!done && g.ring_up_u) ring_up_dispatch<DBITS>(a, false), done = true;
 			if constexpr (DBITS != 4) {
 				if (!done && g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
 			}
@@ -626,7 +633,8 @@ int run_token(int mode) {
 			}
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			if (g.ring_down_u) ring_res_dispatch<DBITS>(a, g.ring_down_u, g.ring_down_s, g.grid_down_ring, g.smem_down_ring, false);
+			if (g.g4_down_s) launch_pdl(k_matres_g4<3>, g.grid_down_g4, G4_WARPS * 32, g.smem_down_g4, a, g.g4_down_s, g.g4_down_tpc);
+			else if (g.ring_down_u) ring_res_dispatch<DBITS>(a, g.ring_down_u, g.ring_down_s, g.grid_down_ring, g.smem_down_ring, false);
 			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
@@ -817,6 +825,31 @@ void make_plan() {
 		}
 		g.ring_wo_u = uw, g.ring_wo_s = sw, g.grid_wo_ring = gw, g.smem_wo_ring = mw;
 		g.ring_down_u = ud, g.ring_down_s = sd, g.grid_down_ring = gd, g.smem_down_ring = md;
+	}
+	// gf4: the tensor-core ring kernels (ring_gf4.cuh) take FFN up, wo and w2 of dense single-GPU models whose rows are whole 256-byte chunks
+	g.g4_up_s = g.g4_wo_s = g.g4_down_s = 0;
+	if constexpr (DBITS == 4) {
+		const bool on = c.n_experts == 0 && g.tp_world == 1 && !(getenv("CALM_B200_GF4_MMA") && atoi(getenv("CALM_B200_GF4_MMA")) == 0);
+		auto plan = [&](int n, int tiles, int ns, int cps, int& s_out, int& tpc_out, int& grid_out, size_t& smem_out) {
+			if (!on || (n / 2) % G4_CH || n > 16384 || tiles < 1) return;
+			const int cpt = n / 2 / G4_CH;
+			const int grid = imin(g.sms * cps, tiles);
+			int S = 1;
+			if (cpt % 2 == 0 && (long long)tiles * (cpt / 2) >= 32LL * g.sms) S = 2; // halve the fold traffic when there are tasks to spare
+			while (cpt / S > G4_MAX_SL && cpt % (S * 2) == 0) S *= 2;
+			if (cpt % S || cpt / S > G4_MAX_SL) return;
+			const int tpc = cdiv(tiles, grid) + 1;
+			const size_t smem = g4_smem_bytes(n, ns, tpc, cpt / S);
+			if (smem > 220 * 1024 / cps) return;
+			s_out = S, tpc_out = tpc, grid_out = grid, smem_out = smem;
+		};
+		if (c.hidden_dim % 8 == 0) plan(c.dim, c.hidden_dim / 8, 2, 2, g.g4_up_s, g.g4_up_tpc, g.grid_up_g4, g.smem_up_g4);
+		if (c.dim % 16 == 0) {
+			plan(g.q_dim, c.dim / 16, 3, 1, g.g4_wo_s, g.g4_wo_tpc, g.grid_wo_g4, g.smem_wo_g4);
+			plan(c.hidden_dim, c.dim / 16, 3, 1, g.g4_down_s, g.g4_down_tpc, g.grid_down_g4, g.smem_down_g4);
+		}
+		if (g.g4_up_s) smem_optin(k_ffn_up_g4<2>, g.smem_up_g4);
+		if (g.g4_wo_s || g.g4_down_s) smem_optin(k_matres_g4<3>, g.smem_wo_g4 > g.smem_down_g4 ? g.smem_wo_g4 : g.smem_down_g4);
 	}
 	g.out_row0 = 0, g.out_row1 = c.vocab_size;
 	if (g.tp_fused) { // vocabulary split: equal slices of whole 32-row CTA iterations (the last rank's may be short)

@@ -109,6 +109,27 @@ def test_fp8_kv_cache_teacher_forced_vs_oracle(oracle_pkg, name):
     assert np.abs(got - ref).max() <= 4 * TOL8_SIGMA * ref.std()
 
 
+@pytest.mark.parametrize("dtype", ["gf4", "fp8", "fp16"])
+def test_ring_fed_kernels_vs_oracle(oracle_pkg, dtype):
+    """Shapes the ring-fed stage kernels serve (rows of whole 1 KB / 256-byte chunks: ring.cuh, and for gf4 the tensor-core
+    ring kernels of ring_gf4.cuh with K-slices folded in shared memory) against the CPU oracle, teacher-forced."""
+    spec = replace(mg.SPECS["pf-tiny-hd128"], name="ring-" + dtype, dtype=dtype, dim=1024, hidden_dim=4096, n_heads=8, n_kv_heads=2, n_layers=2)
+    toks = mg.teacher_tokens(spec.vocab_size, 20)
+    host = mg.HostModel(spec, seed=7)
+    ck = oracle_pkg.Checker("port")
+    ref = oracle_pkg.teacher_forced(ck, host, toks)
+    with lib.DeviceModel(spec, host.tensors) as dm:
+        got = np.stack([dm.forward(t, i) for i, t in enumerate(toks)])
+    ck.release(host)
+    sigma = float(ref.std())
+    err = float(np.abs(got - ref).max())
+    print(f"ring-fed {dtype}: |cuda-oracle| {err:.2e} = {err / sigma:.1e} sigma")
+    assert err <= TOL_SIGMA * sigma
+    srt = np.sort(ref, 1)
+    safe = (srt[:, -1] - srt[:, -2]) > 2 * TOL_SIGMA * sigma
+    assert (got.argmax(1)[safe] == ref.argmax(1)[safe]).all()
+
+
 def _ref_cuda(tmp_path, args):
     out = str(tmp_path / "ref.npz")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_cuda_worker.py"), "--out", out] + args, capture_output=True, text=True, timeout=900,
