@@ -153,3 +153,43 @@ def test_calm_file_loads_in_reference_driver(tmp_path, oracle_pkg):
         pos += 1
     expect = "".join(f"<|t{t}|>" for t in gen)
     assert expect in r.stdout, (expect, r.stdout)
+
+
+def test_oracle_e5m2_cache_rounding_is_bit_exact(oracle_pkg):
+    """oracle_round_e5m2 (the fp8 KV cache of reference infer.cu:476-481, __nv_fp8_e5m2(float): round to nearest even,
+    saturate to the largest finite value) against torch's float8_e5m2 cast over normals, subnormals and ties."""
+    import ctypes as C
+
+    L = oracle_pkg.Checker("port").lib
+    L.oracle_round_e5m2.argtypes, L.oracle_round_e5m2.restype = [C.c_float], C.c_float
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(4000).astype(np.float32) * s for s in (1e-6, 1e-4, 1e-2, 1, 100, 1e4)] +
+                       [np.array([0, -0.0, 57344, 57343.9, 2 ** -17, 2 ** -16 * 1.5, 2 ** -16 * 2.5, 1.25, 1.375, 1.5, -3.5], np.float32)])
+    ref = torch.from_numpy(x).to(torch.float8_e5m2).to(torch.float32).numpy()
+    got = np.array([L.oracle_round_e5m2(float(v)) for v in x], np.float32)
+    assert np.array_equal(got, ref)
+    assert L.oracle_round_e5m2(1e9) == 57344.0 and L.oracle_round_e5m2(-6e4) == -57344.0  # SATFINITE, where torch would give inf
+
+
+def test_oracle_fp8_cache_mode_changes_only_the_cache(oracle_pkg):
+    """kvbits == 8 in the oracle: same path, cache entries are e5m2 values; logits stay close to the fp16-cache run."""
+    spec = mg.SPECS["tiny-fp8"]
+    toks = mg.teacher_tokens(spec.vocab_size, 12)
+    out = {}
+    for kvbits in (16, 8):
+        model = mg.HostModel(spec, seed=0, kvbits=kvbits)
+        ck = oracle_pkg.Checker("port")
+        out[kvbits] = oracle_pkg.teacher_forced(ck, model, toks)
+        k, v = ck.read_kv(model, 1, 5)
+        if kvbits == 8:
+            for a in (k, v):
+                assert np.array_equal(torch.from_numpy(a).to(torch.float8_e5m2).to(torch.float32).numpy(), a)
+        ck.release(model)
+    assert 0 < np.abs(out[8] - out[16]).max() < 0.5 * out[16].std()  # 2 mantissa bits per cache entry: visibly coarser, still the same function
+
+
+def test_kv_fill_pattern_is_deterministic_and_bounded():
+    a1, b1 = mg.kv_fill_pattern(3, 17, 32, seed=5)
+    a2, b2 = mg.kv_fill_pattern(3, 17, 32, seed=5)
+    assert np.array_equal(a1, a2) and np.array_equal(b1, b2) and a1.shape == (3, 17, 32)
+    assert np.abs(a1).max() < 1 and np.abs(b1).max() < 1 and abs(float(a1.mean())) < 0.05 and not np.array_equal(a1, b1)
