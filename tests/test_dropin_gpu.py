@@ -55,3 +55,19 @@ def test_reference_driver_with_our_backend(tmp_path, oracle_pkg, name):
     # the driver prints the prompt tokens after BOS, then the generated ones
     assert got[:2] == [7, 8]
     assert got[2:2 + len(gen)] == gen[:len(got) - 2]
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/run_b200 did not travel (needs /root/reference at build time)")
+def test_perf_table_through_the_reference_driver(tmp_path):
+    """CALM_B200_PERF=1: the unmodified reference driver, linked to our backend, ends with perf_cuda()'s per-stage table (the
+    reference prints its own under a CUPTI injection, run.c:630-632, infer.cu:761-801); timings come from inside the production graph."""
+    spec = mg.SPECS["tiny-llama"]
+    model = mg.HostModel(spec, seed=0)
+    path = str(tmp_path / "m.calm")
+    mg.write_calm(path, spec, model.tensors)
+    env = dict(os.environ, OMP_NUM_THREADS="2", CALM_B200_PERF="1")
+    r = subprocess.run([EXE, path, "-n", "16", "-t", "0", "-i", "<|t7|>"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    assert "forward breakdown" in r.stdout and "matmul_ffn_up" in r.stdout and "GB/s" in r.stdout, r.stdout[-600:]
+    rows = re.findall(r"\[(\d)\]\s+(\w+):\s+([0-9.]+)%;\s+([0-9.]+) usec/run", r.stdout)
+    assert len(rows) >= 5 and abs(sum(float(x[2]) for x in rows) - 100.0) < 1.0
