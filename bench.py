@@ -212,7 +212,7 @@ def run_reference_arm(args, spec):
     tps, kind, threads, done = cpu_tokens_per_s(spec, args.seed, args.steps, min(args.warmup, 4), pos0, budget_s=150.0)
     out = {
         "impl": "reference", "metric": "tok/s single-batch decode", "value": tps, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / tps, "higher_is_better": True, "scaling": "strong" if (args.parallel == "tp" and args.gpus > 1) else "weak", "vs_baseline": None, "dtype": "f32 (fp8 e5m2 weights)",
+        "warmup": args.warmup, "ms_per_step": 1e3 / tps, "higher_is_better": True, "scaling": "strong" if (args.parallel == "tp" and args.gpus > 1) else "weak", "vs_baseline": None, "dtype": f"f32 ({spec.dtype} weights)",
         "data": "synthetic", "config": workload_config(spec, pos0, args),
         "cpu_baseline": {"value": tps, "unit": "tok/s", "cores": threads, "kind": kind,
                          "sample": f"{done} of {args.steps} steps (tokens) timed at pos {pos0 + min(args.warmup, 4)}.. of the same model, 150 s bound, all {threads} host threads"},
