@@ -121,6 +121,8 @@ struct Engine {
 	bool use_pdl = true;
 	int carveout = -1;   // cudaFuncAttributePreferredSharedMemoryCarveout applied to every kernel of the token, or -1
 	bool mma_up = false; // FFN-up on the tensor cores (k_ffn_up_mma)
+	bool mma_res_wo = false, mma_res_down = false; // wo / w2 on the tensor cores (k_matres_mma; gf4)
+	int grid_wo_mma = 0, grid_down_mma = 0;
 	int* tile_ctr = nullptr; // [n_layers] dynamic tile counters of k_ffn_up_mma (zeroed by k_embed every token)
 	int grid_up_mma = 0;
 	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + k_ffn_up with 8 KB in flight per warp
@@ -199,6 +201,11 @@ int cdiv(int a, int b) { return (a + b - 1) / b; }
 int balanced_grid(int units, int cap) {
 	if (units <= cap) return units < 1 ? 1 : units;
 	return cdiv(units, cdiv(units, cap));
+}
+
+// shared memory of the tensor-core matvec kernels: 32 floats + the activation vector as f16 hi / lo pairs
+inline size_t xs_bytes_h(int n) {
+	return (size_t)(32 + n) * sizeof(float);
 }
 
 template <int DBITS>
@@ -544,7 +551,7 @@ int run_token(int mode) {
 		EmbedArgs<KVT> a = {};
 		a.x = g.x, a.table = w.token_embedding_table, a.tp = g.tp, a.dim = dim;
 		a.embed_blocks = cdiv(dim, 256);
-		a.tile_ctr = g.tile_ctr, a.n_ctr = c.n_layers;
+		a.tile_ctr = g.tile_ctr, a.n_ctr = 3 * c.n_layers; // [l] FFN up, [L + l] wo, [2L + l] w2
 		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq, a.rope_cs = g.rope_cs;
 		a.n_layers = c.n_layers, a.n_kv_heads = c.n_kv_heads, a.head_dim = hd, a.seq_len = c.seq_len;
 		a.stamp = nullptr, a.stamp_reset = g.perf ? g.stamps : nullptr, a.n_stamps = MAX_STAMPS + 8; // + the 16 debug stamps
@@ -591,7 +598,8 @@ int run_token(int mode) {
 			if (dense && g.pf_wo_up) pf_up_prefix(a.pf, 0, w.w1[l], w.w3[l], g.pf_attn_up, g.pf_wo_up, up_bytes);
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l); // partial over this rank's heads, summed over the ranks in the kernel
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			if (g.g4_wo_s) launch_pdl(k_matres_g4<3>, g.grid_wo_g4, G4_WARPS * 32, g.smem_wo_g4, a, g.g4_wo_s, g.g4_wo_tpc);
+			if (g.mma_res_wo) launch_pdl(k_matres_mma<DBITS>, g.grid_wo_mma, 256, xs_bytes_h(g.q_dim), a, g.tile_ctr ? g.tile_ctr + c.n_layers + l : (int*)nullptr);
+			else if (g.g4_wo_s) launch_pdl(k_matres_g4<3>, g.grid_wo_g4, G4_WARPS * 32, g.smem_wo_g4, a, g.g4_wo_s, g.g4_wo_tpc);
 			else if (g.ring_wo_u) ring_res_dispatch<DBITS>(a, g.ring_wo_u, g.ring_wo_s, g.grid_wo_ring, g.smem_wo_ring, false);
 			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
@@ -615,9 +623,7 @@ int run_token(int mode) {
 			bool done = false;
 			if (g.g4_up_s) launch_pdl(k_ffn_up_g4<2>, g.grid_up_g4, G4_WARPS * 32, g.smem_up_g4, a, g.g4_up_s, g.g4_up_tpc), done = true;
 			if (!done && g.ring_up_u) ring_up_dispatch<DBITS>(a, false), done = true;
-			if constexpr (DBITS != 4) {
-				if (!done && g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
-			}
+			if (!done && g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
 			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, 256, g.smem_dim, a);
 			++nl;
 		}
@@ -633,7 +639,8 @@ int run_token(int mode) {
 			}
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			if (g.g4_down_s) launch_pdl(k_matres_g4<3>, g.grid_down_g4, G4_WARPS * 32, g.smem_down_g4, a, g.g4_down_s, g.g4_down_tpc);
+			if (g.mma_res_down) launch_pdl(k_matres_mma<DBITS>, g.grid_down_mma, 256, xs_bytes_h(c.hidden_dim), a, g.tile_ctr ? g.tile_ctr + 2 * c.n_layers + l : (int*)nullptr);
+			else if (g.g4_down_s) launch_pdl(k_matres_g4<3>, g.grid_down_g4, G4_WARPS * 32, g.smem_down_g4, a, g.g4_down_s, g.g4_down_tpc);
 			else if (g.ring_down_u) ring_res_dispatch<DBITS>(a, g.ring_down_u, g.ring_down_s, g.grid_down_ring, g.smem_down_ring, false);
 			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
@@ -770,14 +777,24 @@ void make_plan() {
 	}
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
 	g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
-	g.mma_up = false;
-	if constexpr (DBITS != 4) { // tensor-core FFN-up (stages.cuh k_ffn_up_mma): dense, whole k-blocks per warp
-		// measured (profiles/README.md): +2.6 % tokens/s with fp16 weights, -1 % with fp8, so it is on by default for fp16 only
-		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : DBITS == 16;
+	g.mma_up = g.mma_res_wo = g.mma_res_down = false;
+	{ // tensor-core matvec stages (stages.cuh k_ffn_up_mma / k_matres_mma): dense, whole k-blocks per warp
+		// measured (profiles/README.md): +2.6 % tokens/s with fp16 weights, -1 % with fp8 (round 1); gf4 is issue-bound in SIMT, so it is the default there
+		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : (DBITS == 16 || DBITS == 4);
 		if (want && c.n_experts == 0 && c.dim % (32 * WFmt<DBITS>::VW) == 0 && c.hidden_dim % 8 == 0 && c.dim <= 16384) {
 			g.mma_up = true;
 			smem_optin(k_ffn_up_mma<DBITS>, g.smem_dim);
 			g.grid_up_mma = imin(max_ctas(k_ffn_up_mma<DBITS>, 256, g.smem_dim), c.hidden_dim / 8);
+		}
+		if (DBITS == 4 && want && c.n_experts == 0 && g.tp_world == 1 && c.dim % 16 == 0) {
+			auto ok = [&](int n) { return n % (4 * WFmt<DBITS>::VW) == 0 && n <= 16384; };
+			const size_t smax = xs_bytes_h(g.q_dim > c.hidden_dim ? g.q_dim : c.hidden_dim);
+			if (ok(g.q_dim) && ok(c.hidden_dim) && smax <= 200 * 1024) {
+				smem_optin(k_matres_mma<DBITS>, smax);
+				g.mma_res_wo = g.mma_res_down = true;
+				g.grid_wo_mma = imin(max_ctas(k_matres_mma<DBITS>, 256, xs_bytes_h(g.q_dim)), c.dim / 16);
+				g.grid_down_mma = imin(max_ctas(k_matres_mma<DBITS>, 256, xs_bytes_h(c.hidden_dim)), c.dim / 16);
+			}
 		}
 	}
 	// TMA-ring kernels for the dense single-GPU stages whose rows are whole 1 KB / 2 KB chunks (ring.cuh)
@@ -829,7 +846,8 @@ void make_plan() {
 	// gf4: the tensor-core ring kernels (ring_gf4.cuh) take FFN up, wo and w2 of dense single-GPU models whose rows are whole 256-byte chunks
 	g.g4_up_s = g.g4_wo_s = g.g4_down_s = 0;
 	if constexpr (DBITS == 4) {
-		const bool on = c.n_experts == 0 && g.tp_world == 1 && !(getenv("CALM_B200_GF4_MMA") && atoi(getenv("CALM_B200_GF4_MMA")) == 0);
+		// (measured slower than both alternatives: 16 bulk copies of 256 bytes per chunk starve the ring -- profiles/r02_sweep_gf4_ring_mma_m16n8k8.jsonl; selectable)
+		const bool on = c.n_experts == 0 && g.tp_world == 1 && getenv("CALM_B200_GF4_RING") && atoi(getenv("CALM_B200_GF4_RING")) != 0;
 		auto plan = [&](int n, int tiles, int ns, int cps, int& s_out, int& tpc_out, int& grid_out, size_t& smem_out) {
 			if (!on || (n / 2) % G4_CH || n > 16384 || tiles < 1) return;
 			const int cpt = n / 2 / G4_CH;
@@ -1102,8 +1120,8 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.out_tokens_cap = 1 << 16;
 	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
 	if (!(getenv("CALM_B200_MMA_STATIC") && atoi(getenv("CALM_B200_MMA_STATIC")))) {
-		g.tile_ctr = (int*)dev_alloc(MAX_LAYERS * sizeof(int));
-		CUDA_CHECK(cudaMemset(g.tile_ctr, 0, MAX_LAYERS * sizeof(int)));
+		g.tile_ctr = (int*)dev_alloc(3 * MAX_LAYERS * sizeof(int));
+		CUDA_CHECK(cudaMemset(g.tile_ctr, 0, 3 * MAX_LAYERS * sizeof(int)));
 	}
 	g.sample_chunks = cdiv(c.vocab_size, SAMPLE_CHUNK);
 	g.sample_state = (SampleState*)dev_alloc(sizeof(SampleState));

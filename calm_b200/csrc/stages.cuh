@@ -1125,6 +1125,31 @@ __device__ __forceinline__ void mma_kblock(float (&d0)[4], float (&d1)[4], const
 			else
 				mma_16816(d0, a0, a1, a2, a3, b.x, b.y);
 		}
+	} else if constexpr (DBITS == 4) { // gf4: 16 words = 128 weights per row and block; this lane's vector holds words 4t..4t+3 = weights 32t..32t+31: 8 k-steps
+		// A = (q - 4) * s as exact f16 (at most 6 significant bits); the -1/4 of the format (infer.c:37-40) is applied to the sum by the caller
+		const uint2* bp = B + kb * 32 + 8 * t;
+		const __half2 k1028 = __half2half2(__ushort_as_half(0x6404));
+		auto pair = [&](uint32_t w, int p, __half2 sc) { // codes 2p, 2p+1 of word w
+			const uint32_t x = w >> (8 + 6 * p);
+			uint32_t h = (x & 7u) | ((x & 0x38u) << 13) | 0x64006400u; // f16 integers 1024 + q
+			const __half2 v = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h), k1028), sc);
+			return *reinterpret_cast<const uint32_t*>(&v);
+		};
+#pragma unroll
+		for (int j = 0; j < 4; ++j) { // word j of the vector: two k-steps
+			uint32_t sa = __byte_perm(wa[j], 0, 0x0404), sb = __byte_perm(wb[j], 0, 0x0404); // the e5m2 scale as an f16 pair
+			const __half2 sca = *reinterpret_cast<__half2*>(&sa), scb = *reinterpret_cast<__half2*>(&sb);
+#pragma unroll
+			for (int hh = 0; hh < 2; ++hh) {
+				const uint2 b = bp[2 * j + hh];
+				const uint32_t a0 = pair(wa[j], 2 * hh, sca), a2 = pair(wa[j], 2 * hh + 1, sca);
+				const uint32_t a1 = pair(wb[j], 2 * hh, scb), a3 = pair(wb[j], 2 * hh + 1, scb);
+				if (hh)
+					mma_16816(d1, a0, a1, a2, a3, b.x, b.y);
+				else
+					mma_16816(d0, a0, a1, a2, a3, b.x, b.y);
+			}
+		}
 	} else { // fp16: 32 weights per row and block: 2 k-steps
 		const uint2* bp = B + kb * 8 + 2 * t;
 #pragma unroll
@@ -1196,10 +1221,71 @@ __global__ void __launch_bounds__(256, 3) k_ffn_up_mma(const FfnUpArgs a) {
 			float u1 = 0.f, u3 = 0.f;
 #pragma unroll
 			for (int w = 0; w < 8; ++w) u1 += part[buf][w][threadIdx.x], u3 += part[buf][w][8 + threadIdx.x];
-			u1 *= out_scale, u3 *= out_scale;
+			u1 *= out_scale * (DBITS == 4 ? -0.25f : 1.f), u3 *= out_scale * (DBITS == 4 ? -0.25f : 1.f);
 			a.hb[ti * 8 + threadIdx.x] = (a.gelu ? act_gelu(u1) : act_silu(u1)) * u3;
 		}
 		ti = next_tile[buf]; // written before this iteration's barrier
+	}
+	stamp_end(a.stamp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_matres_mma: y[row] += W[row] . xin on the tensor cores, the k_ffn_up_mma scheme for wo / w2 (dense).  tile = 16 consecutive
+// rows (fragment rows g and g + 8); a CTA owns a tile, its 8 warps split k, tiles beyond the first round come from a counter.
+// Used for gf4, where SIMT decode is issue-bound (~3.3 slots per half-byte weight vs ~0.1 here).
+template <int DBITS>
+__global__ void __launch_bounds__(256, 2) k_matres_mma(const MatResArgs a, int* tile_ctr) {
+	pdl_launch_next();
+	extern __shared__ __align__(16) float smem[];
+	__shared__ float part[2][8][16];
+	__shared__ int next_tile[2];
+	float* red = smem;
+	uint2* H = reinterpret_cast<uint2*>(smem + 32);
+	uint2* Lo = H + a.n / 4;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+	const int rowvecs = a.n / WFmt<DBITS>::VW; // uint4 per row
+	const int nkb = rowvecs / 4;                // 64-byte k-blocks per row
+	const int kb_lo = (int)(((long long)warp * nkb) / 8), kb_hi = (int)(((long long)(warp + 1) * nkb) / 8);
+	const int ntiles = a.d / 16;
+	const uint4* w = reinterpret_cast<const uint4*>(a.w);
+	pdl_wait_prev();
+	stamp_begin(a.stamp);
+	float out_scale;
+	if (a.n / 4 <= (int)blockDim.x * 4) out_scale = stage_vector_h<4>(H, Lo, red, a.xin, a.n, nullptr, 0.f, false);
+	else out_scale = stage_vector_h_long(H, Lo, red, a.xin, a.n, nullptr, 0.f, false);
+	if (DBITS == 4) out_scale *= -0.25f;
+	const uint2* B = g == 1 ? Lo : H;
+	int buf = 0;
+	for (int ti = blockIdx.x; ti < ntiles; buf ^= 1) {
+		if (threadIdx.x == 0) next_tile[buf] = tile_ctr ? (int)gridDim.x + atomicAdd(tile_ctr, 1) : ti + (int)gridDim.x;
+		const uint4* ra = w + (size_t)(ti * 16 + g) * rowvecs + t;
+		const uint4* rb = w + (size_t)(ti * 16 + g + 8) * rowvecs + t;
+		float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+		for (int k0 = kb_lo; k0 < kb_hi; k0 += 4) {
+			uint4 va[4], vb[4];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				const bool in = k0 + u < kb_hi;
+				va[u] = in ? ldg_stream(ra + (size_t)(k0 + u) * 4) : make_uint4(0, 0, 0, 0);
+				vb[u] = in ? ldg_stream(rb + (size_t)(k0 + u) * 4) : make_uint4(0, 0, 0, 0);
+			}
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+				if (k0 + u < kb_hi) mma_kblock<DBITS>(d0, d1, va[u], vb[u], B, k0 + u, t);
+		}
+		if (t == 0) { // column 0 = w.hi, column 1 = w.lo
+			part[buf][warp][g] = (d0[0] + d1[0]) + (d0[1] + d1[1]);
+			part[buf][warp][8 + g] = (d0[2] + d1[2]) + (d0[3] + d1[3]);
+		}
+		__syncthreads(); // (one barrier per tile: the buffers alternate)
+		if (threadIdx.x < 16) {
+			float v = 0.f;
+#pragma unroll
+			for (int ww = 0; ww < 8; ++ww) v += part[buf][ww][threadIdx.x];
+			float* y = a.y + ti * 16 + threadIdx.x;
+			*y = (a.accumulate ? *y : 0.f) + v * out_scale;
+		}
+		ti = next_tile[buf];
 	}
 	stamp_end(a.stamp);
 }
