@@ -435,7 +435,7 @@ def dm_roofline(dm, L, spec, pos, peak, peak_src, ms_per_tok, bytes_per_tok):
     name, (ms, by, nl) = max(((k, v) for k, v in stats.items() if v[1] > 0), key=lambda kv: kv[1][0])
     achieved = by / 1e9 / (ms / 1e3) if ms > 0 else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch: not measurable in-run; the figure of the committed ncu capture is quoted with its source
-    traffic, traffic_src = (117.53e6 + 5.33e6, "profiles/r01_ncu_full_one_layer_staged.csv (k_ffn_up<8>, Llama-3-8B fp8)") if (name == "matmul_ffn_up" and spec.name == "llama3-8b-fp8") else (None, None)
+    traffic, traffic_src = (117.53e6 + 3.41e6, "profiles/r02_ncu_full_one_layer.csv (k_ffn_up_ring<8,4,2>, Llama-3-8B fp8: dram__bytes_read.sum + dram__bytes_write.sum of one launch)") if (name == "matmul_ffn_up" and spec.name == "llama3-8b-fp8") else (None, None)
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": by / max(nl, 1), "us_per_launch": ms / max(nl, 1) * 1e3,
             "timing": "in-kernel %globaltimer stamps, production graph", "token_span_us_profiled": span_ms * 1e3, "stages": table}
