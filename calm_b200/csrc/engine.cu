@@ -786,7 +786,8 @@ void make_plan() {
 			smem_optin(k_ffn_up_mma<DBITS>, g.smem_dim);
 			g.grid_up_mma = imin(max_ctas(k_ffn_up_mma<DBITS>, 256, g.smem_dim), c.hidden_dim / 8);
 		}
-		if (DBITS == 4 && want && c.n_experts == 0 && g.tp_world == 1 && c.dim % 16 == 0) {
+		const bool want_res = getenv("CALM_B200_MMA_RES") ? atoi(getenv("CALM_B200_MMA_RES")) != 0 : (DBITS == 4 && want);
+		if (want_res && c.n_experts == 0 && g.tp_world == 1 && c.dim % 16 == 0) {
 			auto ok = [&](int n) { return n % (4 * WFmt<DBITS>::VW) == 0 && n <= 16384; };
 			const size_t smax = xs_bytes_h(g.q_dim > c.hidden_dim ? g.q_dim : c.hidden_dim);
 			if (ok(g.q_dim) && ok(c.hidden_dim) && smax <= 200 * 1024) {
