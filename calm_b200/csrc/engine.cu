@@ -420,6 +420,11 @@ template <typename KVT, int HG, int LPP>
 void launch_attn2(const AttnArgs& a, int nunits, int* nl) {
 	if (!nl) { // prepare time: opt-ins, and whether the cluster form can be scheduled at all
 		smem_optin(k_attn2<KVT, HG, LPP, false>, g.attn2_smem);
+		{ // the cell fold polls its peers: the whole grid must fit on the device at once
+			int per_sm = 0;
+			CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_attn2<KVT, HG, LPP, false>, ATTN_THREADS, g.attn2_smem));
+			if (per_sm * g.sms < nunits * a.nsplit) g.attn2 = false; // k_attn (global partials, last-CTA fold) has no such requirement
+		}
 		if (g.attn2_cluster) {
 			smem_optin(k_attn2<KVT, HG, LPP, true>, g.attn2_smem);
 			if (a.nsplit > 8) CUDA_CHECK(cudaFuncSetAttribute(k_attn2<KVT, HG, LPP, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1077,12 +1082,13 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.attn_lpp = 1;
 	while (g.attn_lpp * 8 < c.head_dim) g.attn_lpp *= 2;
 	int units = c.n_kv_heads * g.attn_qgroups;
-	int want = g.sms / units;                           // about one 256-thread CTA per SM
+	const int split_mul = getenv("CALM_B200_ATTN_SPLIT_MUL") ? atoi(getenv("CALM_B200_ATTN_SPLIT_MUL")) : 1; // CTAs per SM (experiments)
+	int want = (split_mul > 1 ? split_mul : 1) * g.sms / units; // about one 256-thread CTA per SM
 	int maxsplit = cdiv(c.seq_len, 64);                 // at least 64 positions per slice at full context
 	g.attn_nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
 	// (measured 9 us per launch SLOWER than the global-partial fold: a 16-CTA cluster needs 16 SMs of one GPC at once, which the
 	// still-resident q/k/v CTAs delay; kept selectable for the record -- profiles/r02_sweep_ring_and_attention_variants.jsonl)
-	if (g.attn_nsplit > ATTN2_MAXB) g.attn_nsplit = ATTN2_MAXB; // k_attn2 keeps one (m, l) pair per slice in static shared memory
+	if (g.attn_nsplit > ATTN2_MAXB + 4) g.attn_nsplit = ATTN2_MAXB + 4; // k_attn2 keeps one (m, l) pair per slice in static shared memory
 	const bool want_cluster = getenv("CALM_B200_ATTN_CLUSTER") && atoi(getenv("CALM_B200_ATTN_CLUSTER")) != 0;
 	if (want_cluster && attn2_shape_ok(g.attn_hg, g.attn_lpp, c.head_dim) && !(getenv("CALM_B200_ATTN2") && atoi(getenv("CALM_B200_ATTN2")) == 0)) {
 		int ns = 1; // the slices of a unit will be one thread-block cluster: a power of two, at most 16 CTAs
@@ -1092,6 +1098,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.attn_partial = (float*)dev_alloc((size_t)units * g.attn_nsplit * g.attn_hg * (c.head_dim + 2) * sizeof(float));
 	{
 		const size_t cell_bytes = (size_t)units * (g.sms / units > g.attn_nsplit ? g.sms / units : g.attn_nsplit) * g.attn_hg * (c.head_dim + 2) * sizeof(unsigned long long);
+		// (the attention grid must be co-resident for the cell fold: units * nsplit CTAs of <= 1/2 SM each)
 		g.attn_cells = (unsigned long long*)dev_alloc(cell_bytes);
 		CUDA_CHECK(cudaMemset(g.attn_cells, 0, cell_bytes));
 		CUDA_CHECK(cudaHostAlloc((void**)&g.dev_err, sizeof(int), cudaHostAllocMapped));
