@@ -785,7 +785,8 @@ void make_plan() {
 	g.mma_up = g.mma_res_wo = g.mma_res_down = false;
 	{ // tensor-core matvec stages (stages.cuh k_ffn_up_mma / k_matres_mma): dense, whole k-blocks per warp
 		// measured (profiles/README.md): +2.6 % tokens/s with fp16 weights, -1 % with fp8 (round 1); gf4 is issue-bound in SIMT, so it is the default there
-		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : (DBITS == 16 || DBITS == 4);
+		// gf4: the 16-byte-load tensor-core kernels measured slower than the ring-fed ones (profiles/r02_sweep_gf4_mma_ldg_vs_simt_ring.jsonl)
+		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : DBITS == 16;
 		if (want && c.n_experts == 0 && c.dim % (32 * WFmt<DBITS>::VW) == 0 && c.hidden_dim % 8 == 0 && c.dim <= 16384) {
 			g.mma_up = true;
 			smem_optin(k_ffn_up_mma<DBITS>, g.smem_dim);
@@ -808,7 +809,7 @@ void make_plan() {
 	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_warps); // 0 slots: stage not ring-fed
 	const bool ring_ok = c.n_experts == 0; // MoE: the expert rows are known only after the router
 	const bool ring_up_on = ring_ok && g.ring_up_ns >= 2 && g.ring_up_ns <= RING_MAX_NS; // (row shards of w1 / w3 under tensor parallelism are fine)
-	const bool ring_res_on = ring_ok && g.tp_world == 1 /* wo / w2 carry the in-kernel exchange there */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) && DBITS != 4;
+	const bool ring_res_on = ring_ok && g.tp_world == 1 /* wo / w2 carry the in-kernel exchange there */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16);
 	auto chunk_units = [](size_t rowbytes) { return rowbytes % 2048 == 0 ? 4 : (rowbytes % 1024 == 0 ? 2 : 0); };
 	if (ring_up_on && !g.mma_up) {
 		const int u = chunk_units((size_t)c.dim * DBITS / 8);
