@@ -360,6 +360,10 @@ __device__ __forceinline__ float dot_vec<4>(const uint4& w, const float4 (&xv)[8
 	return acc;
 }
 
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+	return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
 // single weight decode (embedding row)
 template <int DBITS>
 __device__ __forceinline__ float weight_at(const void* w, size_t idx);

@@ -18,7 +18,6 @@
 #include "attn.cuh"
 #include "ring.cuh"
 #include "prefill.cuh"
-#include "ring_gf4.cuh"
 
 namespace {
 
@@ -64,10 +63,6 @@ struct Engine {
 	int ring_up_u = 0, ring_wo_u = 0, ring_down_u = 0, ring_wo_s = 1, ring_down_s = 1;
 	int grid_up_ring = 0, grid_wo_ring = 0, grid_down_ring = 0;
 	size_t smem_up_ring = 0, smem_wo_ring = 0, smem_down_ring = 0;
-	// gf4: ring-fed tensor-core stages (ring_gf4.cuh): K-slice chunks per task (0: stage not served), tiles per CTA, grids, shared memory
-	int g4_up_s = 0, g4_wo_s = 0, g4_down_s = 0, g4_up_tpc = 0, g4_wo_tpc = 0, g4_down_tpc = 0;
-	int grid_up_g4 = 0, grid_wo_g4 = 0, grid_down_g4 = 0;
-	size_t smem_up_g4 = 0, smem_wo_g4 = 0, smem_down_g4 = 0;
 	bool attn2_cluster = false; // ... with the CTAs of a unit as one thread-block cluster (slices folded through distributed shared memory)
 	bool attn2 = false; // k_attn2 (attn.cuh): KV slice requested into shared memory ahead of the dependency wait
 	int attn_nbmax = 0;
@@ -120,11 +115,6 @@ struct Engine {
 	bool use_graph = true;
 	bool use_pdl = true;
 	int carveout = -1;   // cudaFuncAttributePreferredSharedMemoryCarveout applied to every kernel of the token, or -1
-	bool mma_up = false; // FFN-up on the tensor cores (k_ffn_up_mma)
-	bool mma_res_wo = false, mma_res_down = false; // wo / w2 on the tensor cores (k_matres_mma; gf4)
-	int grid_wo_mma = 0, grid_down_mma = 0;
-	int* tile_ctr = nullptr; // [n_layers] dynamic tile counters of k_ffn_up_mma (zeroed by k_embed every token)
-	int grid_up_mma = 0;
 	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + k_ffn_up with 8 KB in flight per warp
 
 	// profiling (perf_cuda): in-kernel %globaltimer stamps per launch of the production graph (stages.cuh stamp_begin/end)
@@ -201,11 +191,6 @@ int cdiv(int a, int b) { return (a + b - 1) / b; }
 int balanced_grid(int units, int cap) {
 	if (units <= cap) return units < 1 ? 1 : units;
 	return cdiv(units, cdiv(units, cap));
-}
-
-// shared memory of the tensor-core matvec kernels: 32 floats + the activation vector as f16 hi / lo pairs
-inline size_t xs_bytes_h(int n) {
-	return (size_t)(32 + n) * sizeof(float);
 }
 
 template <int DBITS>
@@ -556,7 +541,6 @@ int run_token(int mode) {
 		EmbedArgs<KVT> a = {};
 		a.x = g.x, a.table = w.token_embedding_table, a.tp = g.tp, a.dim = dim;
 		a.embed_blocks = cdiv(dim, 256);
-		a.tile_ctr = g.tile_ctr, a.n_ctr = 3 * c.n_layers; // [l] FFN up, [L + l] wo, [2L + l] w2
 		a.key_cache = (KVT*)g.kc, a.rope_freq = g.rope_freq, a.rope_cs = g.rope_cs;
 		a.n_layers = c.n_layers, a.n_kv_heads = c.n_kv_heads, a.head_dim = hd, a.seq_len = c.seq_len;
 		a.stamp = nullptr, a.stamp_reset = g.perf ? g.stamps : nullptr, a.n_stamps = MAX_STAMPS + 8; // + the 16 debug stamps
@@ -603,9 +587,7 @@ int run_token(int mode) {
 			if (dense && g.pf_wo_up) pf_up_prefix(a.pf, 0, w.w1[l], w.w3[l], g.pf_attn_up, g.pf_wo_up, up_bytes);
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l); // partial over this rank's heads, summed over the ranks in the kernel
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			if (g.mma_res_wo) launch_pdl(k_matres_mma<DBITS>, g.grid_wo_mma, 256, xs_bytes_h(g.q_dim), a, g.tile_ctr ? g.tile_ctr + c.n_layers + l : (int*)nullptr);
-			else if (g.g4_wo_s) launch_pdl(k_matres_g4<3>, g.grid_wo_g4, G4_WARPS * 32, g.smem_wo_g4, a, g.g4_wo_s, g.g4_wo_tpc);
-			else if (g.ring_wo_u) ring_res_dispatch<DBITS>(a, g.ring_wo_u, g.ring_wo_s, g.grid_wo_ring, g.smem_wo_ring, false);
+			if (g.ring_wo_u) ring_res_dispatch<DBITS>(a, g.ring_wo_u, g.ring_wo_s, g.grid_wo_ring, g.smem_wo_ring, false);
 			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
@@ -621,14 +603,11 @@ int run_token(int mode) {
 			a.gate = c.n_experts ? w.moegate[l] : nullptr, a.w1 = w.w1[l], a.w3 = w.w3[l], a.hb = g.hb, a.sel = g.moe_sel;
 			a.dim = dim, a.hidden = hidden, a.n_experts = c.n_experts, a.nact = g.nact;
 			a.eps = c.norm_eps, a.ln = c.norm_ln, a.gelu = c.act_gelu;
-			a.tile_ctr = g.tile_ctr ? g.tile_ctr + l : nullptr;
 			a.expert_stride = g.up_expert_stride;
 			a.stamp = t.slot;
 			if (dense && g.pf_up_down) a.pf.p[0] = w.w2[l], a.pf.bytes[0] = (g.pf_up_down < down_bytes ? g.pf_up_down : down_bytes) & ~(size_t)15;
 			bool done = false;
-			if (g.g4_up_s) launch_pdl(k_ffn_up_g4<2>, g.grid_up_g4, G4_WARPS * 32, g.smem_up_g4, a, g.g4_up_s, g.g4_up_tpc), done = true;
-			if (!done && g.ring_up_u) ring_up_dispatch<DBITS>(a, false), done = true;
-			if (!done && g.mma_up) launch_pdl(k_ffn_up_mma<DBITS>, g.grid_up_mma, 256, g.smem_dim, a), done = true;
+			if (g.ring_up_u) ring_up_dispatch<DBITS>(a, false), done = true;
 			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, 256, g.smem_dim, a);
 			++nl;
 		}
@@ -644,9 +623,7 @@ int run_token(int mode) {
 			}
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
-			if (g.mma_res_down) launch_pdl(k_matres_mma<DBITS>, g.grid_down_mma, 256, xs_bytes_h(c.hidden_dim), a, g.tile_ctr ? g.tile_ctr + 2 * c.n_layers + l : (int*)nullptr);
-			else if (g.g4_down_s) launch_pdl(k_matres_g4<3>, g.grid_down_g4, G4_WARPS * 32, g.smem_down_g4, a, g.g4_down_s, g.g4_down_tpc);
-			else if (g.ring_down_u) ring_res_dispatch<DBITS>(a, g.ring_down_u, g.ring_down_s, g.grid_down_ring, g.smem_down_ring, false);
+			if (g.ring_down_u) ring_res_dispatch<DBITS>(a, g.ring_down_u, g.ring_down_s, g.grid_down_ring, g.smem_down_ring, false);
 			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
@@ -782,36 +759,15 @@ void make_plan() {
 	}
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
 	g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
-	g.mma_up = g.mma_res_wo = g.mma_res_down = false;
-	{ // tensor-core matvec stages (stages.cuh k_ffn_up_mma / k_matres_mma): dense, whole k-blocks per warp
-		// measured (profiles/README.md): +2.6 % tokens/s with fp16 weights, -1 % with fp8 (round 1); gf4 is issue-bound in SIMT, so it is the default there
-		// gf4: the 16-byte-load tensor-core kernels measured slower than the ring-fed ones (profiles/r02_sweep_gf4_mma_ldg_vs_simt_ring.jsonl)
-		const bool want = getenv("CALM_B200_MMA") ? atoi(getenv("CALM_B200_MMA")) != 0 : DBITS == 16;
-		if (want && c.n_experts == 0 && c.dim % (32 * WFmt<DBITS>::VW) == 0 && c.hidden_dim % 8 == 0 && c.dim <= 16384) {
-			g.mma_up = true;
-			smem_optin(k_ffn_up_mma<DBITS>, g.smem_dim);
-			g.grid_up_mma = imin(max_ctas(k_ffn_up_mma<DBITS>, 256, g.smem_dim), c.hidden_dim / 8);
-		}
-		const bool want_res = getenv("CALM_B200_MMA_RES") ? atoi(getenv("CALM_B200_MMA_RES")) != 0 : (DBITS == 4 && want);
-		if (want_res && c.n_experts == 0 && g.tp_world == 1 && c.dim % 16 == 0) {
-			auto ok = [&](int n) { return n % (4 * WFmt<DBITS>::VW) == 0 && n <= 16384; };
-			const size_t smax = xs_bytes_h(g.q_dim > c.hidden_dim ? g.q_dim : c.hidden_dim);
-			if (ok(g.q_dim) && ok(c.hidden_dim) && smax <= 200 * 1024) {
-				smem_optin(k_matres_mma<DBITS>, smax);
-				g.mma_res_wo = g.mma_res_down = true;
-				g.grid_wo_mma = imin(max_ctas(k_matres_mma<DBITS>, 256, xs_bytes_h(g.q_dim)), c.dim / 16);
-				g.grid_down_mma = imin(max_ctas(k_matres_mma<DBITS>, 256, xs_bytes_h(c.hidden_dim)), c.dim / 16);
-			}
-		}
-	}
 	// TMA-ring kernels for the dense single-GPU stages whose rows are whole 1 KB / 2 KB chunks (ring.cuh)
 	g.ring_up_u = g.ring_wo_u = g.ring_down_u = 0;
 	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_warps); // 0 slots: stage not ring-fed
 	const bool ring_ok = c.n_experts == 0; // MoE: the expert rows are known only after the router
 	const bool ring_up_on = ring_ok && g.ring_up_ns >= 2 && g.ring_up_ns <= RING_MAX_NS; // (row shards of w1 / w3 under tensor parallelism are fine)
-	const bool ring_res_on = ring_ok && g.tp_world == 1 /* wo / w2 carry the in-kernel exchange there */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16);
+	const bool ring_res_on = ring_ok && g.tp_world == 1 /* wo / w2 carry the in-kernel exchange there */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) &&
+	                         DBITS != 4; // gf4 rows are half as long in bytes: one-chunk K-slices fold twice as often and the SIMT decode is issue-bound (measured slower)
 	auto chunk_units = [](size_t rowbytes) { return rowbytes % 2048 == 0 ? 4 : (rowbytes % 1024 == 0 ? 2 : 0); };
-	if (ring_up_on && !g.mma_up) {
+	if (ring_up_on) {
 		const int u = chunk_units((size_t)c.dim * DBITS / 8);
 		if (u) {
 			g.smem_up_ring = ring_smem_bytes<DBITS>(c.dim, u, g.ring_up_ns, 8);
@@ -849,32 +805,6 @@ void make_plan() {
 		}
 		g.ring_wo_u = uw, g.ring_wo_s = sw, g.grid_wo_ring = gw, g.smem_wo_ring = mw;
 		g.ring_down_u = ud, g.ring_down_s = sd, g.grid_down_ring = gd, g.smem_down_ring = md;
-	}
-	// gf4: the tensor-core ring kernels (ring_gf4.cuh) take FFN up, wo and w2 of dense single-GPU models whose rows are whole 256-byte chunks
-	g.g4_up_s = g.g4_wo_s = g.g4_down_s = 0;
-	if constexpr (DBITS == 4) {
-		// (measured slower than both alternatives: 16 bulk copies of 256 bytes per chunk starve the ring -- profiles/r02_sweep_gf4_ring_mma_m16n8k8.jsonl; selectable)
-		const bool on = c.n_experts == 0 && g.tp_world == 1 && getenv("CALM_B200_GF4_RING") && atoi(getenv("CALM_B200_GF4_RING")) != 0;
-		auto plan = [&](int n, int tiles, int ns, int cps, int& s_out, int& tpc_out, int& grid_out, size_t& smem_out) {
-			if (!on || (n / 2) % G4_CH || n > 16384 || tiles < 1) return;
-			const int cpt = n / 2 / G4_CH;
-			const int grid = imin(g.sms * cps, tiles);
-			int S = 1;
-			if (cpt % 2 == 0 && (long long)tiles * (cpt / 2) >= 32LL * g.sms) S = 2; // halve the fold traffic when there are tasks to spare
-			while (cpt / S > G4_MAX_SL && cpt % (S * 2) == 0) S *= 2;
-			if (cpt % S || cpt / S > G4_MAX_SL) return;
-			const int tpc = cdiv(tiles, grid) + 1;
-			const size_t smem = g4_smem_bytes(n, ns, tpc, cpt / S);
-			if (smem > 220 * 1024 / cps) return;
-			s_out = S, tpc_out = tpc, grid_out = grid, smem_out = smem;
-		};
-		if (c.hidden_dim % 8 == 0) plan(c.dim, c.hidden_dim / 8, 2, 2, g.g4_up_s, g.g4_up_tpc, g.grid_up_g4, g.smem_up_g4);
-		if (c.dim % 16 == 0) {
-			plan(g.q_dim, c.dim / 16, 3, 1, g.g4_wo_s, g.g4_wo_tpc, g.grid_wo_g4, g.smem_wo_g4);
-			plan(c.hidden_dim, c.dim / 16, 3, 1, g.g4_down_s, g.g4_down_tpc, g.grid_down_g4, g.smem_down_g4);
-		}
-		if (g.g4_up_s) smem_optin(k_ffn_up_g4<2>, g.smem_up_g4);
-		if (g.g4_wo_s || g.g4_down_s) smem_optin(k_matres_g4<3>, g.smem_wo_g4 > g.smem_down_g4 ? g.smem_wo_g4 : g.smem_down_g4);
 	}
 	g.out_row0 = 0, g.out_row1 = c.vocab_size;
 	if (g.tp_fused) { // vocabulary split: equal slices of whole 32-row CTA iterations (the last rank's may be short)
@@ -1128,10 +1058,6 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.cand_idx = (int*)dev_alloc(g.ncand * sizeof(int));
 	g.out_tokens_cap = 1 << 16;
 	g.out_tokens = (int*)dev_alloc(g.out_tokens_cap * sizeof(int));
-	if (!(getenv("CALM_B200_MMA_STATIC") && atoi(getenv("CALM_B200_MMA_STATIC")))) {
-		g.tile_ctr = (int*)dev_alloc(3 * MAX_LAYERS * sizeof(int));
-		CUDA_CHECK(cudaMemset(g.tile_ctr, 0, 3 * MAX_LAYERS * sizeof(int)));
-	}
 	g.sample_chunks = cdiv(c.vocab_size, SAMPLE_CHUNK);
 	g.sample_state = (SampleState*)dev_alloc(sizeof(SampleState));
 	g.sample_count = (int*)dev_alloc(g.sample_chunks * sizeof(int));
@@ -1192,7 +1118,6 @@ extern "C" void calm_b200_release(struct Transformer* transformer) {
 		if (g.tp_peer[p] && g.tp_peer[p] != g.tp_area) cudaIpcCloseMemHandle(g.tp_peer[p]);
 	if (g.tp_area) cudaFree(g.tp_area);
 	if (g.tp_err) cudaFreeHost(g.tp_err);
-	if (g.tile_ctr) cudaFree(g.tile_ctr);
 	cudaFree(g.sample_state), cudaFree(g.sample_count), cudaFree(g.sample_csum), cudaFree(g.sample_idx), cudaFree(g.sample_prob);
 	if (g.tp_comm) g_nccl.CommDestroy(g.tp_comm);
 	if (g.xpart) cudaFree(g.xpart);

@@ -42,25 +42,6 @@ __host__ __device__ inline size_t ring_smem_bytes(int n, int u, int ns, int warp
 	return xs + (size_t)warps * ns * 2 * u * 512;
 }
 
-// gf4 consume of a 2-row slot on the tensor cores.  SIMT gf4 costs ~3.3 issue slots per half-byte weight (shift + LOP3 + FFMA and the
-// fp32 activation reads) -- issue-bound at about a third of the HBM roofline even when ring-fed.  Here the two rows of the slot are
-// columns 0 / 1 of the B operand of mma.m16n8k16 ((q - 4) * scale as exact f16: at most 6 significant bits) and the activation
-// vector, split into an f16 hi / lo pair (22 bits after a power-of-two pre-scale), is rows 0 / 1 of A: lane (g, t) decodes code
-// pair t of two consecutive words of row (g & 1) per k-step and supplies x pairs when g < 2 -- ~18 instructions per 32 weights.
-// D[0][n] + D[1][n] = row n . x.  The slots are the same 2 KB-per-row bulk copies as for the other formats (a variant that
-// gave each MMA row its own 256-byte copy starved the ring: profiles/README.md).
-__device__ __forceinline__ uint32_t gf4_pair_scaled(uint32_t w, int sh, __half2 sc) {
-	const uint32_t x = w >> sh;
-	uint32_t h = (x & 7u) | ((x & 0x38u) << 13) | 0x64006400u; // f16 integers 1024 + q
-	const __half2 v = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h), __half2half2(__ushort_as_half(0x6404))), sc);
-	return *reinterpret_cast<const uint32_t*>(&v);
-}
-__device__ __forceinline__ void mma_16816_rows01(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) { // A rows 8..15 are zero
-	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%5}, {%7,%8}, {%0,%1,%2,%3};"
-	             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-	             : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
-}
-
 // The streaming loop of one warp.  rows(task, rp0, rp1, chunk0): byte pointers of the task's two rows and its first chunk
 // index inside the row; done(task, v0, v1): the two finished dot products (called by every lane, values valid in all).
 // issue_prologue() must be called (warp-uniformly) before consume_all(); in between the caller waits for the previous grid
@@ -154,53 +135,6 @@ struct RingWarp {
 			}
 		}
 	}
-
-	// gf4 on the tensor cores (see gf4_pair_scaled above).  xh / xl: the activation vector as f16 pairs (u32), hi and lo;
-	// out_scale: 2^e of the pre-scale.  The format's -1/4 (infer.c:37-40) is applied to the sums.
-	__device__ __forceinline__ void consume_all_g4(const uint32_t* __restrict__ xh, const uint32_t* __restrict__ xl, float out_scale) {
-		static_assert(DBITS == 4, "gf4 only");
-		const int g = lane >> 2, t = lane & 3;
-		const uint32_t* xa = g == 0 ? xh : xl; // A row g: 0 = hi, 1 = lo, the rest zero
-		const bool arow = g < 2;
-		const int sh = 8 + 6 * t;
-		float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-		while (consumed < issued) {
-			const int slot = consumed % NS;
-			mbar_wait(&ctl->bar[warp][slot], (consumed / NS) & 1);
-			const int task = ctl->slot_task[warp][slot], piece = ctl->slot_piece[warp][slot];
-			int chunk0;
-			{
-				const unsigned char *rp0, *rp1;
-				rows(task, rp0, rp1, chunk0);
-			}
-			const uint4* srow = reinterpret_cast<const uint4*>(ring + (size_t)slot * 2 * CH + (size_t)(g & 1) * CH); // B column g: row g & 1 of the slot
-			const uint32_t* xp = xa + (size_t)(chunk0 + piece) * CH; // CH bytes = 2 CH weights = CH f16 pairs
-#pragma unroll 4
-			for (int q = 0; q < CH / 16; ++q) { // 4 words = 32 weights of the row: two k-steps
-				const uint4 w = srow[q];
-				uint32_t s0 = __byte_perm(w.x, 0, 0x0404), s1 = __byte_perm(w.y, 0, 0x0404), s2 = __byte_perm(w.z, 0, 0x0404), s3 = __byte_perm(w.w, 0, 0x0404);
-				const uint32_t b00 = gf4_pair_scaled(w.x, sh, *reinterpret_cast<__half2*>(&s0)), b01 = gf4_pair_scaled(w.y, sh, *reinterpret_cast<__half2*>(&s1));
-				const uint32_t b10 = gf4_pair_scaled(w.z, sh, *reinterpret_cast<__half2*>(&s2)), b11 = gf4_pair_scaled(w.w, sh, *reinterpret_cast<__half2*>(&s3));
-				const uint32_t a00 = arow ? xp[16 * q + t] : 0u, a02 = arow ? xp[16 * q + 4 + t] : 0u;
-				const uint32_t a10 = arow ? xp[16 * q + 8 + t] : 0u, a12 = arow ? xp[16 * q + 12 + t] : 0u;
-				mma_16816_rows01(d0, a00, a02, b00, b01);
-				mma_16816_rows01(d1, a10, a12, b10, b11);
-			}
-			++consumed;
-			__syncwarp();
-			if (more) issue_one();
-			if (piece == S - 1) {
-				// lane (g, 0) holds D[g][0], D[g][1]: hi (g = 0) and lo (g = 1) parts of the two rows
-				const float r0 = d0[0] + d1[0], r1 = d0[1] + d1[1];
-				const float k = -0.25f * out_scale;
-				const float v0 = (__shfl_sync(0xffffffffu, r0, 0) + __shfl_sync(0xffffffffu, r0, 4)) * k;
-				const float v1 = (__shfl_sync(0xffffffffu, r1, 0) + __shfl_sync(0xffffffffu, r1, 4)) * k;
-				done(task, v0, v1);
-#pragma unroll
-				for (int i = 0; i < 4; ++i) d0[i] = d1[i] = 0.f;
-			}
-		}
-	}
 };
 
 template <int NS>
@@ -242,16 +176,8 @@ __global__ void __launch_bounds__(256, 2) k_ffn_up_ring(const FfnUpArgs a) {
 	rw.issue_prologue(); // the first NS chunks of every warp are in flight before the previous kernel has finished
 	pdl_wait_prev();
 	stamp_begin(a.stamp);
-	if constexpr (DBITS == 4) { // the activation vector as f16 hi / lo pairs for the tensor-core consume (norm applied while staging)
-		uint2* H = reinterpret_cast<uint2*>(xs);
-		uint2* Lo = H + a.dim / 4;
-		const float out_scale = (a.dim / 4 <= (int)blockDim.x * 4) ? stage_vector_h<4>(H, Lo, red, a.x, a.dim, a.normw, a.eps, a.ln != 0)
-		                                                           : stage_vector_h_long(H, Lo, red, a.x, a.dim, a.normw, a.eps, a.ln != 0);
-		rw.consume_all_g4(reinterpret_cast<const uint32_t*>(H), reinterpret_cast<const uint32_t*>(Lo), out_scale);
-	} else {
-		post = stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
-		rw.consume_all(reinterpret_cast<const float4*>(xs));
-	}
+	post = stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
+	rw.consume_all(reinterpret_cast<const float4*>(xs));
 	stamp_end(a.stamp);
 }
 
@@ -301,15 +227,7 @@ __global__ void __launch_bounds__(512, 1) k_matres_ring(const MatResArgs a, cons
 	rw.issue_prologue();
 	pdl_wait_prev();
 	stamp_begin(a.stamp);
-	if constexpr (DBITS == 4) {
-		uint2* H = reinterpret_cast<uint2*>(xs);
-		uint2* Lo = H + a.n / 4;
-		const float out_scale = (a.n / 4 <= (int)blockDim.x * 4) ? stage_vector_h<4>(H, Lo, red, a.xin, a.n, nullptr, 0.f, false)
-		                                                         : stage_vector_h_long(H, Lo, red, a.xin, a.n, nullptr, 0.f, false);
-		rw.consume_all_g4(reinterpret_cast<const uint32_t*>(H), reinterpret_cast<const uint32_t*>(Lo), out_scale);
-	} else {
-		stage_vector<DBITS, 16>(xs, red, a.xin, a.n, nullptr, 0.f, false, nullptr);
-		rw.consume_all(reinterpret_cast<const float4*>(xs));
-	}
+	stage_vector<DBITS, 16>(xs, red, a.xin, a.n, nullptr, 0.f, false, nullptr);
+	rw.consume_all(reinterpret_cast<const float4*>(xs));
 	stamp_end(a.stamp);
 }

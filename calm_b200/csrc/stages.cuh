@@ -221,8 +221,6 @@ struct EmbedArgs {
 	const TokenParams* tp;
 	int dim;
 	int embed_blocks;
-	int* tile_ctr; // per-layer work counters of k_ffn_up_mma, zeroed here once per token
-	int n_ctr;
 	float2* rope_cs;           // [head_dim / 2]: (cos, sin)(pos * freq) of this token, written here for every layer's k_qkv
 	unsigned long long* stamp; // perf_cuda: {min start, max end} of this launch, or NULL
 	unsigned long long* stamp_reset; // perf_cuda: all slots of the token, re-armed here
@@ -245,8 +243,6 @@ __global__ void k_embed(const EmbedArgs<KVT> a) {
 	if ((int)blockIdx.x < a.embed_blocks) {
 		int i = blockIdx.x * blockDim.x + threadIdx.x;
 		if (i < a.dim) a.x[i] = weight_at<DBITS>(a.table, (size_t)a.tp->token * a.dim + i);
-		if (blockIdx.x == 0 && a.tile_ctr)
-			for (int j = threadIdx.x; j < a.n_ctr; j += blockDim.x) a.tile_ctr[j] = 0;
 		if (blockIdx.x == 0 && (int)threadIdx.x < a.head_dim / 2) { // RoPE angles (reference infer.c:223-236), once per token instead of once per row pair
 			float fcr, fci;
 			sincosf((float)a.tp->pos * a.rope_freq[threadIdx.x], &fci, &fcr);
@@ -928,7 +924,6 @@ struct FfnUpArgs {
 	int dim, hidden, n_experts, nact;
 	float eps;
 	int ln, gelu;
-	int* tile_ctr;      // k_ffn_up_mma: tiles beyond the first round are handed out through this counter (NULL: static stride)
 	size_t expert_stride; // 16-byte vectors between experts in w1 / w3 (tensor parallelism: a rank's rows are a slice of every expert)
 };
 
@@ -998,294 +993,6 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpA
 			const float u1 = v[0] * post, u3 = v[1] * post;
 			a.hb[p] = (a.gelu ? act_gelu(u1) : act_silu(u1)) * u3;
 		}
-	}
-	stamp_end(a.stamp);
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_ffn_up_mma: the FFN-up stage with the dot products on the tensor cores (mma.sync m16n8k16, f16 x f16 -> f32).
-// Why: k_ffn_up is the one stage that is limited by instruction issue -- an e5m2 weight costs 2.9 SIMT instructions
-// (PRMT/2 + HADD2.F32 + FFMA + LDS share) -- while the byte permute alone already yields exact f16 operands; one MMA
-// then replaces 256 convert+FMA pairs (0.8 instructions per weight).  This is a matvec, not a GEMM: the activation
-// vector x = hi + lo is split into two f16 vectors (22 mantissa bits after a power-of-two pre-scale that keeps
-// max|x| below 2^14) which occupy columns 0 and 1 of the B operand, so ONE instruction forms w.hi and w.lo with f32
-// accumulation; the other six columns are ignored.
-//   tile   = 8 rows of w1 (A rows 0..7) + the same 8 rows of w3 (A rows 8..15); a CTA owns a tile, its 8 warps split k
-//   lane   (g = lane / 4, t = lane % 4) loads 16 bytes of row g at byte offset 64 kb + 16 t of k-block kb (and of
-//          row g + 8); word s of that vector holds the weights that k-step s of the block multiplies
-//   B      lane (g, t) reads the 4 consecutive f16 x[k0..k0+3] of its own k range as one 8-byte word: hi for g = 0, lo for
-//          g = 1 (anything for the rest); the k order inside a block is permuted consistently for A and B.
-// Dense models, fp8 / fp16 weights, dim a multiple of 8 k-blocks; everything else uses k_ffn_up.
-
-__device__ __forceinline__ float block_max(float v, float* red) {
-	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
-	for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
-	__syncthreads();
-	if (lane == 0) red[warp] = v;
-	__syncthreads();
-	float r = lane < nwarps ? red[lane] : 0.f;
-	for (int m = 16; m > 0; m >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, m));
-	return r;
-}
-
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-	return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-
-// x (optionally normalised) -> H[n/4], Lo[n/4]: entry i holds the f16 pairs of x[4i..4i+3] * 2^-e (hi, and the
-// rounding residual lo).  Returns 2^e, the factor the dot products are multiplied by.  n/4 <= blockDim * SV.
-template <int SV>
-__device__ __forceinline__ float stage_vector_h(uint2* H, uint2* Lo, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps,
-                                                bool ln) {
-	const int tid = threadIdx.x, nthr = blockDim.x;
-	const int n4 = n >> 2;
-	const float4* x4 = reinterpret_cast<const float4*>(x);
-	float4 v[SV];
-#pragma unroll
-	for (int k = 0; k < SV; ++k) {
-		int i = tid + k * nthr;
-		v[k] = i < n4 ? __ldcg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-	}
-	if (normw) {
-		float4 w[SV];
-#pragma unroll
-		for (int k = 0; k < SV; ++k) {
-			int i = tid + k * nthr;
-			w[k] = i < n4 ? __ldg(reinterpret_cast<const float4*>(normw) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-		}
-		float mean = 0.f;
-		if (ln) {
-			float s = 0.f;
-#pragma unroll
-			for (int k = 0; k < SV; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-			mean = block_sum(s, red) / n;
-		}
-		float ss = 0.f;
-#pragma unroll
-		for (int k = 0; k < SV; ++k) {
-			if (tid + k * nthr < n4) {
-				float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
-				ss = fmaf(dx, dx, ss), ss = fmaf(dy, dy, ss), ss = fmaf(dz, dz, ss), ss = fmaf(dw, dw, ss);
-			}
-		}
-		ss = block_sum(ss, red);
-		const float scale = 1.0f / sqrtf(ss / n + eps);
-#pragma unroll
-		for (int k = 0; k < SV; ++k) {
-			v[k].x = (v[k].x - mean) * scale * w[k].x, v[k].y = (v[k].y - mean) * scale * w[k].y;
-			v[k].z = (v[k].z - mean) * scale * w[k].z, v[k].w = (v[k].w - mean) * scale * w[k].w;
-		}
-	}
-	float amax = 0.f;
-#pragma unroll
-	for (int k = 0; k < SV; ++k) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[k].x), fabsf(v[k].y)), fmaxf(fabsf(v[k].z), fabsf(v[k].w))));
-	amax = block_max(amax, red);
-	int e = 0;
-	if (amax > 0.f && amax < 3.0e38f) e = ilogbf(amax) - 13; // max |x| 2^-e in [2^13, 2^14): far from the f16 limits
-	const float down = ldexpf(1.0f, -e);
-#pragma unroll
-	for (int k = 0; k < SV; ++k) {
-		int i = tid + k * nthr;
-		if (i < n4) {
-			float4 q = make_float4(v[k].x * down, v[k].y * down, v[k].z * down, v[k].w * down); // exact: power of two
-			__half hx = __float2half_rn(q.x), hy = __float2half_rn(q.y), hz = __float2half_rn(q.z), hw = __float2half_rn(q.w);
-			H[i] = make_uint2(pack_h2(hx, hy), pack_h2(hz, hw));
-			Lo[i] = make_uint2(pack_h2(__float2half_rn(q.x - __half2float(hx)), __float2half_rn(q.y - __half2float(hy))),
-			                   pack_h2(__float2half_rn(q.z - __half2float(hz)), __float2half_rn(q.w - __half2float(hw))));
-		}
-	}
-	__syncthreads();
-	return ldexpf(1.0f, e);
-}
-
-// long vectors (dim > 4096): out of line, so that its 128 staging registers do not count against the matvec loop
-__device__ __noinline__ float stage_vector_h_long(uint2* H, uint2* Lo, float* red, const float* __restrict__ x, int n, const float* __restrict__ normw, float eps, bool ln) {
-	return stage_vector_h<16>(H, Lo, red, x, n, normw, eps, ln);
-}
-
-__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-	             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-	             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-// one 64-byte k-block of the two rows a lane owns against the staged activations; B = this lane's column source
-template <int DBITS>
-__device__ __forceinline__ void mma_kblock(float (&d0)[4], float (&d1)[4], const uint4& ra, const uint4& rb, const uint2* B, int kb, int t) {
-	const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
-	if constexpr (DBITS == 8) { // 64 weights per row and block: 4 k-steps of 16
-		const uint2* bp = B + kb * 16 + 4 * t;
-#pragma unroll
-		for (int s = 0; s < 4; ++s) {
-			const uint2 b = bp[s];
-			const uint32_t a0 = __byte_perm(wa[s], 0, 0x1404), a2 = __byte_perm(wa[s], 0, 0x3424); // e5m2 byte = high byte of the f16
-			const uint32_t a1 = __byte_perm(wb[s], 0, 0x1404), a3 = __byte_perm(wb[s], 0, 0x3424);
-			if (s & 1)
-				mma_16816(d1, a0, a1, a2, a3, b.x, b.y);
-			else
-				mma_16816(d0, a0, a1, a2, a3, b.x, b.y);
-		}
-	} else if constexpr (DBITS == 4) { // gf4: 16 words = 128 weights per row and block; this lane's vector holds words 4t..4t+3 = weights 32t..32t+31: 8 k-steps
-		// A = (q - 4) * s as exact f16 (at most 6 significant bits); the -1/4 of the format (infer.c:37-40) is applied to the sum by the caller
-		const uint2* bp = B + kb * 32 + 8 * t;
-		const __half2 k1028 = __half2half2(__ushort_as_half(0x6404));
-		auto pair = [&](uint32_t w, int p, __half2 sc) { // codes 2p, 2p+1 of word w
-			const uint32_t x = w >> (8 + 6 * p);
-			uint32_t h = (x & 7u) | ((x & 0x38u) << 13) | 0x64006400u; // f16 integers 1024 + q
-			const __half2 v = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h), k1028), sc);
-			return *reinterpret_cast<const uint32_t*>(&v);
-		};
-#pragma unroll
-		for (int j = 0; j < 4; ++j) { // word j of the vector: two k-steps
-			uint32_t sa = __byte_perm(wa[j], 0, 0x0404), sb = __byte_perm(wb[j], 0, 0x0404); // the e5m2 scale as an f16 pair
-			const __half2 sca = *reinterpret_cast<__half2*>(&sa), scb = *reinterpret_cast<__half2*>(&sb);
-#pragma unroll
-			for (int hh = 0; hh < 2; ++hh) {
-				const uint2 b = bp[2 * j + hh];
-				const uint32_t a0 = pair(wa[j], 2 * hh, sca), a2 = pair(wa[j], 2 * hh + 1, sca);
-				const uint32_t a1 = pair(wb[j], 2 * hh, scb), a3 = pair(wb[j], 2 * hh + 1, scb);
-				if (hh)
-					mma_16816(d1, a0, a1, a2, a3, b.x, b.y);
-				else
-					mma_16816(d0, a0, a1, a2, a3, b.x, b.y);
-			}
-		}
-	} else { // fp16: 32 weights per row and block: 2 k-steps
-		const uint2* bp = B + kb * 8 + 2 * t;
-#pragma unroll
-		for (int s = 0; s < 2; ++s) {
-			const uint2 b = bp[s];
-			if (s & 1)
-				mma_16816(d1, wa[2 * s], wb[2 * s], wa[2 * s + 1], wb[2 * s + 1], b.x, b.y);
-			else
-				mma_16816(d0, wa[2 * s], wb[2 * s], wa[2 * s + 1], wb[2 * s + 1], b.x, b.y);
-		}
-	}
-}
-
-template <int DBITS>
-__global__ void __launch_bounds__(256, 3) k_ffn_up_mma(const FfnUpArgs a) {
-	pdl_launch_next();
-	extern __shared__ __align__(16) float smem[];
-	__shared__ float part[2][8][16];
-	float* red = smem;
-	uint2* H = reinterpret_cast<uint2*>(smem + 32);
-	uint2* Lo = H + a.dim / 4;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-	const int rowvecs = a.dim / WFmt<DBITS>::VW; // uint4 per row
-	const int nkb = rowvecs / 4, kpw = nkb / 8;  // k-blocks (64 bytes) per row, per warp
-	const int ntiles = a.hidden / 8;
-	const uint4* w1 = reinterpret_cast<const uint4*>(a.w1);
-	const uint4* w3 = reinterpret_cast<const uint4*>(a.w3);
-	if ((int)blockIdx.x < ntiles && t == 0) { // this warp's share of the first tile: 8 + 8 row pieces of kpw * 64 bytes
-		const size_t off = (size_t)(blockIdx.x * 8 + g) * rowvecs + (size_t)warp * kpw * 4;
-		l2_prefetch(w1 + off, kpw * 64), l2_prefetch(w3 + off, kpw * 64);
-	}
-	pdl_wait_prev();
-	stamp_begin(a.stamp);
-	prefetch_ranges(a.pf);
-	float out_scale;
-	if (a.dim / 4 <= (int)blockDim.x * 4)
-		out_scale = stage_vector_h<4>(H, Lo, red, a.x, a.dim, a.normw, a.eps, a.ln != 0);
-	else
-		out_scale = stage_vector_h_long(H, Lo, red, a.x, a.dim, a.normw, a.eps, a.ln != 0);
-	const uint2* B = g == 1 ? Lo : H;
-
-	// the first tile is static, the rest are taken from a counter: 1792 tiles over 444 resident CTAs would otherwise cost
-	// five full rounds for 4.04 rounds of work
-	__shared__ int next_tile[2];
-	int buf = 0;
-	for (int ti = blockIdx.x; ti < ntiles; buf ^= 1) {
-		if (threadIdx.x == 0) next_tile[buf] = a.tile_ctr ? (int)gridDim.x + atomicAdd(a.tile_ctr, 1) : ti + (int)gridDim.x;
-		const uint4* ra = w1 + (size_t)(ti * 8 + g) * rowvecs + t;
-		const uint4* rb = w3 + (size_t)(ti * 8 + g) * rowvecs + t;
-		float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-		for (int k0 = warp * kpw; k0 < (warp + 1) * kpw; k0 += 4) {
-			uint4 va[4], vb[4];
-#pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				const bool in = k0 + u < (warp + 1) * kpw;
-				va[u] = in ? ldg_stream(ra + (size_t)(k0 + u) * 4) : make_uint4(0, 0, 0, 0);
-				vb[u] = in ? ldg_stream(rb + (size_t)(k0 + u) * 4) : make_uint4(0, 0, 0, 0);
-			}
-#pragma unroll
-			for (int u = 0; u < 4; ++u)
-				if (k0 + u < (warp + 1) * kpw) mma_kblock<DBITS>(d0, d1, va[u], vb[u], B, k0 + u, t);
-		}
-		if (t == 0) { // column 0 = w.hi, column 1 = w.lo
-			part[buf][warp][g] = (d0[0] + d1[0]) + (d0[1] + d1[1]);
-			part[buf][warp][8 + g] = (d0[2] + d1[2]) + (d0[3] + d1[3]);
-		}
-		__syncthreads(); // (one barrier per tile: the buffers alternate)
-		if (threadIdx.x < 8) {
-			float u1 = 0.f, u3 = 0.f;
-#pragma unroll
-			for (int w = 0; w < 8; ++w) u1 += part[buf][w][threadIdx.x], u3 += part[buf][w][8 + threadIdx.x];
-			u1 *= out_scale * (DBITS == 4 ? -0.25f : 1.f), u3 *= out_scale * (DBITS == 4 ? -0.25f : 1.f);
-			a.hb[ti * 8 + threadIdx.x] = (a.gelu ? act_gelu(u1) : act_silu(u1)) * u3;
-		}
-		ti = next_tile[buf]; // written before this iteration's barrier
-	}
-	stamp_end(a.stamp);
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_matres_mma: y[row] += W[row] . xin on the tensor cores, the k_ffn_up_mma scheme for wo / w2 (dense).  tile = 16 consecutive
-// rows (fragment rows g and g + 8); a CTA owns a tile, its 8 warps split k, tiles beyond the first round come from a counter.
-// Used for gf4, where SIMT decode is issue-bound (~3.3 slots per half-byte weight vs ~0.1 here).
-template <int DBITS>
-__global__ void __launch_bounds__(256, 2) k_matres_mma(const MatResArgs a, int* tile_ctr) {
-	pdl_launch_next();
-	extern __shared__ __align__(16) float smem[];
-	__shared__ float part[2][8][16];
-	__shared__ int next_tile[2];
-	float* red = smem;
-	uint2* H = reinterpret_cast<uint2*>(smem + 32);
-	uint2* Lo = H + a.n / 4;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-	const int rowvecs = a.n / WFmt<DBITS>::VW; // uint4 per row
-	const int nkb = rowvecs / 4;                // 64-byte k-blocks per row
-	const int kb_lo = (int)(((long long)warp * nkb) / 8), kb_hi = (int)(((long long)(warp + 1) * nkb) / 8);
-	const int ntiles = a.d / 16;
-	const uint4* w = reinterpret_cast<const uint4*>(a.w);
-	pdl_wait_prev();
-	stamp_begin(a.stamp);
-	float out_scale;
-	if (a.n / 4 <= (int)blockDim.x * 4) out_scale = stage_vector_h<4>(H, Lo, red, a.xin, a.n, nullptr, 0.f, false);
-	else out_scale = stage_vector_h_long(H, Lo, red, a.xin, a.n, nullptr, 0.f, false);
-	if (DBITS == 4) out_scale *= -0.25f;
-	const uint2* B = g == 1 ? Lo : H;
-	int buf = 0;
-	for (int ti = blockIdx.x; ti < ntiles; buf ^= 1) {
-		if (threadIdx.x == 0) next_tile[buf] = tile_ctr ? (int)gridDim.x + atomicAdd(tile_ctr, 1) : ti + (int)gridDim.x;
-		const uint4* ra = w + (size_t)(ti * 16 + g) * rowvecs + t;
-		const uint4* rb = w + (size_t)(ti * 16 + g + 8) * rowvecs + t;
-		float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-		for (int k0 = kb_lo; k0 < kb_hi; k0 += 4) {
-			uint4 va[4], vb[4];
-#pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				const bool in = k0 + u < kb_hi;
-				va[u] = in ? ldg_stream(ra + (size_t)(k0 + u) * 4) : make_uint4(0, 0, 0, 0);
-				vb[u] = in ? ldg_stream(rb + (size_t)(k0 + u) * 4) : make_uint4(0, 0, 0, 0);
-			}
-#pragma unroll
-			for (int u = 0; u < 4; ++u)
-				if (k0 + u < kb_hi) mma_kblock<DBITS>(d0, d1, va[u], vb[u], B, k0 + u, t);
-		}
-		if (t == 0) { // column 0 = w.hi, column 1 = w.lo
-			part[buf][warp][g] = (d0[0] + d1[0]) + (d0[1] + d1[1]);
-			part[buf][warp][8 + g] = (d0[2] + d1[2]) + (d0[3] + d1[3]);
-		}
-		__syncthreads(); // (one barrier per tile: the buffers alternate)
-		if (threadIdx.x < 16) {
-			float v = 0.f;
-#pragma unroll
-			for (int ww = 0; ww < 8; ++ww) v += part[buf][ww][threadIdx.x];
-			float* y = a.y + ti * 16 + threadIdx.x;
-			*y = (a.accumulate ? *y : 0.f) + v * out_scale;
-		}
-		ti = next_tile[buf];
 	}
 	stamp_end(a.stamp);
 }
