@@ -399,6 +399,31 @@ struct PfAttnArgs {
 	float inv_sqrt_hd;
 };
 
+// DPL (2 or 4) consecutive cache elements -> floats with a single shared-memory load
+template <int DPL>
+__device__ __forceinline__ void pf_load_dims(const __half* p, float (&o)[DPL]) {
+	if constexpr (DPL == 4) {
+		const uint2 r = *reinterpret_cast<const uint2*>(p);
+		const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+		o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y;
+	} else {
+		const float2 a = __half22float2(*reinterpret_cast<const __half2*>(p));
+		o[0] = a.x, o[1] = a.y;
+	}
+}
+template <int DPL>
+__device__ __forceinline__ void pf_load_dims(const uint8_t* p, float (&o)[DPL]) {
+	if constexpr (DPL == 4) {
+		const uint32_t r = *reinterpret_cast<const uint32_t*>(p);
+		const float2 a = e5m2x2_lo(r), b = e5m2x2_hi(r);
+		o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y;
+	} else {
+		const uint32_t r = *reinterpret_cast<const unsigned short*>(p);
+		const float2 a = e5m2x2_lo(r);
+		o[0] = a.x, o[1] = a.y;
+	}
+}
+
 // CTA = (kv head, 8 consecutive query tokens); warp = one token with all kv_mul query heads of the kv head (KM of them per pass)
 template <typename KVT, int HD, int KM>
 __global__ void __launch_bounds__(PFA_WARPS * 32) k_pf_attn(const PfAttnArgs a) {
@@ -471,9 +496,7 @@ __global__ void __launch_bounds__(PFA_WARPS * 32) k_pf_attn(const PfAttnArgs a) 
 			const int nk = min(PFA_TILE, mypos - k0 + 1);
 			for (int j = 0; j < nk; ++j) {
 				float vf[DPL];
-				const KVT* vp = reinterpret_cast<const KVT*>(vs) + (size_t)j * HD + lane * DPL;
-#pragma unroll
-				for (int d = 0; d < DPL; ++d) vf[d] = kv_load(vp + d);
+				pf_load_dims<DPL>(reinterpret_cast<const KVT*>(vs) + (size_t)j * HD + lane * DPL, vf); // one 8- / 4- / 2-byte load
 #pragma unroll
 				for (int h = 0; h < KM; ++h) {
 					const float pj = __shfl_sync(0xffffffffu, p[h], j);
