@@ -228,7 +228,7 @@ def workload_config(spec, pos0, args):
 
     per_gpu = mg.algorithmic_bytes(spec) / (args.gpus if (args.gpus > 1 and args.parallel == "tp") else 1)
     return {"workload": f"{spec.name}: {spec.n_layers} layers, dim {spec.dim}, hidden {spec.hidden_dim}, heads {spec.n_heads}/{spec.n_kv_heads}x{spec.head_dim}, "
-                        f"vocab {spec.vocab_size}, {spec.dtype} weights, fp16 KV cache, context 4096, batch 1",
+                        f"vocab {spec.vocab_size}, {spec.dtype} weights, {'fp16' if getattr(args, 'kvbits', 16) == 16 else 'e5m2'} KV cache, context 4096, batch 1",
             "positions": f"{pos0}..{pos0 + args.steps + args.warmup - 1} (KV cache pre-filled to pos0)",
             "l2": f"inputs ({per_gpu / 1e9:.2f} GB of weights per step and GPU) exceed the 126 MB L2; no flush",
             "parallelism": "single GPU" if args.gpus <= 1 else (f"tp{args.gpus}" if args.parallel == "tp" else "replicas")}
@@ -250,6 +250,7 @@ def main():
                     help="N>1: ONE token stream tensor-parallel over the N GPUs (strong scaling; the two all-reduces per layer run "
                          "inside k_matres over NVLink peer memory; default) or independent replicas (weak scaling, no data-path collective)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference infer.cu (oracle/_ref/libcalm_ref_cuda.so) on this GPU")
+    ap.add_argument("--kvbits", type=int, default=16, choices=[16, 8], help="KV cache element: fp16 (what the reference uses up to 4096 positions) or e5m2 (its choice beyond, run.c:537-539)")
     ap.add_argument("--layers", type=int, default=None, help="(debug) override the layer count")
     ap.add_argument("--pos0", type=int, default=None, help="(debug) first timed position instead of the end of the context")
     args = ap.parse_args()
@@ -301,13 +302,13 @@ def main():
     is_tp = tp is not None
     tensors = mg.generate(spec, args.seed + (0 if is_tp else rank), device="cuda")  # TP ranks hold the SAME model
     torch.cuda.synchronize()
-    dm = lib.DeviceModel(spec, tensors, seq_len=seq_len, device=local, tp=tp)
+    dm = lib.DeviceModel(spec, tensors, seq_len=seq_len, device=local, tp=tp, kvbits=args.kvbits)
     K, W = args.steps, args.warmup
     pos0 = max(0, seq_len - (K + W)) if args.pos0 is None else args.pos0
     dm.fill_kv(min(pos0, seq_len), seed=1 + rank)
 
     alg_bytes = mg.algorithmic_bytes(spec)
-    kv_b = [mg.kv_bytes(spec, pos0 + W + i, seq_len) for i in range(K)]
+    kv_b = [mg.kv_bytes(spec, pos0 + W + i, seq_len, args.kvbits) for i in range(K)]
     bytes_per_tok = alg_bytes + float(np.mean(kv_b))
 
     # ---- leg 1: device-resident greedy decode (inputs resident in HBM)
