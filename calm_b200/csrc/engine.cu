@@ -783,9 +783,10 @@ void make_plan() {
 	if (ring_res_on) {
 		auto plan_res = [&](int n, int& u_out, int& s_out, int& grid_out, size_t& smem_out) {
 			const size_t rowbytes = (size_t)n * DBITS / 8;
-			const int u = chunk_units(rowbytes);
+			int u = chunk_units(rowbytes);
 			if (!u) return;
-			const size_t smem = ring_smem_bytes<DBITS>(n, u, g.ring_res_ns, g.ring_res_warps);
+			size_t smem = ring_smem_bytes<DBITS>(n, u, g.ring_res_ns, g.ring_res_warps);
+			if (smem > 220 * 1024 && u == 4) u = 2, smem = ring_smem_bytes<DBITS>(n, u, g.ring_res_ns, g.ring_res_warps); // long activation vectors (70B w2: 112 KB): 1 KB chunks
 			if (smem > 220 * 1024) return;
 			const int grid = imin(g.sms * imin(16 / g.ring_res_warps, (int)(224 * 1024 / smem)), c.dim / 2);
 			const int cpt = (int)(rowbytes / (u * 512));
