@@ -26,7 +26,7 @@
 #define RING_MAX_WARPS 16 // warps per CTA: 8 (two CTAs per SM) or 16 (one CTA per SM when the activation vector is long: w2)
 #define RING_MAX_NS 4
 #define RING_MAX_PAIRS 48 // row pairs per CTA when K-slices are folded through shared memory
-#define RING_MAX_SLICES 16
+#define RING_MAX_SLICES 32
 
 struct RingCtl {
 	uint64_t bar[RING_MAX_WARPS][RING_MAX_NS];
