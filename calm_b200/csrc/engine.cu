@@ -764,7 +764,7 @@ void make_plan() {
 	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_warps); // 0 slots: stage not ring-fed
 	const bool ring_ok = c.n_experts == 0; // MoE: the expert rows are known only after the router
 	const bool ring_up_on = ring_ok && g.ring_up_ns >= 2 && g.ring_up_ns <= RING_MAX_NS; // (row shards of w1 / w3 under tensor parallelism are fine)
-	const bool ring_res_on = ring_ok && g.tp_world == 1 /* wo / w2 carry the in-kernel exchange there */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) &&
+	const bool ring_res_on = ring_ok && (g.tp_world == 1 || g.tp_fused) /* the ring kernels carry the in-kernel exchange too */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) &&
 	                         DBITS != 4; // gf4 rows are half as long in bytes: one-chunk K-slices fold twice as often and the SIMT decode is issue-bound (measured slower)
 	auto chunk_units = [](size_t rowbytes) { return rowbytes % 2048 == 0 ? 4 : (rowbytes % 1024 == 0 ? 2 : 0); };
 	if (ring_up_on) {
@@ -790,6 +790,7 @@ void make_plan() {
 			if (smem > 220 * 1024) return;
 			const int grid = imin(g.sms * imin(16 / g.ring_res_warps, (int)(224 * 1024 / smem)), c.dim / 2);
 			const int cpt = (int)(rowbytes / (u * 512));
+			if (g.tp_world > 1 && cdiv(c.dim / 2, grid) + 1 > RING_MAX_PAIRS) return; // the exchange keeps a CTA's rows in shared memory
 			const bool split = cdiv(c.dim / 2, grid) + 1 <= RING_MAX_PAIRS && cpt <= RING_MAX_SLICES; // K-slices of one chunk, folded in shared memory
 			u_out = u, s_out = split ? 1 : cpt, grid_out = grid < 1 ? 1 : grid, smem_out = smem;
 			MatResArgs ma = {};

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(512, 1) k_matres_ring(const MatResArgs a, cons
 	__shared__ RingCtl ctl;
 	__shared__ float2 part[RING_MAX_PAIRS][RING_MAX_SLICES];
 	__shared__ int cnt[RING_MAX_PAIRS];
+	__shared__ __align__(8) float ypart[2 * RING_MAX_PAIRS]; // tensor parallelism: this rank's partial of the CTA's rows, summed over the ranks at the end
 	float* red = reinterpret_cast<float*>(smem_raw);
 	float* xs = red + 32;
 	unsigned char* ring = smem_raw + (((size_t)(32 + xs_floats<DBITS>(a.n)) * sizeof(float) + 127) & ~(size_t)127);
@@ -218,6 +219,10 @@ __global__ void __launch_bounds__(512, 1) k_matres_ring(const MatResArgs a, cons
 			v0 = 0.f, v1 = 0.f;
 			for (int k = 0; k < nsl; ++k) v0 += part[pl][k].x, v1 += part[pl][k].y; // slice order: deterministic
 		}
+		if (a.tpx.world > 1) { // the matvec -> all-reduce fusion of stages.cuh TpExchange, on this kernel's contiguous row ranges
+			ypart[2 * (p - p_lo)] = v0, ypart[2 * (p - p_lo) + 1] = v1;
+			return;
+		}
 		float2* dst = reinterpret_cast<float2*>(a.y + 2 * p);
 		float2 cur = a.accumulate ? *dst : make_float2(0.f, 0.f);
 		cur.x += v0, cur.y += v1;
@@ -229,5 +234,6 @@ __global__ void __launch_bounds__(512, 1) k_matres_ring(const MatResArgs a, cons
 	stamp_begin(a.stamp);
 	stage_vector<DBITS, 16>(xs, red, a.xin, a.n, nullptr, 0.f, false, nullptr);
 	rw.consume_all(reinterpret_cast<const float4*>(xs));
+	if (a.tpx.world > 1) tp_exchange_rows(a.tpx, ypart, 2 * p_lo, 2 * (p_hi - p_lo), a.y, a.d);
 	stamp_end(a.stamp);
 }

@@ -829,6 +829,50 @@ __device__ __forceinline__ void tp_exchange_add(const TpExchange& t, const float
 	}
 }
 
+// The same exchange for a CTA that owns the CONTIGUOUS rows [row0, row0 + nrows) (ring-fed kernels): part[j] = this rank's partial
+// of row row0 + j.  Cells are indexed by row, so the two forms interoperate with any row-to-CTA mapping as long as every rank
+// pushes every row once.  All threads of the CTA call; the grid must be co-resident (it is: at most one or two CTAs per SM).
+__device__ __forceinline__ void tp_exchange_rows(const TpExchange& t, const float* part, int row0, int nrows, float* y, int d) {
+	const unsigned epoch = (unsigned)t.tp->tp_seq * t.stride + t.idx;
+	const int slot = epoch & 1, W = t.world;
+	__syncthreads(); // part[] complete
+	for (int i = threadIdx.x; i < nrows * (W - 1); i += blockDim.x) {
+		int peer = i / nrows;
+		const int j = i - peer * nrows;
+		peer += peer >= t.rank; // skip self
+		const unsigned long long cell = ((unsigned long long)epoch << 32) | __float_as_uint(part[j]);
+		asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(t.cell[peer] + ((size_t)slot * W + t.rank) * d + row0 + j), "l"(cell) : "memory");
+	}
+	for (int j = threadIdx.x; j < nrows; j += blockDim.x) {
+		const uint2* base = t.cell[t.rank] + (size_t)slot * W * d + row0 + j;
+		float sum = 0.f;
+		for (int p = 0; p < W; ++p) { // rank order: identical on every rank
+			if (p == t.rank) {
+				sum += part[j];
+				continue;
+			}
+			unsigned spins = 0;
+			unsigned long long t0 = 0, cell;
+			for (;;) {
+				asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(cell) : "l"(base + (size_t)p * d) : "memory");
+				if ((unsigned)(cell >> 32) == epoch) break;
+				if ((++spins & 1023) == 0) {
+					unsigned long long now;
+					asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+					if (!t0) t0 = now;
+					if (now - t0 > 20000000000ull) {
+						if (t.err) *reinterpret_cast<volatile int*>(t.err) = 9000 + p;
+						__threadfence_system();
+						__trap();
+					}
+				}
+			}
+			sum += __uint_as_float((unsigned)cell);
+		}
+		y[row0 + j] += sum;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_matres: y[row] (+)= sum_e weight_e * (W_e[row] . xin_e)   -- wo (+ residual, infer.c:410-415) and
 // w2 (* router weight, + residual, infer.c:452-456).  Experts are visited in selection order by the

@@ -111,6 +111,8 @@ SPECS.update({
     # the smallest shapes the batched prompt pass serves (every dim a multiple of 128, head_dim 64 / 128)
     "pf-tiny": ModelSpec("pf-tiny", 256, 512, 2, 4, 2, 64, 512, "fp8", rope_theta=1e4, max_seq_len=512),
     "pf-tiny-hd128": ModelSpec("pf-tiny-hd128", 512, 1024, 2, 4, 1, 128, 512, "fp8", rope_theta=5e5, max_seq_len=512, qkv_bias=True),
+    # wide enough for the ring-fed kernels (rows of whole 1 KB chunks) and splittable over 2 / 4 tensor-parallel ranks
+    "ring-tp": ModelSpec("ring-tp", 2048, 4096, 2, 8, 4, 128, 512, "fp8", rope_theta=5e5, max_seq_len=64),
     # Gemma-style multi-query attention: 8 query heads on ONE kv head of 256 dims (the attention kernel's merge
     # records exceed the default 48 KB of dynamic shared memory)
     # (hidden >= dim >= q_dim: the reference CPU backend reuses xb2[dim] and hb[hidden] as scratch, infer.c:152-153, 404, 409)

@@ -45,7 +45,7 @@ def _run_world(tmp_path, name, world, fused, tokens, greedy=12):
 
 
 CASES = [("tiny-fp8", 2, 1), ("tiny-gf4", 2, 1), ("tiny-bias2", 2, 1), ("tiny-lnpar", 2, 1), ("tiny-mha", 2, 1), ("tiny-fp8", 2, 0), ("tiny-bias2", 2, 0),
-         ("tiny-moe", 2, 1), ("tiny-tp8", 2, 1), ("tiny-tp8", 4, 1), ("tiny-tp8-moe", 4, 1), ("tiny-tp8", 4, 0), ("tiny-tp8", 8, 1), ("tiny-tp8-moe", 8, 1), ("tiny-tp8", 8, 0)]
+         ("tiny-moe", 2, 1), ("ring-tp", 2, 1), ("tiny-tp8", 2, 1), ("ring-tp", 4, 1), ("tiny-tp8", 4, 1), ("tiny-tp8-moe", 4, 1), ("tiny-tp8", 4, 0), ("tiny-tp8", 8, 1), ("tiny-tp8-moe", 8, 1), ("tiny-tp8", 8, 0)]
 
 
 @pytest.mark.parametrize("name,world,fused", CASES)

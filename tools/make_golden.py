@@ -27,7 +27,7 @@ import oracle  # noqa: E402
 from calm_b200 import modelgen as mg  # noqa: E402
 
 GOLDEN_SPECS = ["tiny-fp8", "tiny-fp16", "tiny-gf4", "tiny-qwen", "tiny-llama", "tiny-moe", "tiny-moe-gf4",
-                "tiny-gelu-clip", "tiny-ln", "tiny-lnpar", "tiny-mha", "tiny-bias2", "tiny-hd256", "tiny-tp8", "tiny-tp8-moe"]
+                "tiny-gelu-clip", "tiny-ln", "tiny-lnpar", "tiny-mha", "tiny-bias2", "tiny-hd256", "tiny-tp8", "tiny-tp8-moe", "ring-tp"]
 N_TOKENS = 24
 STEPS = [0, 1, 7, 15, 23]
 KVPOS = [0, 5, 23]

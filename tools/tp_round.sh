@@ -10,7 +10,7 @@ timeout 1200 python -m pytest tests/test_tp_gpu.py -q -rs -x ${KSEL:+-k "$KSEL"}
 run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $N "$@"; }
 run --steps 64 --warmup 8 > gpurun_out/bench_tp${N}_llama3-8b-fp8.jsonl 2> gpurun_out/bench_tp${N}_8b.err; tail -c 1500 gpurun_out/bench_tp${N}_llama3-8b-fp8.jsonl; tail -3 gpurun_out/bench_tp${N}_8b.err
 run --steps 32 --warmup 4 --workload llama3-70b-fp8 > gpurun_out/bench_tp${N}_llama3-70b-fp8.jsonl 2> gpurun_out/bench_tp${N}_70b.err; tail -c 1500 gpurun_out/bench_tp${N}_llama3-70b-fp8.jsonl; tail -3 gpurun_out/bench_tp${N}_70b.err
-if [ "$N" = "2" ]; then
+if [ "$N" = "2" ] && [ -n "$EXTRA" ]; then
   run --steps 64 --warmup 8 --parallel replicas > gpurun_out/bench_replicas${N}_llama3-8b-fp8.jsonl 2>> gpurun_out/bench_tp${N}_8b.err; tail -c 600 gpurun_out/bench_replicas${N}_llama3-8b-fp8.jsonl
   run --steps 32 --warmup 4 --workload mixtral-8x7b-fp8 > gpurun_out/bench_tp${N}_mixtral-8x7b-fp8.jsonl 2> gpurun_out/bench_tp${N}_mx.err; tail -c 800 gpurun_out/bench_tp${N}_mixtral-8x7b-fp8.jsonl; tail -3 gpurun_out/bench_tp${N}_mx.err
 fi
