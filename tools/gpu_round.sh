@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 set -x
-timeout 1500 python -m pytest tests -q -m gpu -rs > gpurun_out/pytest_gpu_full.log 2>&1; grep -v "^# CUDA" gpurun_out/pytest_gpu_full.log | tail -8
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v "^# CUDA" | tail -2
-timeout 600 python bench.py --workload llama3-70b-fp8 --steps 32 --warmup 4 --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_llama3-70b-fp8.jsonl 2> gpurun_out/bench_70b.err; tail -c 900 gpurun_out/bench_llama3-70b-fp8.jsonl; tail -2 gpurun_out/bench_70b.err
+timeout 600 python tools/sweep.py --steps 64 --set base --set "CALM_B200_RING_QKV=1" --set "CALM_B200_RING_QKV=2" > gpurun_out/sweep_qkv.jsonl 2> gpurun_out/sweep_qkv.err
+cat gpurun_out/sweep_qkv.jsonl | cut -c1-700; tail -3 gpurun_out/sweep_qkv.err
+CALM_B200_RING_QKV=1 timeout 300 python -m pytest tests -q -m gpu -x -k "golden or ring_fed or full_size" 2>&1 | tail -3
