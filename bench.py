@@ -401,6 +401,7 @@ def main():
             tensors = None
         except Exception as e:
             out["ref_cuda"] = {"unavailable": str(e)}
+            tensors = None
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
