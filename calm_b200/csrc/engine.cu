@@ -61,8 +61,6 @@ struct Engine {
 	// TMA-ring matvec kernels (ring.cuh): slots per warp / CTAs per SM for FFN-up and for wo / w2; u = 512-byte units per row and chunk (0: not used)
 	int ring_up_ns = 2, ring_up_cps = 2, ring_res_ns = 2, ring_res_warps = 16; // measured: 16 consuming warps per SM are needed (profiles/r02_sweep_ring_*.jsonl)
 	int ring_up_u = 0, ring_wo_u = 0, ring_down_u = 0, ring_wo_s = 1, ring_down_s = 1;
-	int ring_qkv_u = 0, grid_qkv_ring = 0; // q/k/v ring-fed (one 8-warp CTA per SM)
-	size_t smem_qkv_ring = 0;
 	int grid_up_ring = 0, grid_wo_ring = 0, grid_down_ring = 0;
 	size_t smem_up_ring = 0, smem_wo_ring = 0, smem_down_ring = 0;
 	bool attn2_cluster = false; // ... with the CTAs of a unit as one thread-block cluster (slices folded through distributed shared memory)
@@ -562,9 +560,7 @@ int run_token(int mode) {
 			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln;
 			a.stamp = t.slot;
 			if (g.pf_kv && (l == 0 || !g.pf_down_qkv)) kv_prefix(a.pf, l); // later layers: requested by the previous w2 kernel
-			if (g.ring_qkv_u == 4) launch_pdl(k_qkv_ring<DBITS, KVT, 4, 2>, g.grid_qkv_ring, 256, g.smem_qkv_ring, a);
-			else if (g.ring_qkv_u == 2) launch_pdl(k_qkv_ring<DBITS, KVT, 2, 2>, g.grid_qkv_ring, 256, g.smem_qkv_ring, a);
-			else launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, QKV_THREADS, g.smem_dim, a);
+			launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, QKV_THREADS, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -771,17 +767,6 @@ void make_plan() {
 	const bool ring_res_on = ring_ok && (g.tp_world == 1 || g.tp_fused) /* the ring kernels carry the in-kernel exchange too */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) &&
 	                         DBITS != 4; // gf4 rows are half as long in bytes: one-chunk K-slices fold twice as often and the SIMT decode is issue-bound (measured slower)
 	auto chunk_units = [](size_t rowbytes) { return rowbytes % 2048 == 0 ? 4 : (rowbytes % 1024 == 0 ? 2 : 0); };
-	g.ring_qkv_u = 0;
-	if (getenv("CALM_B200_RING_QKV") && atoi(getenv("CALM_B200_RING_QKV")) != 0) { // experiment: default off until measured
-		const int u = chunk_units((size_t)c.dim * DBITS / 8);
-		if (u) {
-			g.smem_qkv_ring = ring_smem_bytes<DBITS>(c.dim, u, 2, 8);
-			g.ring_qkv_u = u;
-			g.grid_qkv_ring = imin(g.sms * atoi(getenv("CALM_B200_RING_QKV")), (g.q_dim + 2 * g.kv_dim) / 2);
-			if (u == 4) smem_optin(k_qkv_ring<DBITS, KVT, 4, 2>, g.smem_qkv_ring);
-			else smem_optin(k_qkv_ring<DBITS, KVT, 2, 2>, g.smem_qkv_ring);
-		}
-	}
 	if (ring_up_on) {
 		const int u = chunk_units((size_t)c.dim * DBITS / 8);
 		if (u) {

@@ -238,63 +238,3 @@ __global__ void __launch_bounds__(512, 1) k_matres_ring(const MatResArgs a, cons
 	stamp_end(a.stamp);
 }
 
-// ------------------------------------------------------------------------------------------------
-// q/k/v (reference infer.c:360-381): task = one row pair of the concatenated [wq; wk; wv], whole rows; epilogue = k_qkv's
-// (bias, clip, RoPE from k_embed's table, q vector / KV-cache append).  One CTA of 8 warps per SM: half the register file
-// and the shared memory k_attn2 needs stay free, so the attention CTAs still become resident (and request their KV slices)
-// while this kernel runs.
-
-template <int DBITS, typename KVT, int U, int NS>
-__global__ void __launch_bounds__(256, 2) k_qkv_ring(const QkvArgs<KVT> a) {
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-	__shared__ RingCtl ctl;
-	float* red = reinterpret_cast<float*>(smem_raw);
-	float* xs = red + 32;
-	unsigned char* ring = smem_raw + (((size_t)(32 + xs_floats<DBITS>(a.dim)) * sizeof(float) + 127) & ~(size_t)127);
-	const size_t rowbytes = (size_t)a.dim * DBITS / 8;
-	const int cpt = (int)(rowbytes / (U * 512));
-	const int npairs = (a.q_dim + 2 * a.kv_dim) / 2;
-	const int p_lo = (int)(((long long)blockIdx.x * npairs) / gridDim.x), p_hi = (int)(((long long)(blockIdx.x + 1) * npairs) / gridDim.x);
-	pdl_launch_next();
-	ring_init<NS>(&ctl, p_lo);
-	float post = 1.f;
-	int kv_pos = 0;
-	auto rows = [&](int p, const unsigned char*& rp0, const unsigned char*& rp1, int& chunk0) {
-		const int j = 2 * p; // row in the concatenated [wq; wk; wv]
-		const void* w;
-		int k;
-		if (j < a.q_dim) w = a.wq, k = j;
-		else if (j < a.q_dim + a.kv_dim) w = a.wk, k = j - a.q_dim;
-		else w = a.wv, k = j - a.q_dim - a.kv_dim;
-		rp0 = reinterpret_cast<const unsigned char*>(w) + (size_t)k * rowbytes, rp1 = rp0 + rowbytes, chunk0 = 0;
-	};
-	auto done = [&](int p, float v0, float v1) {
-		if ((threadIdx.x & 31) != 0) return;
-		const int j = 2 * p;
-		v0 *= post, v1 *= post;
-		if (a.bias) v0 += a.bias[j], v1 += a.bias[j + 1];
-		v0 = fminf(fmaxf(v0, -a.clip), a.clip), v1 = fminf(fmaxf(v1, -a.clip), a.clip);
-		if (j < a.q_dim + a.kv_dim) { // rotate q and k (reference infer.c:223-236); angles from k_embed's table
-			const float2 cs = a.rope_cs[(j % a.head_dim) >> 1];
-			const float r0 = v0 * cs.x - v1 * cs.y, r1 = v0 * cs.y + v1 * cs.x;
-			v0 = r0, v1 = r1;
-		}
-		if (j < a.q_dim) {
-			a.q_out[j] = v0, a.q_out[j + 1] = v1;
-		} else {
-			const int k = j < a.q_dim + a.kv_dim ? j - a.q_dim : j - a.q_dim - a.kv_dim;
-			KVT* c = (j < a.q_dim + a.kv_dim) ? a.kc : a.vc;
-			KVT* dst = c + ((size_t)(k / a.head_dim) * a.seq_len + kv_pos) * a.head_dim + k % a.head_dim;
-			kv_store(dst, v0);
-			kv_store(dst + 1, v1);
-		}
-	};
-	RingWarp<DBITS, U, NS, decltype(rows), decltype(done)> rw(&ctl, ring, p_hi, cpt, rows, done);
-	rw.issue_prologue();
-	pdl_wait_prev();
-	stamp_begin(a.stamp);
-	post = stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, blockIdx.x == 0 ? a.xb_out : nullptr);
-	kv_pos = a.tp->kv_pos;
-	rw.consume_all(reinterpret_cast<const float4*>(xs));
-	stamp_end(a.stamp);
-}
