@@ -331,17 +331,20 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 			mls[s][h][1] = s == split ? myrec[h * REC + HD + 1] : attn_cell_wait(c + 1, epoch, a.err);
 		}
 		__syncthreads();
-		if (tid < HG) {
+		__shared__ float cfs[ATTN2_MAXB + 4][HG]; // exp(m_s - M): one exponential per (slice, head), in parallel
+		for (int i = tid; i < nsplit * HG; i += ATTN_THREADS) {
+			const int s = i / HG, h = i % HG;
 			float M = -FLT_MAX;
-			for (int s = 0; s < nsplit; ++s) M = fmaxf(M, mls[s][tid][0]);
+			for (int s2 = 0; s2 < nsplit; ++s2) M = fmaxf(M, mls[s2][h][0]);
+			cfs[s][h] = expf(mls[s][h][0] - M);
+		}
+		__syncthreads();
+		if (tid < HG) {
 			float L = 0.f;
-			for (int s = 0; s < nsplit; ++s) {
-				const float c = expf(mls[s][tid][0] - M);
-				L = fmaf(mls[s][tid][1], c, L);
-				mls[s][tid][0] = c;
-			}
+			for (int s = 0; s < nsplit; ++s) L = fmaf(mls[s][tid][1], cfs[s][tid], L); // slice order: deterministic
 			invl[tid] = 1.0f / L;
 		}
+		for (int i = tid; i < nsplit * HG; i += ATTN_THREADS) mls[i / HG][i % HG][0] = cfs[i / HG][i % HG]; // the output loop reads the coefficient from mls
 		__syncthreads();
 		ATTN_DBG(6);
 		// CTA `split` normalises outputs [split * per, (split + 1) * per): 8 adjacent lanes share an output, each sums every 8th slice

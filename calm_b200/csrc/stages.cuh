@@ -467,19 +467,24 @@ __device__ __forceinline__ void attn_cta_merge(const AttnArgs& a, int HG, int h0
 		}
 	}
 	__syncthreads();
+	// per (warp, head) rescaling coefficients once (nwarps * HG exponentials instead of nwarps per element)
+	__shared__ float s_coef[16][8], s_mn[8];
+	if ((int)threadIdx.x < nwarps * HG) {
+		const int w = threadIdx.x / HG, h = threadIdx.x % HG;
+		float mn = -FLT_MAX;
+		for (int w2 = 0; w2 < nwarps; ++w2) mn = fmaxf(mn, scratch[((size_t)w2 * HG + h) * rec + hd]);
+		s_coef[w][h] = expf(scratch[((size_t)w * HG + h) * rec + hd] - mn);
+		if (w == 0) s_mn[h] = mn;
+	}
+	__syncthreads();
 	for (int idx = threadIdx.x; idx < HG * rec; idx += blockDim.x) {
 		int h = idx / rec, e = idx % rec;
-		float mn = -FLT_MAX;
-		for (int w = 0; w < nwarps; ++w) mn = fmaxf(mn, scratch[((size_t)w * HG + h) * rec + hd]);
 		float v;
 		if (e == hd) {
-			v = mn;
+			v = s_mn[h];
 		} else {
 			v = 0.f;
-			for (int w = 0; w < nwarps; ++w) {
-				const float* r = scratch + ((size_t)w * HG + h) * rec;
-				v += r[e] * expf(r[hd] - mn); // e == hd+1 merges the sums the same way
-			}
+			for (int w = 0; w < nwarps; ++w) v = fmaf(scratch[((size_t)w * HG + h) * rec + e], s_coef[w][h], v); // e == hd+1 merges the sums the same way
 		}
 		dst[idx] = v;
 	}
