@@ -28,6 +28,8 @@
 #define RING_MAX_PAIRS 48 // row pairs per CTA when K-slices are folded through shared memory
 #define RING_MAX_SLICES 32
 
+__device__ int d_ring_l2_hint = 1; // 1: weights are requested with L2::evict_first (read once per token); 0: default policy (experiments)
+
 struct RingCtl {
 	uint64_t bar[RING_MAX_WARPS][RING_MAX_NS];
 	int slot_task[RING_MAX_WARPS][RING_MAX_NS];
@@ -62,7 +64,7 @@ struct RingWarp {
 	__device__ __forceinline__ RingWarp(RingCtl* c, unsigned char* ring_base, int t_hi_, int S_, RowsFn r, DoneFn d)
 	    : ctl(c), warp(threadIdx.x >> 5), lane(threadIdx.x & 31), t_hi(t_hi_), S(S_), rows(r), done(d) {
 		ring = ring_base + (size_t)warp * NS * 2 * CH;
-		policy = l2_policy_evict_first();
+		policy = d_ring_l2_hint ? l2_policy_evict_first() : 0;
 		cur_piece = S; // forces a task grab
 	}
 
@@ -86,8 +88,13 @@ struct RingWarp {
 			ctl->slot_task[warp][slot] = cur_task, ctl->slot_piece[warp][slot] = cur_piece;
 			uint64_t* bar = &ctl->bar[warp][slot];
 			mbar_expect_tx(bar, 2 * CH);
-			tma_load_1d_hint(ring + (size_t)slot * 2 * CH, rp0 + off, CH, bar, policy);
-			tma_load_1d_hint(ring + (size_t)slot * 2 * CH + CH, rp1 + off, CH, bar, policy);
+			if (policy) {
+				tma_load_1d_hint(ring + (size_t)slot * 2 * CH, rp0 + off, CH, bar, policy);
+				tma_load_1d_hint(ring + (size_t)slot * 2 * CH + CH, rp1 + off, CH, bar, policy);
+			} else {
+				tma_load_1d(ring + (size_t)slot * 2 * CH, rp0 + off, CH, bar);
+				tma_load_1d(ring + (size_t)slot * 2 * CH + CH, rp1 + off, CH, bar);
+			}
 		}
 		++issued, ++cur_piece;
 	}

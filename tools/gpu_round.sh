@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
 set -x
-timeout 900 python -m pytest tests -q -m gpu -x -k "golden or long_context or fp8_kv or full_size or rolling or prefill_matches" 2>&1 | grep -v "^# CUDA" | tail -3
-timeout 600 python tools/sweep.py --steps 64 --set base > gpurun_out/sweep_attn_merge.jsonl 2> gpurun_out/sweep.err
-cat gpurun_out/sweep_attn_merge.jsonl | cut -c1-700; tail -3 gpurun_out/sweep.err
+timeout 600 python tools/sweep.py --steps 64 --set base --set "CALM_B200_RING_HINT=0" --set "CALM_B200_EARLY=0" --set base > gpurun_out/sweep_hint.jsonl 2> gpurun_out/sweep.err
+cat gpurun_out/sweep_hint.jsonl | cut -c1-330; tail -3 gpurun_out/sweep.err
