@@ -761,8 +761,8 @@ void make_plan() {
 	g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
 	// TMA-ring kernels for the dense single-GPU stages whose rows are whole 1 KB / 2 KB chunks (ring.cuh)
 	g.ring_up_u = g.ring_wo_u = g.ring_down_u = 0;
-	if (getenv("CALM_B200_RING_HINT")) {
-		const int hint = atoi(getenv("CALM_B200_RING_HINT"));
+	{ // weights are read once per token: L2::evict_first on the ring's bulk copies measured 2 % faster than the default policy
+		const int hint = getenv("CALM_B200_RING_HINT") ? atoi(getenv("CALM_B200_RING_HINT")) : 1;
 		CUDA_CHECK(cudaMemcpyToSymbol(d_ring_l2_hint, &hint, sizeof(int)));
 	}
 	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_warps); // 0 slots: stage not ring-fed
