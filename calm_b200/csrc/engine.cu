@@ -788,6 +788,7 @@ void make_plan() {
 		auto plan_res = [&](int n, int& u_out, int& s_out, int& grid_out, size_t& smem_out) {
 			const size_t rowbytes = (size_t)n * DBITS / 8;
 			int u = chunk_units(rowbytes);
+			if (u == 4 && getenv("CALM_B200_RING_RES_U") && atoi(getenv("CALM_B200_RING_RES_U")) == 2) u = 2; // (experiments) 1 KB chunks
 			if (!u) return;
 			size_t smem = ring_smem_bytes<DBITS>(n, u, g.ring_res_ns, g.ring_res_warps);
 			if (smem > 220 * 1024 && u == 4) u = 2, smem = ring_smem_bytes<DBITS>(n, u, g.ring_res_ns, g.ring_res_warps); // long activation vectors (70B w2: 112 KB): 1 KB chunks
