@@ -115,7 +115,6 @@ struct Engine {
 	bool use_graph = true;
 	bool use_pdl = true;
 	int carveout = -1;   // cudaFuncAttributePreferredSharedMemoryCarveout applied to every kernel of the token, or -1
-	int early = 1; // what the matvec kernels do ahead of the PDL wait (stages.cuh EARLY): 0 nothing, 1 L2 prefetch, 2 = 1 + k_ffn_up with 8 KB in flight per warp
 
 	// profiling (perf_cuda): in-kernel %globaltimer stamps per launch of the production graph (stages.cuh stamp_begin/end)
 	bool perf = false;
@@ -516,7 +515,7 @@ static void pf_up_prefix(Prefetch& pf, int slot, const void* w1, const void* w3,
 }
 
 // mode: 0 kv only, 1 logits -> host, 2 logits -> device + advance (greedy loop), 3 logits -> host + argmax, 4 logits -> device + min-p sample + advance
-template <int DBITS, typename KVT, int EARLY>
+template <int DBITS, typename KVT>
 int run_token(int mode) {
 	const Config& c = g.cfg;
 	const Weights& w = g.w;
@@ -560,7 +559,7 @@ int run_token(int mode) {
 			a.eps = c.norm_eps, a.clip = c.qkv_clip, a.ln = c.norm_ln;
 			a.stamp = t.slot;
 			if (g.pf_kv && (l == 0 || !g.pf_down_qkv)) kv_prefix(a.pf, l); // later layers: requested by the previous w2 kernel
-			launch_pdl(k_qkv<DBITS, KVT, EARLY>, g.grid_qkv, QKV_THREADS, g.smem_dim, a);
+			launch_pdl(k_qkv<DBITS, KVT>, g.grid_qkv, QKV_THREADS, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -588,7 +587,7 @@ int run_token(int mode) {
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l); // partial over this rank's heads, summed over the ranks in the kernel
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
 			if (g.ring_wo_u) ring_res_dispatch<DBITS>(a, g.ring_wo_u, g.ring_wo_s, g.grid_wo_ring, g.smem_wo_ring, false);
-			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_wo, 256, g.smem_qdim, a);
+			else launch_pdl(k_matres<DBITS>, g.grid_wo, 256, g.smem_qdim, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
@@ -608,7 +607,7 @@ int run_token(int mode) {
 			if (dense && g.pf_up_down) a.pf.p[0] = w.w2[l], a.pf.bytes[0] = (g.pf_up_down < down_bytes ? g.pf_up_down : down_bytes) & ~(size_t)15;
 			bool done = false;
 			if (g.ring_up_u) ring_up_dispatch<DBITS>(a, false), done = true;
-			if (!done) launch_pdl(k_ffn_up<DBITS, EARLY>, g.grid_up, 256, g.smem_dim, a);
+			if (!done) launch_pdl(k_ffn_up<DBITS>, g.grid_up, 256, g.smem_dim, a);
 			++nl;
 		}
 		{
@@ -624,7 +623,7 @@ int run_token(int mode) {
 			if (g.tp_fused) tp_fill(a.tpx, 2 * l + 1); // partial over this rank's FFN rows
 			else if (g.tp_world > 1) a.y = g.xpart, a.accumulate = 0;
 			if (g.ring_down_u) ring_res_dispatch<DBITS>(a, g.ring_down_u, g.ring_down_s, g.grid_down_ring, g.smem_down_ring, false);
-			else launch_pdl(k_matres<DBITS, EARLY>, g.grid_down, 256, g.smem_hidden, a);
+			else launch_pdl(k_matres<DBITS>, g.grid_down, 256, g.smem_hidden, a);
 			++nl;
 			if (g.tp_world > 1 && !g.tp_fused) {
 				tp_allreduce(g.xpart, dim);
@@ -729,7 +728,7 @@ void tp_shard_model() {
 }
 
 // Fix grid sizes and shared-memory opt-ins for this model (called once from prepare_cuda).
-template <int DBITS, typename KVT, int EARLY>
+template <int DBITS, typename KVT>
 void make_plan() {
 	const Config& c = g.cfg;
 	g.smem_dim = xs_bytes<DBITS>(c.dim);
@@ -737,8 +736,8 @@ void make_plan() {
 	g.smem_hidden = xs_bytes<DBITS>(c.hidden_dim);
 	size_t smem_res = g.smem_qdim > g.smem_hidden ? g.smem_qdim : g.smem_hidden;
 	if (smem_res > 227 * 1024 || g.smem_dim > 227 * 1024) CALM_FATAL("activation vector does not fit in shared memory (dim %d, hidden %d)", c.dim, c.hidden_dim);
-	smem_optin(k_qkv<DBITS, KVT, EARLY>, g.smem_dim), smem_optin(k_ffn_up<DBITS, EARLY>, g.smem_dim), smem_optin(k_output<DBITS>, g.smem_dim);
-	smem_optin(k_matres<DBITS, EARLY>, smem_res); // ONE attribute per kernel: the larger of its two launch shapes (wo, w2)
+	smem_optin(k_qkv<DBITS, KVT>, g.smem_dim), smem_optin(k_ffn_up<DBITS>, g.smem_dim), smem_optin(k_output<DBITS>, g.smem_dim);
+	smem_optin(k_matres<DBITS>, smem_res); // ONE attribute per kernel: the larger of its two launch shapes (wo, w2)
 	{
 		// k_attn2 when the shape is instantiated and the CTA's share of the context fits in shared memory
 		g.attn_nbmax = cdiv(cdiv(c.seq_len, ATTN2_BP), g.attn_nsplit);
@@ -750,15 +749,15 @@ void make_plan() {
 		aa.head_dim = c.head_dim, aa.nsplit = g.attn_nsplit;
 		dispatch_attn<KVT>(aa, c.n_kv_heads * g.attn_qgroups, nullptr);
 	}
-	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT, EARLY>, QKV_THREADS, g.smem_dim));
-	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_qdim));
-	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS, EARLY>, 256, g.smem_hidden));
+	g.grid_qkv = balanced_grid(cdiv((g.q_dim + 2 * g.kv_dim) / 2, 8), max_ctas(k_qkv<DBITS, KVT>, QKV_THREADS, g.smem_dim));
+	g.grid_wo = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_qdim));
+	g.grid_down = balanced_grid(cdiv(c.dim / 2, 8), max_ctas(k_matres<DBITS>, 256, g.smem_hidden));
 	if (g.tp_fused) { // the in-kernel exchange needs co-resident grids (they are: balanced_grid stays under the cap) within its tables
 		for (int grid : {g.grid_wo, g.grid_down})
 			if (cdiv(c.dim / 2, grid * 8) > TP_MAX_ITERS) CALM_FATAL("tensor parallelism: grid %d outside the exchange tables for dim %d", grid, c.dim);
 	}
 	// (measured: for the long FFN-up stage a full 4-CTA/SM grid with uneven rounds beats a balanced 3-CTA/SM one)
-	g.grid_up = imin(max_ctas(k_ffn_up<DBITS, EARLY>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
+	g.grid_up = imin(max_ctas(k_ffn_up<DBITS>, 256, g.smem_dim), cdiv(g.nact * c.hidden_dim, 8));
 	// TMA-ring kernels for the dense single-GPU stages whose rows are whole 1 KB / 2 KB chunks (ring.cuh)
 	g.ring_up_u = g.ring_wo_u = g.ring_down_u = 0;
 	{ // weights are read once per token: L2::evict_first on the ring's bulk copies measured 2 % faster than the default policy
@@ -827,20 +826,12 @@ void make_plan() {
 
 template <int DBITS>
 void make_plan_kv() {
-	switch (g.early) {
-	case 1: g.kvbits == 8 ? make_plan<DBITS, uint8_t, 1>() : make_plan<DBITS, __half, 1>(); break;
-	case 2: g.kvbits == 8 ? make_plan<DBITS, uint8_t, 2>() : make_plan<DBITS, __half, 2>(); break;
-	default: g.kvbits == 8 ? make_plan<DBITS, uint8_t, 0>() : make_plan<DBITS, __half, 0>(); break;
-	}
+	g.kvbits == 8 ? make_plan<DBITS, uint8_t>() : make_plan<DBITS, __half>();
 }
 
 template <int DBITS>
 int run_token_kv(int mode) {
-	switch (g.early) {
-	case 1: return g.kvbits == 8 ? run_token<DBITS, uint8_t, 1>(mode) : run_token<DBITS, __half, 1>(mode);
-	case 2: return g.kvbits == 8 ? run_token<DBITS, uint8_t, 2>(mode) : run_token<DBITS, __half, 2>(mode);
-	default: return g.kvbits == 8 ? run_token<DBITS, uint8_t, 0>(mode) : run_token<DBITS, __half, 0>(mode);
-	}
+	return g.kvbits == 8 ? run_token<DBITS, uint8_t>(mode) : run_token<DBITS, __half>(mode);
 }
 
 int run_token_any(int mode) {
@@ -956,9 +947,7 @@ extern "C" void prepare_cuda(struct Transformer* transformer) {
 	g.q_dim = q_dim, g.kv_dim = kv_dim, g.kv_mul = g.cfg.n_heads / g.cfg.n_kv_heads;
 	g.use_graph = !(getenv("CALM_B200_GRAPH") && atoi(getenv("CALM_B200_GRAPH")) == 0);
 	g.use_pdl = !(getenv("CALM_B200_PDL") && atoi(getenv("CALM_B200_PDL")) == 0);
-	if (getenv("CALM_B200_EARLY")) g.early = atoi(getenv("CALM_B200_EARLY"));
 	g.carveout = getenv("CALM_B200_CARVEOUT") ? atoi(getenv("CALM_B200_CARVEOUT")) : -1;
-	if (g.early < 0 || g.early > 2) g.early = 0;
 	g.debug = getenv("CALM_B200_DEBUG") && atoi(getenv("CALM_B200_DEBUG"));
 	if (g.debug) g.use_graph = false;
 	g.perf = (getenv("CALM_B200_PERF") && atoi(getenv("CALM_B200_PERF"))) || getenv("CUDA_INJECTION64_PATH");

@@ -292,16 +292,14 @@ struct QkvArgs {
 	Prefetch pf;
 };
 
-// EARLY: what a warp does about its first row pair BEFORE waiting for the previous kernel and staging the activations
-// (weights are immutable, so this is always legal): 0 nothing; 1 ask the L2 for the rows (cp.async.bulk.prefetch.L2,
-// no registers); 2 the same, and k_ffn_up keeps 8 vectors per row in flight at 2 CTAs per SM instead of 4 at 3.
-// (Issuing the first loads into registers instead was measured 25 % slower: 32 more live registers across the
-// staging cost a CTA per SM or spills.)
+// Before waiting for the previous kernel a warp asks the L2 for its first row pair (cp.async.bulk.prefetch.L2: no registers;
+// weights are immutable, so this is always legal).  (Issuing the first loads into registers instead measured 25 % slower:
+// 32 more live registers across the staging cost a CTA per SM.)
 #define QKV_THREADS 256
 // One warp per row pair (the whole 2 x rowbytes pair is requested in one batch), 3 CTAs per SM.  (A one-CTA-per-SM form with
 // equal contiguous shares, meant to leave half the register file to an early attention CTA, measured 2.8 us slower per
 // launch: most warps then need a second DRAM round trip -- profiles/README.md, round 2.)
-template <int DBITS, typename KVT, int EARLY>
+template <int DBITS, typename KVT>
 __global__ void __launch_bounds__(QKV_THREADS, 3) k_qkv(const QkvArgs<KVT> a) {
 	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
@@ -325,7 +323,7 @@ __global__ void __launch_bounds__(QKV_THREADS, 3) k_qkv(const QkvArgs<KVT> a) {
 	};
 	// weights first: they do not depend on the previous kernel, so their latency hides its tail and the staging of x
 	const int p0 = blockIdx.x * nwarps + warp;
-	if (EARLY != 0 && p0 < npairs && lane == 0) {
+	if (p0 < npairs && lane == 0) {
 		const uint4* rp[2];
 		int j, k;
 		rows_of(p0, rp, j, k);
@@ -896,7 +894,7 @@ struct MatResArgs {
 	Prefetch pf;
 };
 
-template <int DBITS, int EARLY>
+template <int DBITS>
 __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
@@ -909,7 +907,7 @@ __global__ void __launch_bounds__(256, 2) k_matres(const MatResArgs a) {
 	const bool long_rows = nvec >= 32 * 8 && DBITS != 4; // a warp has ONE pair and is latency-bound: 8 KB in flight per warp (wo: the whole pair at once)
 	// dense models: request the first row pair before waiting for the previous kernel (the expert of a MoE layer is its result)
 	const int p0 = blockIdx.x * nwarps + warp;
-	const bool early = EARLY != 0 && a.sel == nullptr && p0 < a.d / 2;
+	const bool early = a.sel == nullptr && p0 < a.d / 2;
 	if (early && lane == 0) {
 		const uint4* r0 = reinterpret_cast<const uint4*>(a.w) + (size_t)(2 * p0) * nvec;
 		l2_prefetch_row(r0, nvec * 16), l2_prefetch_row(r0 + nvec, nvec * 16);
@@ -976,8 +974,8 @@ struct FfnUpArgs {
 	size_t expert_stride; // 16-byte vectors between experts in w1 / w3 (tensor parallelism: a rank's rows are a slice of every expert)
 };
 
-template <int DBITS, int EARLY>
-__global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpArgs a) {
+template <int DBITS>
+__global__ void __launch_bounds__(256, 3) k_ffn_up(const FfnUpArgs a) {
 	pdl_launch_next();
 	extern __shared__ __align__(16) float smem[];
 	__shared__ float glog[64];
@@ -989,7 +987,7 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpA
 	const float4* xs4 = reinterpret_cast<const float4*>(xs);
 	// dense models: the first (w1, w3) row pair is requested before the previous kernel has finished and x is staged
 	const int p0 = blockIdx.x * nwarps + warp;
-	const bool early = EARLY != 0 && a.n_experts == 0 && p0 < a.hidden;
+	const bool early = a.n_experts == 0 && p0 < a.hidden;
 	if (early && lane == 0) {
 		l2_prefetch_row(reinterpret_cast<const uint4*>(a.w1) + (size_t)p0 * nvec, nvec * 16);
 		l2_prefetch_row(reinterpret_cast<const uint4*>(a.w3) + (size_t)p0 * nvec, nvec * 16);
@@ -1034,10 +1032,7 @@ __global__ void __launch_bounds__(256, EARLY == 2 ? 2 : 3) k_ffn_up(const FfnUpA
 		size_t off = (a.n_experts ? (size_t)ssel.expert[e] * esize : 0) + (size_t)i * nvec;
 		const uint4* rp[2] = {reinterpret_cast<const uint4*>(a.w1) + off, reinterpret_cast<const uint4*>(a.w3) + off};
 		float v[2];
-		if constexpr (EARLY == 2 && DBITS != 4) // the whole row pair in one round trip: 8 KB per warp, 2 CTAs per SM
-			warp_dot_rows<DBITS, 2, 8>(rp, nvec, xs4, v);
-		else
-			warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
+		warp_dot_rows<DBITS, 2, 4>(rp, nvec, xs4, v);
 		if (lane == 0) {
 			const float u1 = v[0] * post, u3 = v[1] * post;
 			a.hb[p] = (a.gelu ? act_gelu(u1) : act_silu(u1)) * u3;
