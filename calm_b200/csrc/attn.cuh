@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	};
 	for (int sb = (warp * G + grp) * P; sb - grp * P < nslots; sb += SC * STEP) { // warp-uniform trip count (full-warp shuffles inside)
 		float sc[SC];
-		bool val[SC];
+		bool val[SC], fast[SC];
 #pragma unroll
 		for (int c = 0; c < SC; ++c) {
 			const int s0 = sb + c * STEP;
@@ -178,17 +178,25 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 			if (inr) slot_of(s0, j, o, t0);
 			if (inr) mbar_wait(&bars[j], 0);
 			if (s0 == 0) ATTN_DBG(3);
+			// the common case for a whole warp -- P cached positions, none of them written during this token -- needs no per-position tests
+			fast[c] = __all_sync(0xffffffffu, inr && t0 + P <= kv_len && (kv_pos < t0 || kv_pos >= t0 + P) && t0 >= kv_sink);
 			float part[NC]; // combo h * P + i: partial dot product of this lane's 8 dims
 			{
 				float kf[P][8];
+				if (fast[c]) {
+					const KVT* kp = Ks + ((size_t)j * ATTN2_BP + o) * HD + li * 8;
 #pragma unroll
-				for (int i = 0; i < P; ++i) {
-					const int t = t0 + i;
-					raw_t kr = KvRaw<KVT>::zero();
-					if (inr && t < kv_len)
-						kr = (t == kv_pos || t < kv_sink) ? KvRaw<KVT>::load(kglob + (size_t)t * HD + li * 8) // written during this token: not in the early copy
-						                                  : *reinterpret_cast<const raw_t*>(Ks + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
-					KvRaw<KVT>::unpack(kr, kf[i]);
+					for (int i = 0; i < P; ++i) KvRaw<KVT>::unpack(*reinterpret_cast<const raw_t*>(kp + i * HD), kf[i]);
+				} else {
+#pragma unroll
+					for (int i = 0; i < P; ++i) {
+						const int t = t0 + i;
+						raw_t kr = KvRaw<KVT>::zero();
+						if (inr && t < kv_len)
+							kr = (t == kv_pos || t < kv_sink) ? KvRaw<KVT>::load(kglob + (size_t)t * HD + li * 8) // written during this token: not in the early copy
+							                                  : *reinterpret_cast<const raw_t*>(Ks + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
+						KvRaw<KVT>::unpack(kr, kf[i]);
+					}
 				}
 #pragma unroll
 				for (int h = 0; h < HG; ++h) {
@@ -244,14 +252,20 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 			int j = 0, o = 0, t0 = 0;
 			if (inr) slot_of(s0, j, o, t0);
 			float vf[P][8];
+			if (fast[c]) {
+				const KVT* vp = Vs + ((size_t)j * ATTN2_BP + o) * HD + li * 8;
 #pragma unroll
-			for (int i = 0; i < P; ++i) {
-				const int t = t0 + i;
-				raw_t vr = KvRaw<KVT>::zero();
-				if (inr && t < kv_len)
-					vr = (t == kv_pos || t < kv_sink) ? KvRaw<KVT>::load(vglob + (size_t)t * HD + li * 8)
-					                                  : *reinterpret_cast<const raw_t*>(Vs + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
-				KvRaw<KVT>::unpack(vr, vf[i]);
+				for (int i = 0; i < P; ++i) KvRaw<KVT>::unpack(*reinterpret_cast<const raw_t*>(vp + i * HD), vf[i]);
+			} else {
+#pragma unroll
+				for (int i = 0; i < P; ++i) {
+					const int t = t0 + i;
+					raw_t vr = KvRaw<KVT>::zero();
+					if (inr && t < kv_len)
+						vr = (t == kv_pos || t < kv_sink) ? KvRaw<KVT>::load(vglob + (size_t)t * HD + li * 8)
+						                                  : *reinterpret_cast<const raw_t*>(Vs + ((size_t)j * ATTN2_BP + o + i) * HD + li * 8);
+					KvRaw<KVT>::unpack(vr, vf[i]);
+				}
 			}
 #pragma unroll
 			for (int h = 0; h < HG; ++h) {
