@@ -230,7 +230,11 @@ __device__ __forceinline__ uint2 ldg_stream8(const uint2* p) {
 // activation vector is staged in shared memory in a layout that makes the
 // matching reads conflict-free 16-byte loads: for vector v = 32*c + lane the
 // VW activations are stored as VW/4 float4 "quads", quad q at float4 index
-// (c*(VW/4) + q)*32 + lane.  xs_index() maps an activation index to that slot.
+// (c*(VW/4) + q)*32 + (lane ^ xs_swz(q)).  xs_index() maps an activation index to that slot.
+// The XOR makes the STAGING stores conflict-free too: consecutive threads stage consecutive float4s of x (coalesced
+// loads), i.e. the quads q = 0..Q-1 of one vector, whose slots are 512 bytes apart -- without the swizzle the 8 lanes of a
+// 16-byte store phase hit 8/Q bank groups (fp8: 4-way, gf4: 8-way conflicts: 1800 of the w2 kernel's cycles for the
+// 57 KB Llama-3 hidden vector, r02 ncu capture: 212 K store conflicts).  Readers XOR their lane with the same constant.
 
 template <int DBITS>
 struct WFmt;
@@ -248,11 +252,16 @@ struct WFmt<4> {
 };
 
 template <int DBITS>
+__host__ __device__ __forceinline__ constexpr int xs_swz(int q) { // lane permutation of quad q: 8 distinct 16-byte bank groups for the 8 lanes of a store phase
+	return (q * (8 / (WFmt<DBITS>::VW / 4))) & 31;
+}
+
+template <int DBITS>
 __device__ __forceinline__ int xs_index(int j) {
 	constexpr int VW = WFmt<DBITS>::VW, Q = VW / 4;
 	int v = j / VW, w = j % VW;
-	int c = v >> 5, lane = v & 31;
-	return (((c * Q + (w >> 2)) << 5) + lane) * 4 + (w & 3);
+	int c = v >> 5, lane = v & 31, q = w >> 2;
+	return (((c * Q + q) << 5) + (lane ^ xs_swz<DBITS>(q))) * 4 + (w & 3);
 }
 
 // number of floats of the staged activation vector (whole 32-vector chunks, zero padded)

@@ -767,8 +767,7 @@ void make_plan() {
 	if (const char* e = getenv("CALM_B200_RING")) sscanf(e, "%d,%d,%d,%d", &g.ring_up_ns, &g.ring_up_cps, &g.ring_res_ns, &g.ring_res_warps); // 0 slots: stage not ring-fed
 	const bool ring_ok = c.n_experts == 0; // MoE: the expert rows are known only after the router
 	const bool ring_up_on = ring_ok && g.ring_up_ns >= 2 && g.ring_up_ns <= RING_MAX_NS; // (row shards of w1 / w3 under tensor parallelism are fine)
-	const bool ring_res_on = ring_ok && (g.tp_world == 1 || g.tp_fused) /* the ring kernels carry the in-kernel exchange too */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16) &&
-	                         DBITS != 4; // gf4 rows are half as long in bytes: one-chunk K-slices fold twice as often and the SIMT decode is issue-bound (measured slower)
+	const bool ring_res_on = ring_ok && (g.tp_world == 1 || g.tp_fused) /* the ring kernels carry the in-kernel exchange too */ && g.ring_res_ns >= 2 && g.ring_res_ns <= RING_MAX_NS && (g.ring_res_warps == 8 || g.ring_res_warps == 16); // (gf4 too: 2.384 vs 2.467 ms per Mistral-7B token, profiles/r02_sweep_gf4_rows_per_slot.jsonl)
 	auto chunk_units = [](size_t rowbytes) { return rowbytes % 2048 == 0 ? 4 : (rowbytes % 1024 == 0 ? 2 : 0); };
 	if (ring_up_on) {
 		const int u = chunk_units((size_t)c.dim * DBITS / 8);

@@ -120,7 +120,7 @@ struct RingWarp {
 			}
 			const uint4* s0 = reinterpret_cast<const uint4*>(ring + (size_t)slot * 2 * CH);
 			const uint4* s1 = s0 + CH / 16;
-			const float4* xp = xs4 + (size_t)((chunk0 + piece) * U) * Q * 32 + lane; // chunk = U groups of 32 vectors
+			const float4* xp = xs4 + (size_t)((chunk0 + piece) * U) * Q * 32; // chunk = U groups of 32 vectors
 			uint4 w0[U], w1[U];
 #pragma unroll
 			for (int u = 0; u < U; ++u) w0[u] = s0[32 * u + lane], w1[u] = s1[32 * u + lane];
@@ -128,7 +128,7 @@ struct RingWarp {
 			for (int u = 0; u < U; ++u) {
 				float4 xv[Q];
 #pragma unroll
-				for (int q = 0; q < Q; ++q) xv[q] = xp[(u * Q + q) * 32];
+				for (int q = 0; q < Q; ++q) xv[q] = xp[(u * Q + q) * 32 + (lane ^ xs_swz<DBITS>(q))];
 				acc0 = dot_vec<DBITS>(w0[u], xv, acc0);
 				acc1 = dot_vec<DBITS>(w1[u], xv, acc1);
 			}

@@ -32,9 +32,9 @@ __device__ __forceinline__ void rows_consume(const uint4 (&w)[U][R], int v0, int
 		int v = v0 + 32 * u;
 		if (!CHECK || v < nvec) {
 			float4 xv[Q];
-			const float4* xp = xs4 + (size_t)(v >> 5) * Q * 32 + lane;
+			const float4* xp = xs4 + (size_t)(v >> 5) * Q * 32;
 #pragma unroll
-			for (int q = 0; q < Q; ++q) xv[q] = xp[q * 32];
+			for (int q = 0; q < Q; ++q) xv[q] = xp[q * 32 + (lane ^ xs_swz<DBITS>(q))];
 #pragma unroll
 			for (int r = 0; r < R; ++r) acc[r] = dot_vec<DBITS>(w[u][r], xv, acc[r]);
 		}
