@@ -272,6 +272,18 @@ __host__ __device__ __forceinline__ int xs_floats(int n) {
 	return ((nvec + 31) & ~31) * VW;
 }
 
+// gf4 only: behind the staged vector sit the group sums the decode needs, 3 * (x_8g + ... + x_8g+7) for every group g of 8
+// activations (one gf4 word), in plain order: lane l of 32-vector chunk c reads its vector's four sums as ONE float4 at
+// index 32 c + l.  They used to be recomputed from the activations by every warp for every row pair (7 FADD per word).
+template <int DBITS>
+__host__ __device__ __forceinline__ int xs_aux_floats(int n) {
+	return DBITS == 4 ? xs_floats<DBITS>(n) / 8 : 0;
+}
+template <int DBITS>
+__host__ __device__ __forceinline__ int xs_all_floats(int n) {
+	return xs_floats<DBITS>(n) + xs_aux_floats<DBITS>(n);
+}
+
 // e5m2 pair (two bytes) -> two floats.  An e5m2 byte is the high byte of a half
 // (reference infer.c:28-35, helpers.cuh:65-98), so a byte permute builds the half2.
 __device__ __forceinline__ float2 e5m2x2_lo(uint32_t w) {
@@ -292,12 +304,12 @@ __device__ __forceinline__ uint8_t float_to_e5m2(float f) {
 	return (uint8_t)__nv_cvt_float_to_fp8(f, __NV_SATFINITE, __NV_E5M2);
 }
 
-// Dot of one 16-byte weight vector with its VW activations (already in registers).
+// Dot of one 16-byte weight vector with its VW activations (already in registers); g3 = the vector's four group sums (gf4; unused otherwise).
 template <int DBITS>
-__device__ __forceinline__ float dot_vec(const uint4& w, const float4 (&xv)[WFmt<DBITS>::VW / 4], float acc);
+__device__ __forceinline__ float dot_vec(const uint4& w, const float4 (&xv)[WFmt<DBITS>::VW / 4], const float4& g3, float acc);
 
 template <>
-__device__ __forceinline__ float dot_vec<16>(const uint4& w, const float4 (&xv)[2], float acc) {
+__device__ __forceinline__ float dot_vec<16>(const uint4& w, const float4 (&xv)[2], const float4&, float acc) {
 	float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
 	float2 b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
 	float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.z));
@@ -323,7 +335,7 @@ __device__ __forceinline__ float dot_e5m2x4(uint32_t w, const float4& x, float a
 }
 
 template <>
-__device__ __forceinline__ float dot_vec<8>(const uint4& w, const float4 (&xv)[4], float acc) {
+__device__ __forceinline__ float dot_vec<8>(const uint4& w, const float4 (&xv)[4], const float4&, float acc) {
 	acc = dot_e5m2x4(w.x, xv[0], acc);
 	acc = dot_e5m2x4(w.y, xv[1], acc);
 	acc = dot_e5m2x4(w.z, xv[2], acc);
@@ -335,14 +347,14 @@ __device__ __forceinline__ float dot_vec<8>(const uint4& w, const float4 (&xv)[4
 // A code is dropped into the top mantissa bits of 1.0f (0x3F800000 | q << 20 == 1 + q/8, exact): one shift and
 // one logic op per weight, no int->float conversion.  With S = sum_k (1 + q_k/8) x_k and X = sum_k x_k:
 //   sum_k w_k x_k = (-s/4) (sum_k q_k x_k - 4 X) = (-s/4) (8 S - 12 X) = s (3 X - 2 S).
-// `xsum` = X of this group of 8 activations (computed once per vector and shared by all rows).
+// `x3` = 3 X of this group of 8 activations (staged once per vector by stage_vector, shared by all rows and warps).
 __device__ __forceinline__ float gf4_code(uint32_t w, int k) { // 1 + q_k / 8
 	const int sh = 8 + 3 * k - 20; // field k sits at bits 8+3k..10+3k; move it to bits 20..22
 	uint32_t f = sh >= 0 ? (w >> sh) : (w << -sh), r;
 	asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(f), "r"(0x00700000u), "r"(0x3F800000u)); // (f & mask) | one: a single LOP3
 	return __uint_as_float(r);
 }
-__device__ __forceinline__ float dot_gf4_word(uint32_t w, const float4& x0, const float4& x1, float xsum, float acc) {
+__device__ __forceinline__ float dot_gf4_word(uint32_t w, const float4& x0, const float4& x1, float x3, float acc) {
 	float S = gf4_code(w, 0) * x0.x;
 	S = fmaf(gf4_code(w, 1), x0.y, S);
 	S = fmaf(gf4_code(w, 2), x0.z, S);
@@ -352,20 +364,15 @@ __device__ __forceinline__ float dot_gf4_word(uint32_t w, const float4& x0, cons
 	S = fmaf(gf4_code(w, 6), x1.z, S);
 	S = fmaf(gf4_code(w, 7), x1.w, S);
 	const float sc = e5m2_to_float((uint8_t)(w & 0xff));
-	return fmaf(sc, fmaf(3.f, xsum, -2.f * S), acc);
+	return fmaf(sc, fmaf(-2.f, S, x3), acc);
 }
 
 template <>
-__device__ __forceinline__ float dot_vec<4>(const uint4& w, const float4 (&xv)[8], float acc) {
-	// group sums of the activations (the compiler keeps them across the rows that share xv)
-	const float s0 = ((xv[0].x + xv[0].y) + (xv[0].z + xv[0].w)) + ((xv[1].x + xv[1].y) + (xv[1].z + xv[1].w));
-	const float s1 = ((xv[2].x + xv[2].y) + (xv[2].z + xv[2].w)) + ((xv[3].x + xv[3].y) + (xv[3].z + xv[3].w));
-	const float s2 = ((xv[4].x + xv[4].y) + (xv[4].z + xv[4].w)) + ((xv[5].x + xv[5].y) + (xv[5].z + xv[5].w));
-	const float s3 = ((xv[6].x + xv[6].y) + (xv[6].z + xv[6].w)) + ((xv[7].x + xv[7].y) + (xv[7].z + xv[7].w));
-	acc = dot_gf4_word(w.x, xv[0], xv[1], s0, acc);
-	acc = dot_gf4_word(w.y, xv[2], xv[3], s1, acc);
-	acc = dot_gf4_word(w.z, xv[4], xv[5], s2, acc);
-	acc = dot_gf4_word(w.w, xv[6], xv[7], s3, acc);
+__device__ __forceinline__ float dot_vec<4>(const uint4& w, const float4 (&xv)[8], const float4& g3, float acc) {
+	acc = dot_gf4_word(w.x, xv[0], xv[1], g3.x, acc);
+	acc = dot_gf4_word(w.y, xv[2], xv[3], g3.y, acc);
+	acc = dot_gf4_word(w.z, xv[4], xv[5], g3.z, acc);
+	acc = dot_gf4_word(w.w, xv[6], xv[7], g3.w, acc);
 	return acc;
 }
 

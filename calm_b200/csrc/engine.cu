@@ -194,7 +194,7 @@ int balanced_grid(int units, int cap) {
 
 template <int DBITS>
 size_t xs_bytes(int n) {
-	return (size_t)(32 + xs_floats<DBITS>(n)) * sizeof(float);
+	return (size_t)(32 + xs_all_floats<DBITS>(n)) * sizeof(float);
 }
 
 

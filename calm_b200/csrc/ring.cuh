@@ -40,7 +40,7 @@ struct RingCtl {
 // shared memory of a ring kernel: [32 floats block-reduce][activation vector][ring: warps x NS x 2 rows x CH bytes]
 template <int DBITS>
 __host__ __device__ inline size_t ring_smem_bytes(int n, int u, int ns, int warps) {
-	size_t xs = ((size_t)(32 + xs_floats<DBITS>(n)) * sizeof(float) + 127) & ~(size_t)127;
+	size_t xs = ((size_t)(32 + xs_all_floats<DBITS>(n)) * sizeof(float) + 127) & ~(size_t)127;
 	return xs + (size_t)warps * ns * 2 * u * 512;
 }
 
@@ -106,7 +106,8 @@ struct RingWarp {
 		__syncwarp();
 	}
 
-	__device__ __forceinline__ void consume_all(const float4* __restrict__ xs4) {
+	__device__ __forceinline__ void consume_all(const float4* __restrict__ xs4, int n) { // n: length of the staged vector
+		const float4* xg4 = xs4 + (xs_floats<DBITS>(n) >> 2); // gf4: the group sums behind the vector (common.cuh xs_aux_floats)
 		constexpr int Q = WFmt<DBITS>::VW / 4;
 		float acc0 = 0.f, acc1 = 0.f;
 		while (consumed < issued) {
@@ -129,8 +130,10 @@ struct RingWarp {
 				float4 xv[Q];
 #pragma unroll
 				for (int q = 0; q < Q; ++q) xv[q] = xp[(u * Q + q) * 32 + (lane ^ xs_swz<DBITS>(q))];
-				acc0 = dot_vec<DBITS>(w0[u], xv, acc0);
-				acc1 = dot_vec<DBITS>(w1[u], xv, acc1);
+				float4 g3 = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (DBITS == 4) g3 = xg4[((chunk0 + piece) * U + u) * 32 + lane];
+				acc0 = dot_vec<DBITS>(w0[u], xv, g3, acc0);
+				acc1 = dot_vec<DBITS>(w1[u], xv, g3, acc1);
 			}
 			++consumed;
 			__syncwarp(); // every lane has read the slot (its values are in registers): the slot may be refilled
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(256, 2) k_ffn_up_ring(const FfnUpArgs a) {
 	__shared__ RingCtl ctl;
 	float* red = reinterpret_cast<float*>(smem_raw);
 	float* xs = red + 32;
-	unsigned char* ring = smem_raw + (((size_t)(32 + xs_floats<DBITS>(a.dim)) * sizeof(float) + 127) & ~(size_t)127);
+	unsigned char* ring = smem_raw + (((size_t)(32 + xs_all_floats<DBITS>(a.dim)) * sizeof(float) + 127) & ~(size_t)127);
 	const size_t rowbytes = (size_t)a.dim * DBITS / 8;
 	const int cpt = (int)(rowbytes / (U * 512));
 	const int t_lo = (int)(((long long)blockIdx.x * a.hidden) / gridDim.x), t_hi = (int)(((long long)(blockIdx.x + 1) * a.hidden) / gridDim.x);
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(256, 2) k_ffn_up_ring(const FfnUpArgs a) {
 	pdl_wait_prev();
 	stamp_begin(a.stamp);
 	post = stage_vector<DBITS>(xs, red, a.x, a.dim, a.normw, a.eps, a.ln != 0, nullptr);
-	rw.consume_all(reinterpret_cast<const float4*>(xs));
+	rw.consume_all(reinterpret_cast<const float4*>(xs), a.dim);
 	stamp_end(a.stamp);
 }
 
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(512, 1) k_matres_ring(const MatResArgs a, cons
 	__shared__ __align__(8) float ypart[2 * RING_MAX_PAIRS]; // tensor parallelism: this rank's partial of the CTA's rows, summed over the ranks at the end
 	float* red = reinterpret_cast<float*>(smem_raw);
 	float* xs = red + 32;
-	unsigned char* ring = smem_raw + (((size_t)(32 + xs_floats<DBITS>(a.n)) * sizeof(float) + 127) & ~(size_t)127);
+	unsigned char* ring = smem_raw + (((size_t)(32 + xs_all_floats<DBITS>(a.n)) * sizeof(float) + 127) & ~(size_t)127);
 	const size_t rowbytes = (size_t)a.n * DBITS / 8;
 	const int cpt = (int)(rowbytes / (U * 512)), nsl = cpt / S;
 	const int npairs = a.d / 2;
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(512, 1) k_matres_ring(const MatResArgs a, cons
 	pdl_wait_prev();
 	stamp_begin(a.stamp);
 	stage_vector<DBITS, 16>(xs, red, a.xin, a.n, nullptr, 0.f, false, nullptr);
-	rw.consume_all(reinterpret_cast<const float4*>(xs));
+	rw.consume_all(reinterpret_cast<const float4*>(xs), a.n);
 	if (a.tpx.world > 1) tp_exchange_rows(a.tpx, ypart, 2 * p_lo, 2 * (p_hi - p_lo), a.y, a.d);
 	stamp_end(a.stamp);
 }

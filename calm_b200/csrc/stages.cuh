@@ -35,8 +35,10 @@ __device__ __forceinline__ void rows_consume(const uint4 (&w)[U][R], int v0, int
 			const float4* xp = xs4 + (size_t)(v >> 5) * Q * 32;
 #pragma unroll
 			for (int q = 0; q < Q; ++q) xv[q] = xp[q * 32 + (lane ^ xs_swz<DBITS>(q))];
+			float4 g3 = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (DBITS == 4) g3 = xs4[(xs_floats<DBITS>(nvec * WFmt<DBITS>::VW) >> 2) + v]; // the vector's group sums (common.cuh xs_aux_floats)
 #pragma unroll
-			for (int r = 0; r < R; ++r) acc[r] = dot_vec<DBITS>(w[u][r], xv, acc[r]);
+			for (int r = 0; r < R; ++r) acc[r] = dot_vec<DBITS>(w[u][r], xv, g3, acc[r]);
 		}
 	}
 }
@@ -140,8 +142,15 @@ __device__ __forceinline__ float stage_vector_batched(float* xs, float* red, con
 			if (xb_out && !rms) reinterpret_cast<float4*>(xb_out)[i] = v[k];
 			*reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = v[k]; // 4 consecutive elements stay consecutive
 		}
+		if (DBITS == 4) { // gf4: 3 * (sum of the group of 8) behind the vector; threads i, i ^ 1 hold the two halves of a group (nthr is even)
+			const float h = i < n4 ? (v[k].x + v[k].y) + (v[k].z + v[k].w) : 0.f;
+			const float o = __shfl_xor_sync(0xffffffffu, h, 1);
+			if (!(i & 1) && i < n4) xs[total4 * 4 + (i >> 1)] = 3.f * (h + o);
+		}
 	}
 	for (int i = n4 + tid; i < total4; i += nthr) *reinterpret_cast<float4*>(xs + xs_index<DBITS>(4 * i)) = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (DBITS == 4)
+		for (int gi = (n4 >> 1) + tid; gi < (total4 >> 1); gi += nthr) xs[total4 * 4 + gi] = 0.f;
 	__syncthreads();
 	if (rms) {
 		const int lane = tid & 31, nwarps = (nthr + 31) >> 5;
@@ -199,6 +208,15 @@ __device__ __forceinline__ float stage_vector(float* xs, float* red, const float
 		xs[xs_index<DBITS>(j)] = v;
 	}
 	__syncthreads();
+	if (DBITS == 4) { // group sums, same association as the batched path
+		for (int gi = tid; gi < (total >> 3); gi += nthr) {
+			float e[8];
+#pragma unroll
+			for (int k = 0; k < 8; ++k) e[k] = xs[xs_index<DBITS>(8 * gi + k)];
+			xs[total + gi] = 3.f * (((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7])));
+		}
+		__syncthreads();
+	}
 	return 1.f;
 }
 
