@@ -78,6 +78,27 @@ __device__ __forceinline__ float attn_cell_wait(const unsigned long long* cell, 
 	return __uint_as_float((unsigned)v);
 }
 
+// two adjacent cells (16-byte aligned) with ONE poll: a slice's (m, l)
+__device__ __forceinline__ void attn_cell_pair_wait(const unsigned long long* cell, unsigned epoch, int* err, float& v0, float& v1) {
+	unsigned long long c0, c1;
+	unsigned spins = 0;
+	unsigned long long t0 = 0;
+	for (;;) {
+		asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "l"(cell) : "memory");
+		if ((unsigned)(c0 >> 32) == epoch && (unsigned)(c1 >> 32) == epoch) break;
+		if ((++spins & 1023) == 0) {
+			const unsigned long long now = globaltimer_ns();
+			if (!t0) t0 = now;
+			if (now - t0 > 5000000000ull) {
+				if (err) *reinterpret_cast<volatile int*>(err) = 9201;
+				__threadfence_system();
+				__trap();
+			}
+		}
+	}
+	v0 = __uint_as_float((unsigned)c0), v1 = __uint_as_float((unsigned)c1);
+}
+
 template <typename KVT, int HG, int LPP, bool CLUSTER>
 __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 	typedef typename KvRaw<KVT>::type raw_t;
@@ -341,8 +362,8 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 		for (int i = tid; i < nsplit * HG; i += ATTN_THREADS) {
 			const int s = i / HG, h = i % HG;
 			const unsigned long long* c = cells + (size_t)s * HG * REC + h * REC + HD;
-			mls[s][h][0] = s == split ? myrec[h * REC + HD] : attn_cell_wait(c, epoch, a.err);
-			mls[s][h][1] = s == split ? myrec[h * REC + HD + 1] : attn_cell_wait(c + 1, epoch, a.err);
+			if (s == split) mls[s][h][0] = myrec[h * REC + HD], mls[s][h][1] = myrec[h * REC + HD + 1];
+			else attn_cell_pair_wait(c, epoch, a.err, mls[s][h][0], mls[s][h][1]); // (REC and HD are even: the pair is 16-byte aligned)
 		}
 		__syncthreads();
 		__shared__ float cfs[ATTN2_MAXB + 4][HG]; // exp(m_s - M): one exponential per (slice, head), in parallel
@@ -369,9 +390,26 @@ __global__ void __launch_bounds__(ATTN_THREADS) k_attn2(const AttnArgs a) {
 			float v = 0.f;
 			if (o < o_end) {
 				const int h = o / HD, e = o % HD;
-				for (int s = sg; s < nsplit; s += 8) {
-					const float x = s == split ? myrec[h * REC + e] : attn_cell_wait(cells + (size_t)s * HG * REC + h * REC + e, epoch, a.err);
-					v = fmaf(x, mls[s][h][0], v);
+				// all of this lane's cells are requested before the first is looked at (their slices' (m, l) have been seen: they are
+				// almost always there) -- one L2 round trip instead of one per slice; a cell that is not there yet is polled as before
+				constexpr int NS8 = (ATTN2_MAXB + 4 + 7) / 8;
+				unsigned long long c[NS8];
+#pragma unroll
+				for (int k = 0; k < NS8; ++k) {
+					const int s = sg + 8 * k;
+					c[k] = 0;
+					if (s < nsplit && s != split) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(c[k]) : "l"(cells + (size_t)s * HG * REC + h * REC + e) : "memory");
+				}
+#pragma unroll
+				for (int k = 0; k < NS8; ++k) {
+					const int s = sg + 8 * k;
+					if (s < nsplit) {
+						float x;
+						if (s == split) x = myrec[h * REC + e];
+						else if ((unsigned)(c[k] >> 32) == epoch) x = __uint_as_float((unsigned)c[k]);
+						else x = attn_cell_wait(cells + (size_t)s * HG * REC + h * REC + e, epoch, a.err);
+						v = fmaf(x, mls[s][h][0], v); // slice order per lane: deterministic
+					}
 				}
 			}
 			v += __shfl_xor_sync(0xffffffffu, v, 1), v += __shfl_xor_sync(0xffffffffu, v, 2), v += __shfl_xor_sync(0xffffffffu, v, 4);
