@@ -1,11 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-set -x
-timeout 600 python -m pytest tests -q -m gpu -x -k "golden or long_context or fp8_kv or rolling or kv_only or greedy or full_size" 2>&1 | grep -v "^# CUDA" | tail -5
-timeout 300 python tools/sweep.py --steps 64 --set base --set base > gpurun_out/sweep_attn_batched_fold.jsonl 2> gpurun_out/sweep.err
+timeout 600 python bench.py > gpurun_out/bench_final3.jsonl 2> gpurun_out/bench_final3.err; cut -c1-300 gpurun_out/bench_final3.jsonl; tail -2 gpurun_out/bench_final3.err
 python - <<'PY'
 import json
-for l in open('gpurun_out/sweep_attn_batched_fold.jsonl'):
-    r=json.loads(l); print(r['cfg'], r['ms_per_token'], r['us_per_launch'], r['attn_dbg_ns'])
+r=json.loads(open('gpurun_out/bench_final3.jsonl').read().strip().splitlines()[-1])
+print(r['value'], r['e2e'], r['prefill'], r['ref_cuda'], r['frac_of_peak_whole_token'])
 PY
-tail -3 gpurun_out/sweep.err
