@@ -111,8 +111,8 @@ def test_fp8_kv_cache_teacher_forced_vs_oracle(oracle_pkg, name):
 
 @pytest.mark.parametrize("dtype", ["gf4", "fp8", "fp16"])
 def test_ring_fed_kernels_vs_oracle(oracle_pkg, dtype):
-    """Shapes the ring-fed stage kernels serve (rows of whole 1 KB / 256-byte chunks: ring.cuh, and for gf4 the tensor-core
-    ring kernels of ring_gf4.cuh with K-slices folded in shared memory) against the CPU oracle, teacher-forced."""
+    """Shapes the ring-fed stage kernels of ring.cuh serve (rows of whole 1 KB / 2 KB chunks, K-slices folded in shared memory;
+    for gf4 with the staged group sums) against the CPU oracle, teacher-forced."""
     spec = replace(mg.SPECS["pf-tiny-hd128"], name="ring-" + dtype, dtype=dtype, dim=2048, hidden_dim=4096, n_heads=8, n_kv_heads=2, n_layers=2)
     toks = mg.teacher_tokens(spec.vocab_size, 20)
     host = mg.HostModel(spec, seed=7)
