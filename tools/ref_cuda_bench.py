@@ -43,14 +43,13 @@ for binary in ("run_ref", "run_b200"):
         env.pop("CALM_CPU", None)
         if poso:
             env["CALM_POSO"] = poso
-        if True:
-            r = subprocess.run([exe, path, "-n", str(n), "-t", "0", "-i", "<|t5|>"], capture_output=True, text=True, env=env, timeout=600)
-            m = re.search(r"throughput: ([0-9.]+) tok/s; latency: ([0-9.]+) ms/tok; bandwidth: ([0-9.]+) GB/s.*#([0-9a-f]+)", r.stderr)
-            key = f"{binary} {label}"
-            if m:
-                out[key] = {"tok_s": float(m.group(1)), "ms_tok": float(m.group(2)), "gbs": float(m.group(3)), "hash": m.group(4)}
-                print(f"{key:34s} {m.group(1):>8s} tok/s  {m.group(2):>7s} ms/tok  {m.group(3):>8s} GB/s  #{m.group(4)}  tokens: {r.stdout.strip()[:60]}", flush=True)
-            else:
-                print(f"{key}: rc={r.returncode} stderr tail: {r.stderr[-300:]}", flush=True)
+        r = subprocess.run([exe, path, "-n", str(n), "-t", "0", "-i", "<|t5|>"], capture_output=True, text=True, env=env, timeout=600)
+        m = re.search(r"throughput: ([0-9.]+) tok/s; latency: ([0-9.]+) ms/tok; bandwidth: ([0-9.]+) GB/s.*#([0-9a-f]+)", r.stderr)
+        key = f"{binary} {label}"
+        if m:
+            out[key] = {"tok_s": float(m.group(1)), "ms_tok": float(m.group(2)), "gbs": float(m.group(3)), "hash": m.group(4)}
+            print(f"{key:34s} {m.group(1):>8s} tok/s  {m.group(2):>7s} ms/tok  {m.group(3):>8s} GB/s  #{m.group(4)}  tokens: {r.stdout.strip()[:60]}", flush=True)
+        else:
+            print(f"{key}: rc={r.returncode} stderr tail: {r.stderr[-300:]}", flush=True)
 os.remove(path)
 print(json.dumps(out))
